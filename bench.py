@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""Benchmark of the YOLO detection-head hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Metric (BASELINE.json): YOLO head images/sec for decode + target assignment + loss + backward
+(one fused launch) + confidence threshold + NMS (one launch), on the configuration the
+north-star target is quoted on: YOLOv2 13x13 grid, 5 anchors, C=20, batch 256 per GPU, synthetic
+VOC-shaped data.  One "step" = one train-head call + one post-process call over one batch.
+
+  value      device-timed throughput, inputs resident in HBM, CUDA-graph replay over rotating
+             buffer sets larger than L2, max over ranks
+  e2e        same step through the host-buffer entry point (pinned host memory -> H2D -> kernels
+             -> D2H of loss, dL/dy and detections), wall clock between device synchronisations
+  roofline   the fused train-head kernel alone: algorithmic bytes / launch duration vs measured HBM
+  cpu_baseline  the CPU port of the reference's torch path (oracle/), bounded sample, rank 0
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = "yolo_head_images_per_sec"
+UNIT = "images/s"
+CONF_THRE, IOU_THRE = 0.5, 0.45
+MAX_OUT = 128
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, only if MEASURED_PEAKS.json is absent
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--sets", type=int, default=8, help="rotating buffer sets (total must exceed L2)")
+    ap.add_argument("--cpu-sample", type=int, default=32, help="images in the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 200)")
+    return ap.parse_args()
+
+
+def workload_config(batch, sets=None):
+    cfg = {
+        "workload": "yolov2_head_13x13x5_c20_b%d_train(decode+assign+loss+bwd)+postprocess(conf%.2f,nms_iou%.2f)"
+                    % (batch, CONF_THRE, IOU_THRE),
+        "batch_per_gpu": batch, "grid": [13, 13], "anchors": 5, "classes": 20, "image": [416, 416],
+        "gt_boxes_per_image": "U{1..5}", "candidates_per_image": "~50 of 845",
+    }
+    if sets is not None:
+        cfg["l2"] = "%d rotating input/output buffer sets per GPU (inputs+outputs %.0f MB > 126 MB L2)" % (
+            sets, sets * 2 * batch * 84500 / 1e6)
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------
+# CPU port of the reference path (oracle/) -- the baseline arm
+# ------------------------------------------------------------------------------------------
+def cpu_port_step(case, lambdas):
+    """One pass of the reference's torch-CPU algorithm over `case`: get_loss + backward
+    (dense per-box replication, autograd) and the per-image detect/NMS loop."""
+    from oracle import yolo_head_oracle as O
+    O.train_head_dense(case, lambdas)
+    O.postprocess_torch(case.y, case.height, case.width, case.version, case.anchors, CONF_THRE, IOU_THRE)
+
+
+def time_cpu_port(sample, reps, warm):
+    from odcp_b200 import synthetic
+    torch.set_num_threads(os.cpu_count() or 1)
+    case = synthetic.headline(n=sample)
+    for _ in range(warm):
+        cpu_port_step(case, synthetic.DEFAULT_LAMBDAS)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        cpu_port_step(case, synthetic.DEFAULT_LAMBDAS)
+        ts.append(time.perf_counter() - t0)
+    return case, ts
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  /root/reference does
+    not exist on the GPU box and the reference is torch-eager Python (nothing to compile), so this
+    arm times the oracle's torch-CPU port of it (same ops in the same order, pinned bit-exact
+    against the reference's outputs in tests/golden/) with all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = args.cpu_sample
+    steps = max(1, min(args.steps, 20))
+    warm = max(1, min(args.warmup, 2))
+    case, ts = time_cpu_port(sample, steps, warm)
+    total = float(np.sum(ts))
+    value = sample * len(ts) / total
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": len(ts), "warmup": warm, "ms_per_step": 1e3 * total / len(ts), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.batch),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d-image sample of the batch-%d workload per step (the reference's per-box "
+                                   "replication grows as M*S*S*A); torch %s CPU, %d threads, os.cpu_count()=%s"
+                                   % (sample, args.batch, torch.__version__, cores, os.cpu_count())},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting"}
+
+    def __init__(self, index, period=0.002):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.sm_max = None
+        self._stop = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                bits = int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for b, name in self.REASONS.items():
+                    if bits & b:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop.set()
+        if self.is_alive():
+            self.join()
+
+    def summary(self, window):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": [], "samples": 0,
+                    "note": getattr(self, "err", "no samples")}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.samples), "window": window}
+
+
+def nvml_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except (ValueError, IndexError):
+            pass
+    return local_rank
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    from odcp_b200 import ops, synthetic, targets
+    from odcp_b200.host import HostHeadPipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    K, W, R, B = args.steps, max(args.warmup, 3), args.sets, args.batch
+    lam = synthetic.DEFAULT_LAMBDAS
+    case = synthetic.headline(n=B)
+    assert synthetic.distinct_scores(case.y, 2, case.a)
+    kw = dict(version=2, img_hw=(case.height, case.width), anchors=case.anchors)
+    m_local = case.m
+    m_global = m_local * world  # every rank holds a shard with the same box count (weak scaling)
+
+    # rotating buffer sets: distinct addresses, > L2 in total
+    gt = targets.records_to_tensor(case.rec, dev)
+    off = torch.from_numpy(case.gt_off).to(dev)
+    y0 = case.y.to(dev)
+    sets = []
+    for i in range(R):
+        s = dict(y=y0.clone(), gt=gt.clone(), off=off.clone(),
+                 out=dict(dy=torch.empty_like(y0), loss=torch.empty((), device=dev), terms=torch.empty(5, device=dev)))
+        sets.append(s)
+
+    stream = torch.cuda.Stream(dev)
+
+    def step(s, post=True, train=True):
+        if train:
+            ops.train_head(s["y"], s["gt"], s["off"], lambdas=lam, m_global=m_global, out=s["out"], **kw)
+        if post:
+            s["post"] = ops.postprocess(s["y"], conf_thre=CONF_THRE, iou_thre=IOU_THRE, max_out=MAX_OUT,
+                                        want_cls_spec=False, out=s.get("post"), **kw)
+
+    def capture(fn):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            fn()
+        return g
+
+    with torch.cuda.stream(stream):
+        for s in sets:  # eager warm-up: allocates outputs/workspaces before any capture
+            step(s)
+        stream.synchronize()
+        g_full = capture(lambda: [step(s) for s in sets])
+        g_one = [capture(lambda s=s: step(s)) for s in sets[: max(K % R, W % R, 1)]] if (K % R or W % R) else []
+        g_train = capture(lambda: [step(s, post=False) for s in sets])
+        g_post = capture(lambda: [step(s, train=False) for s in sets])
+
+        def run_steps(n):
+            for _ in range(n // R):
+                g_full.replay()
+            for i in range(n % R):
+                g_one[i].replay()
+
+        def barrier():
+            if dist is not None:
+                dist.barrier()
+
+        run_steps(W)
+        stream.synchronize()
+
+        # ---- timed region: exactly K steps, device time, max over ranks
+        sampler = ClockSampler(nvml_index(local_rank))
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        torch.cuda.synchronize()
+        sampler.start()
+        ev0.record(stream)
+        run_steps(K)
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        window = "timed region"
+        if len(sampler.samples) < 5:  # the timed region was too short to sample: keep the same load on
+            t_end = time.perf_counter() + 0.25
+            while time.perf_counter() < t_end:
+                g_full.replay()
+            stream.synchronize()
+            window = "timed region + 0.25 s of the same graph replayed right after it"
+        sampler.stop()
+        if dist is not None:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            # the only data-path exchange: the scalar loss terms (6 floats per step), reduced in a batch
+            terms = torch.stack([torch.cat([s["out"]["terms"], s["out"]["loss"].reshape(1)]) for s in sets])
+            dist.all_reduce(terms)
+        loss_value = float(sets[0]["out"]["loss"].item())
+
+        # ---- per-kernel durations (train head alone / post-process alone), same rotation
+        def time_graph(g, reps):
+            for _ in range(3):
+                g.replay()
+            stream.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(reps):
+                g.replay()
+            b.record(stream)
+            stream.synchronize()
+            return a.elapsed_time(b) / (reps * R)
+
+        reps = max(10, min(K // R, 500))
+        train_ms = time_graph(g_train, reps)
+        post_ms = time_graph(g_post, reps)
+
+    images = B * world
+    value = images * K / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (fused train head)
+    kept = sets[0]["post"]["keep_cnt"].clamp(max=MAX_OUT).sum().item()
+    p_bytes = case.image_bytes
+    train_bytes = 2 * p_bytes * B + 48 * m_local
+    post_bytes = p_bytes * B + 28 * kept
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+    achieved = train_bytes / (train_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "yh_train_kernel (fused decode+assign+loss+dL/dy)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": train_bytes,
+                "us_per_launch": train_ms * 1e3,
+                "postprocess_kernel": {"us_per_launch": post_ms * 1e3, "algorithmic_bytes_per_launch": post_bytes,
+                                       "achieved": post_bytes / (post_ms * 1e-3) / 1e9,
+                                       "frac": post_bytes / (post_ms * 1e-3) / 1e9 / peak},
+                "step": {"algorithmic_bytes": train_bytes + post_bytes,
+                         "frac": (train_bytes + post_bytes) / (ms / K * 1e-3) / 1e9 / peak}}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get("yh_train_kernel_dram_bytes_per_launch")
+        except Exception:  # noqa: BLE001
+            pass
+
+    # ---- e2e: host buffers in, host buffers out
+    e2e = None
+    if not args.no_e2e:
+        ke = args.e2e_steps or max(20, min(K, 200))
+        pipe = HostHeadPipeline(B, case.s_h, case.s_w, case.a, case.c, img_hw=(case.height, case.width),
+                                anchors=case.anchors, lambdas=lam, conf_thre=CONF_THRE, iou_thre=IOU_THRE,
+                                max_out=MAX_OUT, max_boxes=m_local, depth=3, device=dev)
+        gt_h = targets.records_to_tensor(case.rec)
+        off_h = torch.from_numpy(case.gt_off)
+        for d in range(pipe.depth):  # fill every slot's pinned staging buffers once (the "producer")
+            hy, hg, ho = pipe.pinned_inputs(d)
+            hy.copy_(case.y)
+            hg[:m_local].copy_(gt_h)
+            ho.copy_(off_h)
+
+        def run_e2e(n):
+            last = None
+            for i in range(n):
+                if i >= pipe.depth:
+                    last = pipe.result(t0 + i - pipe.depth)
+                pipe.submit(None, gt_h, None, m_global=m_global, staged=True)
+            for i in range(max(0, n - pipe.depth), n):
+                last = pipe.result(t0 + i)
+            return last
+
+        t0 = pipe._ticket
+        run_e2e(max(3, pipe.depth))
+        torch.cuda.synchronize()
+        barrier()
+        t0 = pipe._ticket
+        tic = time.perf_counter()
+        res = run_e2e(ke)
+        torch.cuda.synchronize()
+        toc = time.perf_counter()
+        e2e_s = toc - tic
+        if dist is not None:
+            t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        assert abs(float(res["loss"]) - loss_value) <= 1e-6 * abs(loss_value), (float(res["loss"]), loss_value)
+        e2e = {"value": images * ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes(m_local),
+               "d2h_bytes_per_step": pipe.d2h_bytes(), "steps": ke, "ms_per_step": 1e3 * e2e_s / ke,
+               "path": "HostHeadPipeline: pinned host y+GT -> H2D -> yh_v2_train + yh_v2_postprocess -> D2H loss, "
+                       "dL/dy, kept boxes; 3 slots, copy/compute streams overlapped"}
+
+    # ---- CPU baseline (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sample = args.cpu_sample
+        _, ts = time_cpu_port(sample, reps=5, warm=1)
+        cpu = {"value": sample / float(np.min(ts)), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "%d-image sample of the same workload, best of 5 after 1 warm-up (%.2f s of CPU work); "
+                         "oracle/ torch-CPU port of get_loss+backward and the per-image nms loop; "
+                         "os.cpu_count()=%s" % (sample, float(np.sum(ts)), os.cpu_count())}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(B, R),
+            "clocks": sampler.summary(window), "e2e": e2e, "gpu_launches": 2 * K,
+            "roofline": roofline, "cpu_baseline": cpu, "loss": loss_value,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,162 @@
+// Shared device/host helpers for libyolohead (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "yolohead.h"
+
+#ifndef __CUDA_ARCH__
+#define YH_HOST_ONLY 1
+#endif
+
+// ------------------------------------------------------------------------------------------
+// host-side error plumbing (thread-local message, never throws)
+// ------------------------------------------------------------------------------------------
+void yh_set_error(const char* fmt, ...);
+int yh_check_cuda(cudaError_t e, const char* what);
+int yh_sm_count();  // SM count of the current device (cached per device)
+
+#define YH_REQUIRE(cond, code, ...)            \
+    do {                                       \
+        if (!(cond)) {                         \
+            yh_set_error(__VA_ARGS__);         \
+            return (code);                     \
+        }                                      \
+    } while (0)
+
+// Geometry of a head tensor, passed by value to every kernel.
+struct YhGeom {
+    int version;      // 1 or 2
+    int n, s_h, s_w;  // images, grid
+    int a, c;         // anchors (v2) / boxes per cell (v1), classes
+    int cells;        // s_h * s_w
+    int cell_floats;  // v2: a*(5+c); v1: 5*a+c
+    int box_stride;   // floats between consecutive boxes of a cell: v2 5+c, v1 5
+    int preds;        // cells * a   (predictors per image)
+    float gw, gh;     // pixels per grid cell: float(double(W)/S_w), float(double(H)/S_h)
+    float pw[YH_MAX_ANCHORS];  // v2 anchor priors; v1: float(S_w) for every box
+    float ph[YH_MAX_ANCHORS];  //                   v1: float(S_h)
+};
+
+int yh_make_geom(YhGeom* g, int version, int n, int s_h, int s_w, int a, int c,
+                 const float* anchors_wh_host, float img_h, float img_w);
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// --- arithmetic with the reference's rounding: every torch elementwise op rounds once, so the
+// decision path (decode -> corners -> IoU) uses explicit round-to-nearest intrinsics, which
+// nvcc never contracts into FMAs.
+__device__ __forceinline__ float yh_sigmoid(float x) {
+    // torch.sigmoid: 1 / (1 + exp(-x))
+    return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+}
+
+struct YhBox {
+    float x1, y1, x2, y2;
+};
+
+// Box decode, reference models/yolov2.py:488-595 / models/yolov1.py:275-382.
+// wa/ha are the activated sizes (v2: exp(t), v1: sigmoid(t)); pw/ph the multipliers.
+__device__ __forceinline__ YhBox yh_decode_box(float sx, float sy, float wa, float ha, float pw,
+                                               float ph, int cx, int cy, float gw, float gh) {
+    const float bw = __fmul_rn(pw, wa);
+    const float bh = __fmul_rn(ph, ha);
+    const float bx = __fadd_rn(sx, (float)cx);
+    const float by = __fadd_rn(sy, (float)cy);
+    const float hw = __fdiv_rn(bw, 2.0f);
+    const float hh = __fdiv_rn(bh, 2.0f);
+    YhBox b;
+    b.x1 = __fmul_rn(__fsub_rn(bx, hw), gw);
+    b.y1 = __fmul_rn(__fsub_rn(by, hh), gh);
+    b.x2 = __fmul_rn(__fadd_rn(bx, hw), gw);
+    b.y2 = __fmul_rn(__fadd_rn(by, hh), gh);
+    return b;
+}
+
+// IoU, reference models/utils.py:47-63: inter / (union + 1e-6), first box = coord1.
+__device__ __forceinline__ float yh_iou_xyxy(const YhBox& p, const YhBox& q) {
+    const float iw = fmaxf(__fsub_rn(fminf(p.x2, q.x2), fmaxf(p.x1, q.x1)), 0.0f);
+    const float ih = fmaxf(__fsub_rn(fminf(p.y2, q.y2), fmaxf(p.y1, q.y1)), 0.0f);
+    const float inter = __fmul_rn(iw, ih);
+    const float a1 = __fmul_rn(__fsub_rn(p.x2, p.x1), __fsub_rn(p.y2, p.y1));
+    const float a2 = __fmul_rn(__fsub_rn(q.x2, q.x1), __fsub_rn(q.y2, q.y1));
+    const float uni = __fsub_rn(__fadd_rn(a1, a2), inter);
+    return __fdiv_rn(inter, __fadd_rn(uni, 1e-6f));
+}
+
+__device__ __forceinline__ float yh_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float yh_warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// --- mbarrier + 1-D TMA bulk copies (cp.async.bulk; SASS: UBLKCP) ---------------------------
+__device__ __forceinline__ uint32_t yh_smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void yh_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(yh_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void yh_mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void yh_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(yh_smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void yh_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "YH_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra YH_DONE_%=;\n\t"
+        "bra YH_WAIT_%=;\n\t"
+        "YH_DONE_%=:\n\t"
+        "}" ::"r"(yh_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared, completion signalled on `bar` (bytes: multiple of 16, both 16-B aligned)
+__device__ __forceinline__ void yh_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes,
+                                             uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(yh_smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(yh_smem_u32(bar))
+        : "memory");
+}
+// shared -> global, tracked by the thread's bulk async-group
+__device__ __forceinline__ void yh_bulk_store(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                 "r"(yh_smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void yh_bulk_commit() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void yh_bulk_wait_read() {  // <= N groups still reading smem
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void yh_bulk_wait_all() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+// make generic-proxy shared-memory writes visible to the async proxy (before a bulk store)
+__device__ __forceinline__ void yh_fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+#endif  // __CUDACC__

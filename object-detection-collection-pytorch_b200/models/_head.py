@@ -1,0 +1,148 @@
+"""Shared implementation of predict / get_loss / detect on the CUDA kernels."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import ops
+
+LAMBDA_KEYS = ops.LAMBDA_KEYS
+
+
+class HeadLoss(torch.autograd.Function):
+    """loss = fused train head(y, compact targets); backward hands out the dL/dy the same
+    kernel already produced, scaled by the upstream gradient on the device (no host sync)."""
+
+    @staticmethod
+    def forward(ctx, y, gt, gt_off, cfg):
+        want_grad = bool(ctx.needs_input_grad[0])
+        r = ops.train_head(y.detach(), gt, gt_off, want_grad=want_grad, want_resp=cfg.get("want_resp", False),
+                           **{k: cfg[k] for k in ("version", "img_hw", "lambdas", "anchors", "boxes_per_cell", "m_global")})
+        ctx.dy = r["dy"]
+        ctx.prev_scale = None
+        cfg["last"] = r
+        ctx.mark_non_differentiable(r["terms"])
+        return r["loss"], r["terms"]
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_terms):
+        dy = ctx.dy
+        if dy is None:
+            raise RuntimeError("get_loss was evaluated without gradients")
+        g = grad_loss.to(device=dy.device, dtype=torch.float32).reshape(())
+        scale = g if ctx.prev_scale is None else g / ctx.prev_scale  # repeated backward(retain_graph)
+        ops.scale_inplace(dy, scale.contiguous())
+        ctx.prev_scale = g
+        return dy, None, None, None
+
+
+class HeadOps:
+    """Mixin: needs `self(x_batch)` -> head tensor, `self._yh_version`, `self.num_anchor_box`,
+    `self.num_cls`, `self.cls_list` and (v2) `self.anchor_box_size_list`."""
+
+    _yh_version = 2
+
+    # -- helpers -----------------------------------------------------------------------------
+    def _yh_anchors(self):
+        return tuple(self.anchor_box_size_list) if self._yh_version == 2 else None
+
+    def _yh_kwargs(self, x_batch):
+        h, w = int(x_batch.shape[1]), int(x_batch.shape[2])
+        return dict(version=self._yh_version, img_hw=(h, w), anchors=self._yh_anchors(),
+                    boxes_per_cell=int(self.num_anchor_box))
+
+    # -- predict -----------------------------------------------------------------------------
+    def predict(self, x_batch):
+        """The reference's six outputs (models/yolov2.py:433-649, models/yolov1.py:207-437):
+        (sig_txty, exp_twth | sig_twth, bbox_xyxy_px, conf, cls_prob, cls_spec_conf).
+        They carry no autograd graph: training goes through get_loss, whose backward is fused."""
+        y = self(x_batch)
+        return ops.decode(y.detach(), **self._yh_kwargs(x_batch))
+
+    # -- loss --------------------------------------------------------------------------------
+    def get_loss(self, x_batch, sig_txty_tgt_batch, wh_tgt_batch, bbox_coord_tgt_batch, cls_tgt_batch,
+                 obj_mask_batch, x_img_id_batch, bbox_img_id_batch, lambda_xy, lambda_wh, lambda_conf,
+                 lambda_noobj, lambda_cls):
+        """Reference signature (models/yolov2.py:747-762, models/yolov1.py:556-571): dense per-box
+        target grids in, 0-dim fp32 loss with a working .backward() out."""
+        y = self(x_batch)
+        dev = y.device
+        gt, gt_off, status = ops.compact_targets(
+            sig_txty_tgt_batch.to(dev), wh_tgt_batch.to(dev), bbox_coord_tgt_batch.to(dev),
+            cls_tgt_batch.to(dev), obj_mask_batch.to(dev), x_img_id_batch, bbox_img_id_batch)
+        self._yh_target_status = status  # device int32[2]: malformed obj_mask rows, non-one-hot class rows
+        lam = dict(zip(LAMBDA_KEYS, (lambda_xy, lambda_wh, lambda_conf, lambda_noobj, lambda_cls)))
+        return self.get_loss_compact(x_batch, gt, gt_off, y=y, **lam)
+
+    def get_loss_compact(self, x_batch, gt, gt_off, *, y=None, m_global=None, want_resp=False,
+                         lambda_xy=5.0, lambda_wh=5.0, lambda_conf=1.0, lambda_noobj=0.5, lambda_cls=1.0):
+        """Fast path: compact ground-truth records (targets.py) instead of dense grids.
+        `m_global` is the box count the means are taken over when the batch is sharded."""
+        if y is None:
+            y = self(x_batch)
+        cfg = self._yh_kwargs(x_batch)
+        cfg.update(lambdas=(lambda_xy, lambda_wh, lambda_conf, lambda_noobj, lambda_cls),
+                   m_global=m_global, want_resp=want_resp)
+        if not y.is_contiguous():
+            y = y.contiguous()
+        loss, terms = HeadLoss.apply(y, gt, gt_off, cfg)
+        self._yh_last = dict(terms=terms, **{k: cfg["last"][k] for k in ("resp", "iou_resp")})
+        return loss
+
+    # -- detect ------------------------------------------------------------------------------
+    def _yh_image_batch(self, img):
+        dev = next(self.parameters(), torch.empty(0, device="cuda")).device
+        if dev.type != "cuda":
+            raise RuntimeError("the model must live on a CUDA device (no CPU path)")
+        return torch.as_tensor(np.asarray([img]), device=dev)
+
+    def postprocess(self, x_batch, conf_score_thre=0.9, iou_thre=0.5, class_aware=False, max_out=None):
+        """Batched decode + threshold + per-image NMS + class pick, everything on the device."""
+        y = self(x_batch)
+        return ops.postprocess(y.detach(), conf_thre=conf_score_thre, iou_thre=iou_thre,
+                               class_aware=class_aware, max_out=max_out, **self._yh_kwargs(x_batch))
+
+    def _yh_annot(self, r, n, box_fn=None):
+        k = min(int(r["keep_cnt"][n].item()), r["keep_idx"].shape[1])
+        bbox = r["bbox"][n, :k].cpu().numpy()
+        if box_fn is not None:
+            bbox = box_fn(bbox)
+        return {
+            "bbox_list": bbox.tolist(),
+            "lbl_list": [self.cls_list[i] for i in r["label"][n, :k].cpu().tolist()],
+            "conf_score_list": r["conf"][n, :k].cpu().numpy().tolist(),
+            "cls_spec_conf_score_list": r["score"][n, :k].cpu().numpy().tolist(),
+        }
+
+    def detect(self, img, conf_score_thre=0.9, iou_thre=0.5):
+        """One image -> dict of python lists (reference models/yolov2.py:651-745)."""
+        self.eval()
+        with torch.no_grad():
+            r = self.postprocess(self._yh_image_batch(img), conf_score_thre, iou_thre)
+        return self._yh_annot(r, 0)
+
+    def detect_batch(self, x_batch, conf_score_thre=0.9, iou_thre=0.5, class_aware=False):
+        """Batched detect: one launch for all images, list of per-image dicts."""
+        self.eval()
+        with torch.no_grad():
+            r = self.postprocess(x_batch, conf_score_thre, iou_thre, class_aware=class_aware)
+        return [self._yh_annot(r, n) for n in range(x_batch.shape[0])]
+
+
+class InjectedHead(torch.nn.Module):
+    """A module whose forward returns a head tensor handed in beforehand: the conv backbone is
+    out of scope of this package, tests and the bench drive the head path with synthetic head
+    tensors through this class."""
+
+    def __init__(self):
+        super().__init__()
+        self._y = None
+
+    def set_head_output(self, y):
+        self._y = y
+        return self
+
+    def forward(self, x_batch):
+        if self._y is None:
+            raise RuntimeError("set_head_output(y) first")
+        return self._y

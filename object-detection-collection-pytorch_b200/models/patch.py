@@ -1,0 +1,40 @@
+"""Install the CUDA head path on the reference's own classes.
+
+    import models.yolov1, models.yolov2, models.utils      # the reference, unmodified
+    from odcp_b200.models import patch_reference
+    patch_reference(models.yolov1, models.yolov2, models.utils)
+
+After this, `train.py` constructs `YOLOv1/YOLOv2` exactly as before (same constructor, same
+parameters and state_dict keys) and `run_one_epoch` / `evaluate_model` reach the kernels through
+the unchanged `get_loss` / `detect` / `nms` / `get_iou` calls.
+"""
+from __future__ import annotations
+
+_METHODS = ("predict", "get_loss", "get_loss_compact", "detect", "detect_batch", "postprocess",
+            "_yh_anchors", "_yh_kwargs", "_yh_image_batch", "_yh_annot")
+
+
+def patch_reference(ref_yolov1=None, ref_yolov2=None, ref_utils=None):
+    from . import utils as u
+    from .yolov1 import YOLOv1HeadOps
+    from .yolov2 import YOLOv2HeadOps
+    done = []
+    for mod, cls_name, ops_cls in ((ref_yolov1, "YOLOv1", YOLOv1HeadOps), (ref_yolov2, "YOLOv2", YOLOv2HeadOps)):
+        if mod is None:
+            continue
+        cls = getattr(mod, cls_name)
+        for name in _METHODS:
+            for klass in ops_cls.__mro__:
+                if name in klass.__dict__:
+                    setattr(cls, name, klass.__dict__[name])
+                    break
+        cls._yh_version = ops_cls._yh_version
+        # the module-level names the reference's methods resolve at call time
+        mod.nms = u.nms
+        mod.get_iou = u.get_iou
+        done.append(cls_name)
+    if ref_utils is not None:
+        ref_utils.nms = u.nms
+        ref_utils.get_iou = u.get_iou
+        done.append("utils")
+    return done

@@ -1,0 +1,261 @@
+"""Tensor-level wrappers over the C ABI (include/yolohead.h).
+
+torch is used here only for device memory and streams: every function takes CUDA tensors,
+hands their raw pointers and the current stream to libyolohead, and returns CUDA tensors.
+Nothing here computes on the CPU and nothing falls back when the library is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+LAMBDA_KEYS = ("lambda_xy", "lambda_wh", "lambda_conf", "lambda_noobj", "lambda_cls")
+
+_ws_cache = {}
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda_f32(t, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise ValueError("%s must be a CUDA tensor (this path has no CPU implementation)" % name)
+    if t.dtype != torch.float32:
+        raise ValueError("%s must be float32, got %s" % (name, t.dtype))
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _host_floats(values):
+    arr = (C.c_float * len(values))(*[float(v) for v in values])
+    return arr
+
+
+def _anchors_host(anchors):
+    flat = [float(v) for wh in anchors for v in wh]
+    return _host_floats(flat)
+
+
+def _train_workspace(device):
+    """Zero-initialised scratch, one per (device, stream): the kernels keep it zeroed."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None:
+        nbytes = int(_lib.load().yh_train_workspace_bytes())
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def head_shape(y, version, a=None):
+    """(n, s_h, s_w, a, c) from a head tensor."""
+    if version == 2:
+        if y.dim() != 5:
+            raise ValueError("YOLOv2 head tensor must be [N,S_h,S_w,A,5+C], got %s" % (tuple(y.shape),))
+        n, s_h, s_w, a_, d = y.shape
+        return n, s_h, s_w, a_, d - 5
+    if y.dim() != 4 or a is None:
+        raise ValueError("YOLOv1 head tensor must be [N,S_h,S_w,5B+C] with B given, got %s" % (tuple(y.shape),))
+    n, s_h, s_w, d = y.shape
+    return n, s_h, s_w, a, d - 5 * a
+
+
+def train_head(y, gt, gt_off, *, version, img_hw, lambdas, anchors=None, boxes_per_cell=None,
+               m_global=None, want_grad=True, want_resp=False, out=None):
+    """Fused decode + assignment + loss (+ dL/dy) -- yh_v2_train / yh_v1_train.
+
+    y       head tensor (CUDA fp32), gt int32 [M,12] records sorted by image (targets.py),
+    gt_off  int32 [N+1] CSR offsets, img_hw (H, W) of the network input,
+    lambdas dict with the five reference weights or a sequence of five floats.
+    Returns dict(loss 0-dim, terms[5], dy or None, resp/iou_resp or None).
+    """
+    y = _require_cuda_f32(y, "y")
+    n, s_h, s_w, a, c = head_shape(y, version, boxes_per_cell)
+    dev = y.device
+    if gt.device != dev or gt_off.device != dev:
+        raise ValueError("gt / gt_off must live on the same device as y")
+    if gt.dtype != torch.int32 or gt.dim() != 2 or gt.shape[1] != 12 or not gt.is_contiguous():
+        raise ValueError("gt must be a contiguous int32 [M,12] record tensor")
+    if gt_off.dtype != torch.int32 or gt_off.numel() != n + 1 or not gt_off.is_contiguous():
+        raise ValueError("gt_off must be a contiguous int32 [N+1] tensor")
+    m_local = int(gt.shape[0])
+    m_glob = m_local if m_global is None else int(m_global)
+    lam = [lambdas[k] for k in LAMBDA_KEYS] if isinstance(lambdas, dict) else list(lambdas)
+    out = out or {}
+    with torch.cuda.device(dev):
+        ws = _train_workspace(dev)
+        dy = out.get("dy") if want_grad else None
+        if want_grad and dy is None:
+            dy = torch.empty_like(y)
+        terms = out.get("terms")
+        if terms is None:
+            terms = torch.empty(5, dtype=torch.float32, device=dev)
+        loss = out.get("loss")
+        if loss is None:
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+        resp = iou_resp = None
+        if want_resp:
+            resp = out.get("resp")
+            if resp is None:
+                resp = torch.empty(m_local, dtype=torch.int32, device=dev)
+            iou_resp = out.get("iou_resp")
+            if iou_resp is None:
+                iou_resp = torch.empty(m_local, dtype=torch.float32, device=dev)
+        lam_h = _host_floats(lam)
+        if version == 2:
+            if anchors is None or len(anchors) != a:
+                raise ValueError("anchors must list %d (w,h) pairs" % a)
+            _lib.call("yh_v2_train", _ptr(y), n, s_h, s_w, a, c, _anchors_host(anchors),
+                      float(img_hw[0]), float(img_hw[1]), _ptr(gt), _ptr(gt_off), m_local, m_glob,
+                      lam_h, _ptr(dy), _ptr(terms), _ptr(loss), _ptr(resp), _ptr(iou_resp),
+                      _ptr(ws), ws.numel(), _stream())
+        else:
+            _lib.call("yh_v1_train", _ptr(y), n, s_h, s_w, a, c,
+                      float(img_hw[0]), float(img_hw[1]), _ptr(gt), _ptr(gt_off), m_local, m_glob,
+                      lam_h, _ptr(dy), _ptr(terms), _ptr(loss), _ptr(resp), _ptr(iou_resp),
+                      _ptr(ws), ws.numel(), _stream())
+    return dict(loss=loss, terms=terms, dy=dy, resp=resp, iou_resp=iou_resp)
+
+
+def decode(y, *, version, img_hw, anchors=None, boxes_per_cell=None):
+    """The six predict() outputs -- yh_v2_decode / yh_v1_decode."""
+    y = _require_cuda_f32(y, "y")
+    n, s_h, s_w, a, c = head_shape(y, version, boxes_per_cell)
+    dev = y.device
+    kw = dict(dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        sig_txty = torch.empty(n, s_h, s_w, a, 2, **kw)
+        wh_act = torch.empty(n, s_h, s_w, a, 2, **kw)
+        bbox = torch.empty(n, s_h, s_w, a, 4, **kw)
+        conf = torch.empty(n, s_h, s_w, a, **kw)
+        spec = torch.empty(n, s_h, s_w, a, c, **kw)
+        if version == 2:
+            prob = torch.empty(n, s_h, s_w, a, c, **kw)
+            _lib.call("yh_v2_decode", _ptr(y), n, s_h, s_w, a, c, _anchors_host(anchors),
+                      float(img_hw[0]), float(img_hw[1]), _ptr(sig_txty), _ptr(wh_act), _ptr(bbox),
+                      _ptr(conf), _ptr(prob), _ptr(spec), _stream())
+        else:
+            prob = torch.empty(n, s_h, s_w, c, **kw)
+            _lib.call("yh_v1_decode", _ptr(y), n, s_h, s_w, a, c,
+                      float(img_hw[0]), float(img_hw[1]), _ptr(sig_txty), _ptr(wh_act), _ptr(bbox),
+                      _ptr(conf), _ptr(prob), _ptr(spec), _stream())
+    return sig_txty, wh_act, bbox, conf, prob, spec
+
+
+def compact_targets(sig_txty, twth, coord, cls_tgt, obj_mask, x_img_id, bbox_img_id):
+    """Dense reference targets -> (gt [M,12] int32, gt_off [N+1] int32, status [2] int32)."""
+    dev = sig_txty.device
+    m, s_h, s_w, _ = sig_txty.shape
+    n = int(x_img_id.numel())
+    c = int(cls_tgt.shape[-1])
+    sig_txty = _require_cuda_f32(sig_txty, "sig_txty_tgt")
+    twth = _require_cuda_f32(twth, "wh_tgt")
+    coord = _require_cuda_f32(coord, "bbox_coord_tgt")
+    cls_tgt = _require_cuda_f32(cls_tgt, "cls_tgt")
+    if obj_mask.dtype not in (torch.float64, torch.float32):
+        obj_mask = obj_mask.to(torch.float32)
+    obj_mask = obj_mask.contiguous()
+    x_img_id = x_img_id.to(device=dev, dtype=torch.int64).contiguous()
+    bbox_img_id = bbox_img_id.to(device=dev, dtype=torch.int64).contiguous()
+    with torch.cuda.device(dev):
+        gt = torch.empty(m, 12, dtype=torch.int32, device=dev)
+        gt_off = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        status = torch.empty(2, dtype=torch.int32, device=dev)
+        nbytes = int(_lib.load().yh_compact_workspace_bytes(m, n))
+        ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+        _lib.call("yh_compact_targets", _ptr(sig_txty), _ptr(twth), _ptr(coord), _ptr(cls_tgt),
+                  _ptr(obj_mask), 1 if obj_mask.dtype == torch.float64 else 0, _ptr(x_img_id),
+                  _ptr(bbox_img_id), m, n, s_h, s_w, c, _ptr(gt), _ptr(gt_off), _ptr(status),
+                  _ptr(ws), ws.numel(), _stream())
+    return gt, gt_off, status
+
+
+def postprocess(y, *, version, img_hw, conf_thre, iou_thre, anchors=None, boxes_per_cell=None,
+                class_aware=False, max_out=None, want_cls_spec=True, out=None):
+    """Decode + threshold + per-image greedy NMS + class pick -- yh_v{1,2}_postprocess.
+
+    Returns dict(keep_idx [N,max_out] int32, keep_cnt [N] int32, bbox, conf, cls_spec, label, score).
+    `out` may be a dict returned by an earlier call with the same shapes: its tensors are reused
+    (no allocation, e.g. inside a pipeline or a CUDA graph).
+    """
+    y = _require_cuda_f32(y, "y")
+    n, s_h, s_w, a, c = head_shape(y, version, boxes_per_cell)
+    p = s_h * s_w * a
+    max_out = p if max_out is None else int(max_out)
+    dev = y.device
+    with torch.cuda.device(dev):
+        if out is not None:
+            keep_idx, keep_cnt, bbox, conf = out["keep_idx"], out["keep_cnt"], out["bbox"], out["conf"]
+            spec, label, score, ws = out["cls_spec"], out["label"], out["score"], out["_ws"]
+            if keep_idx.shape != (n, max_out) or keep_idx.device != dev:
+                raise ValueError("`out` does not match this call's shapes")
+        else:
+            keep_idx = torch.empty(n, max_out, dtype=torch.int32, device=dev)
+            keep_cnt = torch.empty(n, dtype=torch.int32, device=dev)
+            bbox = torch.empty(n, max_out, 4, dtype=torch.float32, device=dev)
+            conf = torch.empty(n, max_out, dtype=torch.float32, device=dev)
+            spec = torch.empty(n, max_out, c, dtype=torch.float32, device=dev) if want_cls_spec else None
+            label = torch.empty(n, max_out, dtype=torch.int32, device=dev)
+            score = torch.empty(n, max_out, dtype=torch.float32, device=dev)
+            nbytes = int(_lib.load().yh_postprocess_workspace_bytes(n, p))
+            ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+        if version == 2:
+            _lib.call("yh_v2_postprocess", _ptr(y), n, s_h, s_w, a, c, _anchors_host(anchors),
+                      float(img_hw[0]), float(img_hw[1]), float(conf_thre), float(iou_thre),
+                      int(bool(class_aware)), max_out, _ptr(keep_idx), _ptr(keep_cnt), _ptr(bbox),
+                      _ptr(conf), _ptr(spec), _ptr(label), _ptr(score), _ptr(ws), ws.numel(), _stream())
+        else:
+            _lib.call("yh_v1_postprocess", _ptr(y), n, s_h, s_w, a, c,
+                      float(img_hw[0]), float(img_hw[1]), float(conf_thre), float(iou_thre),
+                      int(bool(class_aware)), max_out, _ptr(keep_idx), _ptr(keep_cnt), _ptr(bbox),
+                      _ptr(conf), _ptr(spec), _ptr(label), _ptr(score), _ptr(ws), ws.numel(), _stream())
+    return dict(keep_idx=keep_idx, keep_cnt=keep_cnt, bbox=bbox, conf=conf, cls_spec=spec,
+                label=label, score=score, _ws=ws)
+
+
+def nms_indices(bbox, conf, *, conf_thre, iou_thre, labels=None, max_out=None):
+    """Per-image greedy NMS on decoded boxes: bbox [N,P,4], conf [N,P] -> (keep_idx, keep_cnt)."""
+    bbox = _require_cuda_f32(bbox, "bbox")
+    conf = _require_cuda_f32(conf, "conf")
+    n, p = conf.shape
+    max_out = p if max_out is None else int(max_out)
+    dev = bbox.device
+    if labels is not None:
+        labels = labels.to(device=dev, dtype=torch.int32).contiguous()
+    with torch.cuda.device(dev):
+        keep_idx = torch.empty(n, max(max_out, 1), dtype=torch.int32, device=dev)
+        keep_cnt = torch.empty(n, dtype=torch.int32, device=dev)
+        nbytes = int(_lib.load().yh_postprocess_workspace_bytes(n, p))
+        ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+        _lib.call("yh_nms", _ptr(bbox), _ptr(conf), _ptr(labels), n, p, float(conf_thre),
+                  float(iou_thre), max_out, _ptr(keep_idx), _ptr(keep_cnt), _ptr(ws), ws.numel(),
+                  _stream())
+    return keep_idx, keep_cnt
+
+
+def iou(boxes1, boxes2):
+    """Elementwise IoU of two [K,4] CUDA tensors -- yh_iou."""
+    boxes1 = _require_cuda_f32(boxes1, "boxes1")
+    boxes2 = _require_cuda_f32(boxes2, "boxes2")
+    if boxes1.shape != boxes2.shape or boxes1.shape[-1] != 4:
+        raise ValueError("boxes must have identical [...,4] shapes")
+    count = boxes1.numel() // 4
+    with torch.cuda.device(boxes1.device):
+        out = torch.empty(boxes1.shape[:-1], dtype=torch.float32, device=boxes1.device)
+        _lib.call("yh_iou", _ptr(boxes1), _ptr(boxes2), count, _ptr(out), _stream())
+    return out
+
+
+def scale_inplace(x, scale):
+    """x *= scale (0-dim CUDA tensor); a device-side no-op when scale == 1."""
+    with torch.cuda.device(x.device):
+        _lib.call("yh_scale_inplace", _ptr(x), x.numel(), _ptr(scale), _stream())
+    return x

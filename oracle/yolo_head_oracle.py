@@ -406,3 +406,53 @@ def postprocess_np(y, height, width, version, anchors, conf_thre, iou_thre, clas
                         cls_spec=spec[i][keep],
                         label=labels_all[keep].astype(np.int32), score=spec[i][keep].max(-1) if len(keep) else np.zeros(0, F32)))
     return out
+
+
+# --------------------------------------------------------------------------------------
+# torch-CPU port of the reference's own NMS loop (cost model for the CPU baseline)
+# --------------------------------------------------------------------------------------
+def nms_torch(bbox, conf, cls_spec, conf_thre=0.9, iou_thre=0.5):
+    """Shrinking-list greedy NMS the way the reference executes it on torch CPU.
+
+    models/utils.py:89-164: threshold with `>=`, flatten, `torch.sort(descending=True)`, then
+    for position i: IoU of row i against all later rows, keep the first i+1 rows and every
+    later row with `iou < iou_thre`, re-gather all three tensors, advance.  Same tensor ops per
+    iteration as the reference, so its wall-clock is representative of the reference's cost;
+    bench.py times this as the CPU baseline ("port").  Returns the three gathered tensors in
+    descending-confidence order, like the reference.
+    """
+    num_cls = cls_spec.shape[-1]
+    sel = (conf >= conf_thre).reshape(-1)
+    bbox = bbox.reshape(-1, 4)[sel]
+    conf = conf.reshape(-1)[sel]
+    cls_spec = cls_spec.reshape(-1, num_cls)[sel]
+    conf, order = torch.sort(conf, descending=True)
+    bbox = bbox[order]
+    cls_spec = cls_spec[order]
+    i = 0
+    while i < conf.numel() - 1:
+        survive = iou_torch(bbox[i:i + 1], bbox[i + 1:]) < iou_thre
+        keep = torch.cat([torch.ones(i + 1, dtype=torch.bool), survive])
+        bbox, conf, cls_spec = bbox[keep], conf[keep], cls_spec[keep]
+        i += 1
+    return bbox, conf, cls_spec
+
+
+def postprocess_torch(y, height, width, version, anchors, conf_thre, iou_thre):
+    """detect() for every image of a batch on torch CPU: decode once, then per image
+    nms_torch + class pick (models/yolov2.py:694-743).  The flat predictor index rides along as
+    an extra class column (exact in fp32 below 2^24) so that kept indices can be read back."""
+    _, _, bbox, conf, _, spec = decode_torch(torch.as_tensor(y), height, width, version, anchors)
+    n = bbox.shape[0]
+    c = spec.shape[-1]
+    out = []
+    for i in range(n):
+        s = spec[i].reshape(-1, c)
+        idx = torch.arange(s.shape[0], dtype=torch.float32)[:, None]
+        kb, kc, ks = nms_torch(bbox[i], conf[i], torch.cat([s, idx], -1), conf_thre, iou_thre)
+        sp = ks[:, :-1]
+        out.append(dict(idx=ks[:, -1].numpy().astype(np.int32), bbox=kb.numpy(), conf=kc.numpy(),
+                        cls_spec=sp.numpy(),
+                        label=sp.argmax(-1).numpy().astype(np.int32) if len(kc) else np.zeros(0, np.int32),
+                        score=sp.max(-1)[0].numpy() if len(kc) else np.zeros(0, F32)))
+    return out

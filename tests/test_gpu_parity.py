@@ -1,0 +1,463 @@
+"""Parity of the CUDA path (through the C ABI, via odcp_b200.ops) against
+  (1) the golden vectors produced by the reference itself (tests/golden/*.npz),
+  (2) the CPU oracle on seeded synthetic inputs,
+  (3) size-independent properties at the BASELINE.json full sizes.
+
+Tolerances (north-star): responsible-predictor and kept-box indices bit-exact, except decisions
+whose two best candidates are within a few ulp of each other (those are listed in the assertion
+message, never silently skipped); loss and dL/dy within 1e-5 relative in fp32.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_lambdas, load_golden, rel_err
+from odcp_b200 import ops, synthetic, targets
+from oracle import yolo_head_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+LOSS_FILES = ["v2_loss_small.npz", "v2_loss_nonsquare.npz", "v1_loss_small.npz", "v1_loss_b3c7.npz"]
+
+
+def run_train(case, lambdas, dev, m_global=None, want_grad=True):
+    y = case.y.to(dev)
+    gt = targets.records_to_tensor(case.rec, dev)
+    off = torch.from_numpy(case.gt_off).to(dev)
+    r = ops.train_head(y, gt, off, version=case.version, img_hw=(case.height, case.width),
+                       lambdas=lambdas, anchors=case.anchors, boxes_per_cell=case.a,
+                       m_global=m_global, want_grad=want_grad, want_resp=True)
+    torch.cuda.synchronize()
+    return dict(loss=float(r["loss"].item()), terms=r["terms"].cpu().numpy(),
+                dy=None if r["dy"] is None else r["dy"].cpu().numpy(),
+                resp=r["resp"].cpu().numpy(), iou_resp=r["iou_resp"].cpu().numpy())
+
+
+def assert_decisions(got, want, iou_all=None, what="resp"):
+    mism = np.nonzero(got != want)[0]
+    for j in mism:
+        assert iou_all is not None, ("%s mismatch at record %d" % (what, j))
+        top2 = np.sort(iou_all[j])[-2:]
+        assert top2[1] - top2[0] <= 4 * np.spacing(np.float32(top2[1])), \
+            ("non-tie %s mismatch" % what, int(j), iou_all[j], int(got[j]), int(want[j]))
+
+
+# ------------------------------------------------------------------------------------------
+# train head
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", LOSS_FILES)
+def test_train_head_matches_reference_golden(name, cuda_device):
+    case, z = load_golden(name)
+    r = run_train(case, golden_lambdas(z), cuda_device)
+    assert abs(r["loss"] - float(z["loss"])) <= TOL * abs(float(z["loss"]))
+    assert r["dy"].shape == z["dy"].shape
+    assert rel_err(r["dy"], z["dy"]) <= TOL
+    assert_decisions(r["resp"], z["resp"], z["iou_all"])
+    assert np.abs(r["iou_resp"] - z["iou_resp"]).max() <= 2e-6
+    assert np.array_equal(r["dy"] != 0, z["dy"] != 0), "gradient sparsity pattern differs"
+    # elementwise on the non-zeros as well (not only relative to the largest entry)
+    nz = z["dy"] != 0
+    assert np.abs(r["dy"][nz] / z["dy"][nz] - 1).max() <= 2e-3
+
+
+@pytest.mark.parametrize("name", LOSS_FILES)
+def test_train_head_loss_only_variant(name, cuda_device):
+    case, z = load_golden(name)
+    r = run_train(case, golden_lambdas(z), cuda_device, want_grad=False)
+    assert r["dy"] is None
+    assert abs(r["loss"] - float(z["loss"])) <= TOL * abs(float(z["loss"]))
+    assert_decisions(r["resp"], z["resp"], z["iou_all"])
+
+
+def test_train_head_cfg2_full_vs_reference_summary(cuda_device):
+    case, z = load_golden("v2_cfg2_summary.npz")
+    live = synthetic.cfg2()
+    r = run_train(live, synthetic.DEFAULT_LAMBDAS, cuda_device)
+    assert abs(r["loss"] - float(z["loss"])) <= TOL * abs(float(z["loss"]))
+    assert np.array_equal(r["resp"], z["resp"])
+    dy = r["dy"]
+    rows = dy[live.rec["img"], live.rec["cy"], live.rec["cx"], r["resp"]]
+    assert rel_err(rows, z["dy_rows"]) <= TOL
+    assert rel_err(dy[..., 4].reshape(-1)[::7], z["dy_to_sample"]) <= TOL
+    assert int(np.count_nonzero(dy)) == int(z["dy_nnz"])
+    assert abs(np.abs(dy.astype(np.float64)).sum() - float(z["dy_abs_sum"])) <= TOL * float(z["dy_abs_sum"])
+
+
+CASES = {
+    "cfg1": lambda: synthetic.cfg1(),
+    "cfg1_coll": lambda: synthetic.with_collisions(synthetic.cfg1(), 9, seed=3),
+    "cfg2": lambda: synthetic.cfg2(),
+    "cfg2_coll": lambda: synthetic.with_collisions(synthetic.cfg2(), 40, seed=4),
+    "cfg2_10gt": lambda: synthetic.cfg2(k_hi=19),
+    "v2_19x19_n8": lambda: synthetic.cfg5(n=8),
+    "v2_nonsq_odd": lambda: synthetic.make_case("odd", 2, 3, 9, 11, 5, 20, 288, 352, seed=21, k_hi=6),
+    "v2_1img": lambda: synthetic.make_case("one", 2, 1, 13, 13, 5, 20, 416, 416, seed=22),
+    "v2_c80_a3": lambda: synthetic.make_case("coco", 2, 5, 13, 13, 3, 80, 416, 416, seed=23,
+                                             anchors=synthetic.YOLOV2_ANCHORS[:3]),
+    "v1_b3_c7": lambda: synthetic.make_case("v1b3", 1, 5, 5, 6, 3, 7, 160, 192, seed=24),
+    "v2_c1": lambda: synthetic.make_case("c1", 2, 4, 13, 13, 5, 1, 416, 416, seed=25),
+}
+
+
+@pytest.mark.parametrize("key", sorted(CASES))
+def test_train_head_vs_oracle(key, cuda_device):
+    case = CASES[key]()
+    lam = synthetic.DEFAULT_LAMBDAS
+    want = O.train_head_compact(case, lam)
+    r = run_train(case, lam, cuda_device)
+    assert abs(r["loss"] - want["loss"]) <= TOL * abs(want["loss"])
+    assert np.abs(r["terms"] - want["terms"]).max() <= TOL * np.abs(want["terms"]).max()
+    assert_decisions(r["resp"], want["resp"], want["iou_all"])
+    assert rel_err(r["dy"], want["dy"]) <= TOL
+    assert np.array_equal(r["dy"] != 0, want["dy"] != 0)
+    assert np.abs(r["iou_resp"] - want["iou_resp"]).max() <= 2e-6
+
+
+def test_train_head_images_without_boxes(cuda_device):
+    """Images with k_n = 0 get an all-zero gradient."""
+    case = synthetic.make_case("empty", 2, 6, 13, 13, 5, 20, 416, 416, seed=31, k_lo=0, k_hi=2)
+    k = np.diff(case.gt_off)
+    assert (k == 0).any() and (k > 0).any()
+    want = O.train_head_compact(case, synthetic.DEFAULT_LAMBDAS)
+    r = run_train(case, synthetic.DEFAULT_LAMBDAS, cuda_device)
+    assert abs(r["loss"] - want["loss"]) <= TOL * abs(want["loss"])
+    assert rel_err(r["dy"], want["dy"]) <= TOL
+    for n in np.nonzero(k == 0)[0]:
+        assert not r["dy"][n].any()
+
+
+def test_train_head_no_boxes_is_an_error(cuda_device):
+    from odcp_b200._lib import YoloHeadError
+    case = synthetic.make_case("none", 2, 2, 13, 13, 5, 20, 416, 416, seed=32, k_lo=0, k_hi=0)
+    with pytest.raises(YoloHeadError) as e:
+        run_train(case, synthetic.DEFAULT_LAMBDAS, cuda_device)
+    assert e.value.code == -2
+
+
+def test_train_head_is_deterministic_and_workspace_reusable(cuda_device):
+    case = synthetic.with_collisions(synthetic.cfg2(), 40, seed=4)
+    a = run_train(case, synthetic.DEFAULT_LAMBDAS, cuda_device)
+    for _ in range(3):
+        b = run_train(case, synthetic.DEFAULT_LAMBDAS, cuda_device)
+        assert a["loss"] == b["loss"]
+        assert np.array_equal(a["dy"], b["dy"])
+
+
+def test_train_head_unaligned_views(cuda_device):
+    """y / dy that are only 4-byte aligned take the non-TMA path; results must not change."""
+    case = synthetic.cfg2(n=5)
+    lam = synthetic.DEFAULT_LAMBDAS
+    base = run_train(case, lam, cuda_device)
+    dev = cuda_device
+    buf = torch.zeros(case.y.numel() + 1, device=dev)
+    y = buf[1:].view(case.y.shape)
+    y.copy_(case.y)
+    assert y.data_ptr() % 16 == 4
+    gt = targets.records_to_tensor(case.rec, dev)
+    off = torch.from_numpy(case.gt_off).to(dev)
+    dybuf = torch.empty(case.y.numel() + 3, device=dev)
+    dy = dybuf[3:].view(case.y.shape)
+    r = ops.train_head(y, gt, off, version=2, img_hw=(case.height, case.width), lambdas=lam,
+                       anchors=case.anchors, out=dict(dy=dy))
+    assert float(r["loss"].item()) == base["loss"]
+    assert np.array_equal(dy.cpu().numpy(), base["dy"])
+
+
+def test_train_head_shards_recombine(cuda_device):
+    """Chunk additivity: image shards evaluated with the global box count add up
+    to the unsharded result -- the property the multi-GPU path relies on."""
+    case = synthetic.with_collisions(synthetic.cfg2(), 40, seed=4)
+    lam = synthetic.DEFAULT_LAMBDAS
+    full = run_train(case, lam, cuda_device)
+    loss = 0.0
+    parts = []
+    for lo, hi in ((0, 13), (13, 14), (14, 40), (40, 64)):
+        rec, off = targets.shard_records(case.rec, case.gt_off, lo, hi)
+        sub = synthetic.HeadCase("s", 2, hi - lo, case.s_h, case.s_w, case.a, case.c, case.height,
+                                 case.width, case.y[lo:hi].contiguous(), rec, off, anchors=case.anchors)
+        r = run_train(sub, lam, cuda_device, m_global=case.m)
+        loss += r["loss"]
+        parts.append(r["dy"])
+    assert abs(loss - full["loss"]) <= TOL * abs(full["loss"])
+    assert np.array_equal(np.concatenate(parts, 0), full["dy"])
+
+
+def test_train_head_full_size_properties_cfg5(cuda_device):
+    """BASELINE cfg 5 at full size (N=512, 19x19, 50..100 boxes/image): the dense reference
+    cannot run it, so check (a) an 8-image slice against the oracle, (b) permutation invariance
+    of the box order inside images, (c) shard additivity."""
+    case = synthetic.cfg5()
+    lam = synthetic.DEFAULT_LAMBDAS
+    full = run_train(case, lam, cuda_device)
+    assert np.isfinite(full["loss"])
+    # (a) slice vs oracle, same global M
+    rec, off = targets.shard_records(case.rec, case.gt_off, 100, 108)
+    sub = synthetic.HeadCase("s", 2, 8, case.s_h, case.s_w, case.a, case.c, case.height, case.width,
+                             case.y[100:108].contiguous(), rec, off, anchors=case.anchors)
+    want = O.train_head_compact(sub, lam, m_global=case.m)
+    assert rel_err(full["dy"][100:108], want["dy"]) <= TOL
+    lo, hi = int(case.gt_off[100]), int(case.gt_off[108])
+    assert_decisions(full["resp"][lo:hi], want["resp"], want["iou_all"])
+    # (b) reverse the box order inside every image
+    perm = np.concatenate([np.arange(case.gt_off[n + 1] - 1, case.gt_off[n] - 1, -1) for n in range(case.n)])
+    pc = synthetic.HeadCase("p", 2, case.n, case.s_h, case.s_w, case.a, case.c, case.height, case.width,
+                            case.y, case.rec[perm], case.gt_off, anchors=case.anchors)
+    rp = run_train(pc, lam, cuda_device)
+    assert abs(rp["loss"] - full["loss"]) <= TOL * abs(full["loss"])
+    assert rel_err(rp["dy"], full["dy"]) <= TOL
+    assert np.array_equal(rp["resp"], full["resp"][perm])
+    # (c) two shards
+    tot = 0.0
+    for a, b in ((0, 200), (200, 512)):
+        rec, off = targets.shard_records(case.rec, case.gt_off, a, b)
+        s = synthetic.HeadCase("s", 2, b - a, case.s_h, case.s_w, case.a, case.c, case.height, case.width,
+                               case.y[a:b].contiguous(), rec, off, anchors=case.anchors)
+        r = run_train(s, lam, cuda_device, m_global=case.m)
+        tot += r["loss"]
+        assert np.array_equal(r["dy"], full["dy"][a:b])
+    assert abs(tot - full["loss"]) <= TOL * abs(full["loss"])
+
+
+# ------------------------------------------------------------------------------------------
+# predict / decode
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,version", [("v2_predict.npz", 2), ("v1_predict.npz", 1)])
+def test_decode_matches_reference_golden(name, version, cuda_device):
+    case, z = load_golden(name)
+    outs = ops.decode(case.y.to(cuda_device), version=version, img_hw=(case.height, case.width),
+                      anchors=case.anchors, boxes_per_cell=case.a)
+    for i, t in enumerate(outs):
+        got = t.cpu().numpy()
+        assert got.shape == z["out%d" % i].shape, i
+        assert rel_err(got, z["out%d" % i]) <= 2e-6, i
+        assert np.allclose(got, z["out%d" % i], rtol=1e-5, atol=1e-7), i
+
+
+def test_decode_full_size_and_nonsquare(cuda_device):
+    for case in (synthetic.cfg3(), synthetic.make_case("odd", 2, 3, 9, 11, 5, 20, 288, 352, seed=21),
+                 synthetic.cfg1()):
+        anchors = case.anchors if case.version == 2 else case.a
+        want = O.decode_torch(case.y, case.height, case.width, case.version, anchors)
+        outs = ops.decode(case.y.to(cuda_device), version=case.version, img_hw=(case.height, case.width),
+                          anchors=case.anchors, boxes_per_cell=case.a)
+        for i, (g, w) in enumerate(zip(outs, want)):
+            assert g.shape == w.shape
+            assert np.allclose(g.cpu().numpy(), w.numpy(), rtol=1e-5, atol=1e-7), (case.name, i)
+
+
+# ------------------------------------------------------------------------------------------
+# dense-target adaptor
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("key", ["cfg1_coll", "cfg2_coll", "v2_nonsq_odd", "v1_b3_c7"])
+def test_compact_targets_recovers_records(key, cuda_device):
+    case = CASES[key]()
+    ids = np.arange(case.n, dtype=np.int64) * 7 + 3        # arbitrary image ids, like dataset indices
+    dense = targets.records_to_dense(case.rec, case.n, case.s_h, case.s_w, case.c, case.version, x_img_id=ids)
+    # shuffle the boxes: get_loss does not require them grouped by image
+    perm = np.random.default_rng(5).permutation(case.m)
+    d = [t[perm] if t.shape[0] == case.m and i != 5 else t for i, t in enumerate(dense)]
+    gt, off, status = ops.compact_targets(*[t.to(cuda_device) for t in d])
+    assert status.cpu().tolist() == [0, 0]
+    assert np.array_equal(off.cpu().numpy(), case.gt_off)
+    got = targets.tensor_to_records(gt)
+    # stable inside an image: expected = records in shuffled order, stably sorted by image
+    exp = case.rec[perm]
+    exp = exp[np.argsort(exp["img"], kind="stable")]
+    assert np.array_equal(got, exp)
+    # fp32 obj_mask is accepted too
+    d[4] = d[4].float()
+    gt2, off2, _ = ops.compact_targets(*[t.to(cuda_device) for t in d])
+    assert torch.equal(gt2, gt) and torch.equal(off2, off)
+
+
+# ------------------------------------------------------------------------------------------
+# post-process / NMS
+# ------------------------------------------------------------------------------------------
+def run_post(case, conf_thre, iou_thre, dev, class_aware=False, max_out=None):
+    r = ops.postprocess(case.y.to(dev), version=case.version, img_hw=(case.height, case.width),
+                        conf_thre=conf_thre, iou_thre=iou_thre, anchors=case.anchors,
+                        boxes_per_cell=case.a, class_aware=class_aware, max_out=max_out)
+    torch.cuda.synchronize()
+    return {k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in r.items()}
+
+
+def flat_kept(r, key):
+    cnt = r["keep_cnt"]
+    return np.concatenate([r[key][n, :cnt[n]] for n in range(len(cnt))], 0)
+
+
+@pytest.mark.parametrize("name", ["v2_nms_cfg3.npz", "v2_nms_default.npz", "v1_nms.npz"])
+def test_postprocess_matches_reference_golden(name, cuda_device):
+    case, z = load_golden(name)
+    r = run_post(case, float(z["conf_thre"]), float(z["iou_thre"]), cuda_device)
+    assert np.array_equal(r["keep_cnt"], z["nms_cnt"])
+    assert z["nms_cnt"].sum() > 0
+    assert np.array_equal(flat_kept(r, "keep_idx"), z["nms_idx"])
+    assert np.allclose(flat_kept(r, "bbox"), z["nms_bbox"], rtol=1e-5, atol=1e-4)
+    assert np.allclose(flat_kept(r, "conf"), z["nms_conf"], rtol=1e-6, atol=1e-7)
+    assert np.allclose(flat_kept(r, "cls_spec"), z["nms_cls_spec"], rtol=1e-5, atol=1e-7)
+    assert np.array_equal(flat_kept(r, "label"), z["nms_cls_spec"].argmax(-1))
+    assert np.allclose(flat_kept(r, "score"), z["nms_cls_spec"].max(-1), rtol=1e-5, atol=1e-7)
+
+
+def check_post_vs_oracle(case, conf_thre, iou_thre, dev, class_aware=False):
+    anchors = case.anchors if case.version == 2 else case.a
+    want = O.postprocess_np(case.y, case.height, case.width, case.version, anchors, conf_thre, iou_thre,
+                            class_aware=class_aware)
+    r = run_post(case, conf_thre, iou_thre, dev, class_aware=class_aware)
+    cnt = np.array([len(w["idx"]) for w in want], dtype=np.int32)
+    assert np.array_equal(r["keep_cnt"], cnt)
+    for n, w in enumerate(want):
+        assert np.array_equal(r["keep_idx"][n, :cnt[n]], w["idx"]), n
+        assert np.array_equal(r["label"][n, :cnt[n]], w["label"]), n
+        assert np.allclose(r["bbox"][n, :cnt[n]], w["bbox"], rtol=1e-5, atol=1e-4)
+        assert np.allclose(r["score"][n, :cnt[n]], w["score"], rtol=1e-5, atol=1e-7)
+    return cnt
+
+
+def test_postprocess_cfg3_full_vs_oracle(cuda_device):
+    case = synthetic.cfg3()
+    assert synthetic.distinct_scores(case.y, 2, 5)
+    cnt = check_post_vs_oracle(case, 0.5, 0.45, cuda_device)
+    assert 5 < cnt.mean() < 60
+
+
+def test_postprocess_class_aware_vs_oracle(cuda_device):
+    check_post_vs_oracle(synthetic.cfg3(n=32), 0.5, 0.45, cuda_device, class_aware=True)
+    check_post_vs_oracle(synthetic.make_case("v1n", 1, 6, 7, 7, 2, 20, 448, 448, seed=41, to_shift=0.5),
+                         0.4, 0.3, cuda_device, class_aware=True)
+
+
+def test_postprocess_dense_candidates_multi_tile(cuda_device):
+    """More candidates than one 256-wide suppression tile (19x19, most predictors pass) and the
+    degenerate thresholds: everything passes / nothing passes / iou_thre 0 and > 1."""
+    case = synthetic.make_case("dense", 2, 3, 19, 19, 5, 20, 608, 608, seed=42, to_shift=1.0)
+    check_post_vs_oracle(case, 0.5, 0.45, cuda_device)
+    check_post_vs_oracle(case, 0.0, 0.6, cuda_device)           # all 1805 predictors are candidates
+    cnt = check_post_vs_oracle(case, 0.5, 1.5, cuda_device)     # nothing is ever suppressed
+    assert (cnt > 256).all()
+    cnt = check_post_vs_oracle(case, 1.1, 0.5, cuda_device)     # no candidates
+    assert (cnt == 0).all()
+    check_post_vs_oracle(case, 0.9, 0.0, cuda_device)           # iou >= 0 always: one box survives
+    check_post_vs_oracle(case, 0.3, 0.45, cuda_device, class_aware=True)
+
+
+def test_postprocess_max_out_truncates_but_counts(cuda_device):
+    case = synthetic.cfg3(n=8)
+    full = run_post(case, 0.5, 0.45, cuda_device)
+    r = run_post(case, 0.5, 0.45, cuda_device, max_out=4)
+    assert np.array_equal(r["keep_cnt"], full["keep_cnt"])
+    for n in range(case.n):
+        k = min(4, full["keep_cnt"][n])
+        assert np.array_equal(r["keep_idx"][n, :k], full["keep_idx"][n, :k])
+
+
+def test_postprocess_properties_cfg5_full(cuda_device):
+    """Full-size cfg 5 post-process: kept ⊆ candidates, descending confidence, no two kept boxes
+    with IoU >= thr, idempotence (NMS of the kept set keeps everything), and agreement with the
+    oracle on a 16-image slice."""
+    case = synthetic.cfg5()
+    r = run_post(case, 0.5, 0.45, cuda_device, max_out=256)
+    cnt = r["keep_cnt"]
+    assert cnt.max() <= 256 and cnt.min() > 0
+    sub = synthetic.HeadCase("s", 2, 16, case.s_h, case.s_w, case.a, case.c, case.height, case.width,
+                             case.y[:16].contiguous(), case.rec[:0], case.gt_off[:17] * 0, anchors=case.anchors)
+    want = O.postprocess_np(sub.y, sub.height, sub.width, 2, sub.anchors, 0.5, 0.45)
+    for n, w in enumerate(want):
+        assert np.array_equal(r["keep_idx"][n, :cnt[n]], w["idx"])
+    thr = np.float32(0.45)
+    for n in range(0, case.n, 37):
+        k = cnt[n]
+        conf, box = r["conf"][n, :k], r["bbox"][n, :k]
+        assert (conf >= np.float32(0.5)).all() and (np.diff(conf) <= 0).all()
+        iou = O.iou_np(box[:, None, :], box[None, :, :])
+        np.fill_diagonal(iou, 0)
+        assert (iou < thr).all()
+    # idempotence through the decoded-box entry point
+    dev = cuda_device
+    bbox = torch.from_numpy(r["bbox"]).to(dev)
+    conf = torch.from_numpy(r["conf"]).to(dev).clone()
+    valid = torch.arange(256, device=dev)[None, :] < torch.from_numpy(cnt).to(dev)[:, None]
+    conf[~valid] = -1.0
+    idx2, cnt2 = ops.nms_indices(bbox, conf, conf_thre=0.5, iou_thre=0.45)
+    assert np.array_equal(cnt2.cpu().numpy(), cnt)
+    assert all(np.array_equal(idx2[n, :cnt[n]].cpu().numpy(), np.arange(cnt[n])) for n in range(0, case.n, 37))
+
+
+def test_nms_on_decoded_boxes_matches_oracle(cuda_device):
+    case = synthetic.cfg3(n=16)
+    _, _, bbox, conf, _, spec = O.decode_torch(case.y, case.height, case.width, 2, case.anchors)
+    b = bbox.reshape(case.n, -1, 4).contiguous()
+    c = conf.reshape(case.n, -1).contiguous()
+    lab = spec.reshape(case.n, -1, case.c).argmax(-1).int()
+    for labels in (None, lab):
+        idx, cnt = ops.nms_indices(b.to(cuda_device), c.to(cuda_device), conf_thre=0.5, iou_thre=0.45,
+                                   labels=None if labels is None else labels.to(cuda_device))
+        idx, cnt = idx.cpu().numpy(), cnt.cpu().numpy()
+        for n in range(case.n):
+            want = O.nms_image_np(b[n].numpy(), c[n].numpy(), 0.5, 0.45,
+                                  labels=None if labels is None else labels[n].numpy())
+            assert cnt[n] == len(want)
+            assert np.array_equal(idx[n, :cnt[n]], want)
+
+
+def test_nms_equal_confidences_order_by_index(cuda_device):
+    """torch.sort leaves ties unspecified (SURVEY B-4); this implementation orders them by
+    ascending predictor index."""
+    b = torch.tensor([[[0, 0, 10, 10], [100, 100, 110, 110], [0, 0, 10, 10.5], [200, 200, 210, 210]]],
+                     dtype=torch.float32, device=cuda_device)
+    c = torch.tensor([[0.7, 0.9, 0.7, 0.9]], device=cuda_device)
+    idx, cnt = ops.nms_indices(b, c, conf_thre=0.5, iou_thre=0.5)
+    assert cnt.item() == 3
+    assert idx[0, :3].cpu().tolist() == [1, 3, 0]
+
+
+def test_iou_known_answers(cuda_device):
+    import os
+    from conftest import GOLDEN
+    z = dict(np.load(os.path.join(GOLDEN, "iou_kat.npz")))
+    got = ops.iou(torch.from_numpy(z["b1"]).to(cuda_device), torch.from_numpy(z["b2"]).to(cuda_device))
+    assert np.array_equal(got.cpu().numpy(), z["iou"])   # +,-,*,/ are correctly rounded on both sides
+    # large random batch against the oracle
+    rng = np.random.default_rng(7)
+    b1 = rng.uniform(0, 400, size=(100003, 4)).astype(np.float32)
+    b2 = rng.uniform(0, 400, size=(100003, 4)).astype(np.float32)
+    b1[:, 2:] += b1[:, :2]
+    b2[:, 2:] += b2[:, :2]
+    got = ops.iou(torch.from_numpy(b1).to(cuda_device), torch.from_numpy(b2).to(cuda_device))
+    assert np.array_equal(got.cpu().numpy(), O.iou_np(b1, b2))
+
+
+def test_cuda_graph_capture_of_a_step(cuda_device):
+    """The entry points only enqueue work: a train + post-process step captures into a CUDA graph
+    and replays with identical results."""
+    case = synthetic.headline(n=32)
+    dev = cuda_device
+    lam = synthetic.DEFAULT_LAMBDAS
+    y = case.y.to(dev)
+    gt = targets.records_to_tensor(case.rec, dev)
+    off = torch.from_numpy(case.gt_off).to(dev)
+    eager = ops.train_head(y, gt, off, version=2, img_hw=(416, 416), lambdas=lam, anchors=case.anchors)
+    eager_post = ops.postprocess(y, version=2, img_hw=(416, 416), conf_thre=0.5, iou_thre=0.45,
+                                 anchors=case.anchors, max_out=64)
+    torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        out = dict(dy=torch.empty_like(y), loss=torch.empty((), device=dev), terms=torch.empty(5, device=dev))
+        ops.train_head(y, gt, off, version=2, img_hw=(416, 416), lambdas=lam, anchors=case.anchors, out=out)
+        s.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            ops.train_head(y, gt, off, version=2, img_hw=(416, 416), lambdas=lam, anchors=case.anchors, out=out)
+            post = ops.postprocess(y, version=2, img_hw=(416, 416), conf_thre=0.5, iou_thre=0.45,
+                                   anchors=case.anchors, max_out=64)
+    out["dy"].zero_()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out["dy"], eager["dy"])
+    assert out["loss"].item() == eager["loss"].item()
+    assert torch.equal(post["keep_cnt"], eager_post["keep_cnt"])
+    cnt = eager_post["keep_cnt"].cpu().numpy()
+    for n in range(case.n):
+        assert torch.equal(post["keep_idx"][n, :cnt[n]], eager_post["keep_idx"][n, :cnt[n]])

@@ -91,6 +91,12 @@ def test_nms_matches_reference(name):
     assert np.array_equal(cat("bbox"), z["nms_bbox"])
     assert np.array_equal(cat("conf"), z["nms_conf"])
     assert np.array_equal(cat("cls_spec"), z["nms_cls_spec"])
+    # the torch port of the reference's shrinking-list loop (the CPU-baseline cost model)
+    res2 = O.postprocess_torch(case.y, case.height, case.width, case.version, anchors,
+                               float(z["conf_thre"]), float(z["iou_thre"]))
+    cat2 = lambda k: np.concatenate([r[k] for r in res2], 0)
+    for k, g in (("idx", "nms_idx"), ("bbox", "nms_bbox"), ("conf", "nms_conf"), ("cls_spec", "nms_cls_spec")):
+        assert np.array_equal(cat2(k), z[g]), k
 
 
 def test_iou_known_answers():
