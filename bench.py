@@ -136,7 +136,7 @@ class ClockSampler(threading.Thread):
         self.index, self.period = index, period
         self.samples, self.reasons = [], set()
         self.sm_max = None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self.ok = False
         try:
             import pynvml
@@ -151,7 +151,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         if not self.ok:
             return
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
                 bits = int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
@@ -163,7 +163,7 @@ class ClockSampler(threading.Thread):
             time.sleep(self.period)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         if self.is_alive():
             self.join()
 
@@ -212,7 +212,6 @@ def main():
     K, W, R, B = args.steps, max(args.warmup, 3), args.sets, args.batch
     lam = synthetic.DEFAULT_LAMBDAS
     case = synthetic.headline(n=B)
-    assert synthetic.distinct_scores(case.y, 2, case.a)
     kw = dict(version=2, img_hw=(case.height, case.width), anchors=case.anchors)
     m_local = case.m
     m_global = m_local * world  # every rank holds a shard with the same box count (weak scaling)
