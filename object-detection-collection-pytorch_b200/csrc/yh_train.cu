@@ -1,37 +1,42 @@
 // Fused YOLO train head: decode + responsible-predictor assignment + five loss terms + dL/dy
-// in one pass over the head tensor.
+// in one pass over the head tensor, ONE launch per batch.
 //
 // Replaces YOLOv2.get_loss / YOLOv1.get_loss and their autograd backward
 // (reference models/yolov2.py:747-1140, models/yolov1.py:556-931, models/utils.py:5-65).
 //
-// Data movement (this kernel is HBM-bound: ~60 flop per 200 bytes):
-//   * the head tensor is treated as a flat stream of cells; each persistent CTA owns a
-//     contiguous range of cells and walks it in chunks of <= 16 KB;
-//   * chunks are pulled into a shared-memory ring with 1-D TMA bulk copies
-//     (cp.async.bulk + mbarrier) several chunks ahead of the compute;
-//   * dL/dy for the chunk is assembled in a second shared-memory ring and pushed back with
-//     TMA bulk stores, so every byte of y is read once and every byte of dy written once,
-//     fully coalesced, with no zero-fill pass (each row owner writes its whole row);
-//   * the five partial sums go through a last-block-done reduction (fixed order ->
-//     run-to-run deterministic), so the whole step is ONE launch.
+// The kernel is HBM-bound (~60 flop per 200 bytes), so it is organised around data movement:
+//   * one persistent CTA per SM owns a contiguous range of grid cells of the flattened batch;
+//   * the range is cut into mini-chunks of a few cells (<= ~4 KB, a multiple of 4 cells so that
+//     every chunk starts 16-byte aligned) that are dealt round-robin to the CTA's warps;
+//   * every warp runs its OWN pipeline with no block-wide barrier: 1-D TMA bulk loads
+//     (cp.async.bulk + mbarrier) fill a private ring of input stages three chunks ahead, the
+//     warp assembles dL/dy for the chunk in a private output stage and pushes it back with a
+//     TMA bulk store.  Every byte of y is read once and every byte of dy written once, fully
+//     coalesced, with no zero-fill pass over dy;
+//   * the CTA's slice of the CSR offsets and its ground-truth records are staged in shared
+//     memory once, so the per-chunk work never waits on global memory;
+//   * the partial sums go through a last-block-done reduction in a fixed order (deterministic).
 //
-// Work split inside a chunk:
-//   phase 1: one thread per predictor row (v2) / per cell (v1): conf = sigmoid(to), the dense
-//            no-object term and its gradient, zeros everywhere else;
-//   phase 2: one warp per ground-truth record that falls into the chunk (records of one cell
-//            always go to the same warp, in CSR order, so collisions accumulate
-//            deterministically): lanes decode the A boxes of the cell, compute IoU against the
-//            record, shuffle-argmax the responsible predictor, lanes then cover the C classes
-//            for the softmax/class term, and the warp adds its sparse gradient rows.
+// Per mini-chunk a warp does
+//   dense pass : one lane per predictor row (v2) / cell (v1): conf = sigmoid(to), the no-object
+//                term and its gradient, zeros elsewhere;
+//   sparse pass: ground-truth records whose cell lies in the chunk, in CSR order (so collisions
+//                on one predictor accumulate deterministically): lanes decode the A boxes of the
+//                cell, IoU against the record, shuffle-argmax picks the responsible predictor,
+//                lanes then cover the C classes for the softmax/class term.
 #include "yh_common.cuh"
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
-constexpr int kChunkBytes = 16 * 1024;
+constexpr int kMaxWarps = 8;
+constexpr int kInStages = 3;
+constexpr int kOutStages = 2;
+constexpr int kStageBytesTarget = 4096;
 constexpr int kMaxGrid = 1024;
-constexpr int kPartials = 8;  // floats per CTA in the workspace (6 used)
+constexpr int kPartials = 8;     // floats per CTA in the workspace (6 used)
+constexpr int kOffCap = 128;     // CSR offsets cached per CTA (images + 1)
+constexpr int kGtCap = 384;      // ground-truth records cached per CTA (18 KB)
+constexpr int kClsRegs = 4;      // class logits per lane kept in registers (C <= 128)
 
 struct TrainParams {
     YhGeom g;
@@ -47,11 +52,12 @@ struct TrainParams {
     unsigned int* ticket;
     long long total_cells;
     long long quads_total;  // ceil(total_cells / 4)
-    int cells_per_chunk;    // multiple of 4
+    int mc;                 // cells per mini-chunk (multiple of 4)
+    int warps;              // warps per CTA
     int tma_in, tma_out;    // base pointers 16-byte aligned
     float lam[5];
     double inv_den[5];      // 1/(2M), 1/(2M), 1/M, 1/(M(P-1)), 1/M
-    float cxy, cwh, cconf, cno, ccls;  // gradient coefficients (see below)
+    float cxy, cwh, cconf, cno, ccls;  // gradient coefficients (see train_impl)
 };
 
 // "a beats b" for torch.max semantics: larger wins, NaN beats everything, first index on ties
@@ -61,276 +67,376 @@ __device__ __forceinline__ bool yh_better(float va, int ia, float vb, int ib) {
     return va > vb || (va == vb && ia < ib);
 }
 
-template <int STAGES_IN, int STAGES_OUT, bool WRITE_DY>
-__global__ void __launch_bounds__(kThreads)
-yh_train_kernel(const TrainParams p) {
+struct WarpSums {
+    float no, xy, wh, conf, nr, cls;
+};
+
+// One ground-truth record against its cell (all 32 lanes cooperate).  `cellp` / `ocell` point at
+// the cell's floats in the input / output stage.
+template <bool WRITE_DY>
+__device__ __forceinline__ void process_record(const TrainParams& p, const YhGt* rec, int jj,
+                                               const float* cellp, float* ocell, int lane, WarpSums& s) {
+    const YhGeom& g = p.g;
+    const int A = g.a, C = g.c, bs = g.box_stride;
+    const int4 hd = *reinterpret_cast<const int4*>(rec);             // img, cy, cx, cls
+    const float4 tt = *(reinterpret_cast<const float4*>(rec) + 1);   // stx, sty, tw, th
+    const float4 bb = *(reinterpret_cast<const float4*>(rec) + 2);   // x1, y1, x2, y2
+
+    // lanes < A: decode the box of anchor `lane` and its IoU with the record
+    float sx = 0.f, sy = 0.f, wa = 0.f, ha = 0.f, conf = 0.f;
+    float iou = -INFINITY;
+    int best = 1 << 20;
+    if (lane < A) {
+        const float* bp = cellp + lane * bs;
+        sx = yh_sigmoid(bp[0]);
+        sy = yh_sigmoid(bp[1]);
+        if (g.version == 2) {
+            wa = expf(bp[2]);
+            ha = expf(bp[3]);
+        } else {
+            wa = yh_sigmoid(bp[2]);
+            ha = yh_sigmoid(bp[3]);
+        }
+        conf = yh_sigmoid(bp[4]);
+        const YhBox pb = yh_decode_box(sx, sy, wa, ha, g.pw[lane], g.ph[lane], hd.z, hd.y, g.gw, g.gh);
+        const YhBox gb{bb.x, bb.y, bb.z, bb.w};
+        iou = yh_iou_xyxy(pb, gb);
+        best = lane;
+    }
+    float bv = iou;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, best, o);
+        if (yh_better(ov, oi, bv, best)) { bv = ov; best = oi; }
+    }
+    const int r = best;  // responsible predictor (uniform across the warp)
+    sx = __shfl_sync(0xffffffffu, sx, r);
+    sy = __shfl_sync(0xffffffffu, sy, r);
+    wa = __shfl_sync(0xffffffffu, wa, r);
+    ha = __shfl_sync(0xffffffffu, ha, r);
+    conf = __shfl_sync(0xffffffffu, conf, r);
+    const float iou_r = bv;
+
+    // class term: softmax over C logits, lanes stride the classes (logits cached in registers)
+    const int coff = g.version == 2 ? r * bs + 5 : 5 * A;
+    const float* cl = cellp + coff;
+    float lg[kClsRegs];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < kClsRegs; ++k) {
+        const int c = lane + 32 * k;
+        lg[k] = c < C ? cl[c] : -INFINITY;
+        mx = fmaxf(mx, lg[k]);
+    }
+    for (int c = lane + 32 * kClsRegs; c < C; c += 32) mx = fmaxf(mx, cl[c]);
+    mx = yh_warp_max(mx);
+    float se = 0.f;
+#pragma unroll
+    for (int k = 0; k < kClsRegs; ++k) {
+        lg[k] = lane + 32 * k < C ? expf(lg[k] - mx) : 0.f;
+        se += lg[k];
+    }
+    for (int c = lane + 32 * kClsRegs; c < C; c += 32) se += expf(cl[c] - mx);
+    se = yh_warp_sum(se);
+    float sq = 0.f, dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < kClsRegs; ++k) {
+        const int c = lane + 32 * k;
+        if (c < C) {
+            lg[k] = __fdiv_rn(lg[k], se);  // p_c
+            const float gg = lg[k] - (c == hd.w ? 1.f : 0.f);
+            sq += gg * gg;
+            dot += gg * lg[k];
+        }
+    }
+    for (int c = lane + 32 * kClsRegs; c < C; c += 32) {
+        const float pc = __fdiv_rn(expf(cl[c] - mx), se);
+        const float gg = pc - (c == hd.w ? 1.f : 0.f);
+        sq += gg * gg;
+        dot += gg * pc;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    }
+
+    if (lane == 0) {
+        float tw_t, th_t;
+        if (g.version == 2) {  // sqrt(bwbh / pwph), models/yolov2.py:946-947
+            tw_t = __fsqrt_rn(__fdiv_rn(tt.z, g.pw[r]));
+            th_t = __fsqrt_rn(__fdiv_rn(tt.w, g.ph[r]));
+        } else {               // sqrt(sig_twth), models/yolov1.py:760-761
+            tw_t = __fsqrt_rn(tt.z);
+            th_t = __fsqrt_rn(tt.w);
+        }
+        const float sqw = __fsqrt_rn(wa), sqh = __fsqrt_rn(ha);
+        const float dx = sx - tt.x, dyv = sy - tt.y;
+        const float dw = sqw - tw_t, dh = sqh - th_t;
+        const float dc = conf - iou_r;
+        s.xy += dx * dx + dyv * dyv;
+        s.wh += dw * dw + dh * dh;
+        s.conf += dc * dc;
+        s.nr += conf * conf;
+        s.cls += sq;
+        if (p.resp) p.resp[jj] = r;
+        if (p.iou_resp) p.iou_resp[jj] = iou_r;
+        if (WRITE_DY) {
+            float* row = ocell + r * bs;
+            row[0] += p.cxy * dx * sx * (1.f - sx);
+            row[1] += p.cxy * dyv * sy * (1.f - sy);
+            if (g.version == 2) {
+                row[2] += p.cwh * dw * sqw;
+                row[3] += p.cwh * dh * sqh;
+            } else {
+                row[2] += p.cwh * dw * sqw * (1.f - wa);
+                row[3] += p.cwh * dh * sqh * (1.f - ha);
+            }
+            row[4] += (p.cconf * dc - p.cno * conf) * conf * (1.f - conf);
+        }
+    }
+    if (WRITE_DY) {
+        float* ocl = ocell + coff;
+#pragma unroll
+        for (int k = 0; k < kClsRegs; ++k) {
+            const int c = lane + 32 * k;
+            if (c < C) ocl[c] += p.ccls * lg[k] * (lg[k] - (c == hd.w ? 1.f : 0.f) - dot);
+        }
+        for (int c = lane + 32 * kClsRegs; c < C; c += 32) {
+            const float pc = __fdiv_rn(expf(cl[c] - mx), se);
+            ocl[c] += p.ccls * pc * (pc - (c == hd.w ? 1.f : 0.f) - dot);
+        }
+    }
+    __syncwarp();
+}
+
+template <bool WRITE_DY>
+__global__ void __launch_bounds__(kMaxWarps * 32, 1) yh_train_kernel(const TrainParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ int s_off[kOffCap];
+    __shared__ __align__(16) YhGt s_gt[kGtCap];
+    __shared__ int s_cell[kGtCap];  // flat cell index (image * cells + cy * s_w + cx) of each cached record
+    __shared__ float red[kMaxWarps * 6];
+    __shared__ bool is_last;
+
     const YhGeom& g = p.g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int cf = g.cell_floats;
-    const int chunk_floats = p.cells_per_chunk * cf;  // multiple of 4 floats
+    const int W = p.warps;
+    const int cf = g.cell_floats, bs = g.box_stride, A = g.a, cells = g.cells;
+    const int mc = p.mc;
+    const int S = mc * cf;  // floats per stage (multiple of 4)
 
-    float* in_ring = reinterpret_cast<float*>(smem_raw);
-    float* out_ring = in_ring + (size_t)STAGES_IN * chunk_floats;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(out_ring + (WRITE_DY ? (size_t)STAGES_OUT * chunk_floats : 0));
-    float* red = reinterpret_cast<float*>(bars + STAGES_IN);  // [kWarps][6]
+    // shared-memory carve-up: per warp kInStages input stages (+ kOutStages output stages)
+    float* in_base = reinterpret_cast<float*>(smem_raw) + (size_t)warp * kInStages * S;
+    float* out_base = reinterpret_cast<float*>(smem_raw) + (size_t)W * kInStages * S + (size_t)warp * kOutStages * S;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(smem_raw) +
+                                                 (size_t)W * (kInStages + (WRITE_DY ? kOutStages : 0)) * S) +
+                     warp * kInStages;
 
-    // this CTA's contiguous cell range (in quads of cells so chunk starts stay 16-B aligned)
-    const long long q0 = p.quads_total * blockIdx.x / gridDim.x;
-    const long long q1 = p.quads_total * (blockIdx.x + 1) / gridDim.x;
-    const long long cta_cell0 = q0 * 4;
-    const long long cta_cell1 = min(q1 * 4, p.total_cells);
-    const long long cta_cells = cta_cell1 - cta_cell0;
-    const int nchunks = cta_cells > 0 ? (int)((cta_cells + p.cells_per_chunk - 1) / p.cells_per_chunk) : 0;
+    // this CTA's contiguous cell range (in quads of cells so chunk starts stay 16-B aligned);
+    // everything below is 32-bit: train_impl checks that the tensor has < 2^31 floats
+    const int q0 = (int)((long long)p.quads_total * blockIdx.x / gridDim.x);
+    const int q1 = (int)((long long)p.quads_total * (blockIdx.x + 1) / gridDim.x);
+    const int cta_cell0 = q0 * 4;
+    const int cta_cell1 = min(q1 * 4, (int)p.total_cells);
+    const int cta_cells = cta_cell1 - cta_cell0;
+    const int nmini = cta_cells > 0 ? (cta_cells + mc - 1) / mc : 0;
+    const int my_n = nmini > warp ? (nmini - warp + W - 1) / W : 0;  // mini-chunks of this warp
 
-    if (tid == 0) {
-        for (int s = 0; s < STAGES_IN; ++s) yh_mbar_init(&bars[s], 1);
-        yh_mbar_fence_init();
-    }
-    __syncthreads();
-
-    auto issue_load = [&](int ci) {  // thread 0 only
-        const long long c0 = cta_cell0 + (long long)ci * p.cells_per_chunk;
-        const int nc = (int)min((long long)p.cells_per_chunk, cta_cell1 - c0);
+    auto issue_load = [&](int k) {  // lane 0 only: mini-chunk k of this warp into stage k % kInStages
+        const int c0 = cta_cell0 + (warp + k * W) * mc;
+        const int nc = min(mc, cta_cell1 - c0);
         const uint32_t bytes = ((uint32_t)nc * cf * 4u) & ~15u;
-        uint64_t* bar = &bars[ci % STAGES_IN];
+        uint64_t* bar = &bars[k % kInStages];
         if (bytes) {
             yh_mbar_expect_tx(bar, bytes);
-            yh_bulk_load(in_ring + (size_t)(ci % STAGES_IN) * chunk_floats, p.y + c0 * cf, bytes, bar);
+            yh_bulk_load(in_base + (k % kInStages) * S, p.y + (size_t)c0 * cf, bytes, bar);
         } else {
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(yh_smem_u32(bar)) : "memory");
         }
     };
-    if (p.tma_in && tid == 0) {
-        const int pre = nchunks < STAGES_IN ? nchunks : STAGES_IN;
-        for (int ci = 0; ci < pre; ++ci) issue_load(ci);
+    if (p.tma_in && lane == 0) {
+        for (int s = 0; s < kInStages; ++s) yh_mbar_init(&bars[s], 1);
+        yh_mbar_fence_init();
+        const int pre = my_n < kInStages ? my_n : kInStages;
+        for (int k = 0; k < pre; ++k) issue_load(k);
+    }
+    if (WRITE_DY) {  // output stages start out all-zero and are kept that way between chunks
+        float4* o4 = reinterpret_cast<float4*>(out_base);
+        for (int i = lane; i < kOutStages * S / 4; i += 32) o4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 
-    // partial sums: s_no is per thread, the rest live in lane 0 of each warp
-    float s_no = 0.f, s_xy = 0.f, s_wh = 0.f, s_conf = 0.f, s_nr = 0.f, s_cls = 0.f;
-    const int cells = g.cells;
-    const int bs = g.box_stride;
-    const int A = g.a, C = g.c;
+    // ---- stage the CTA's CSR offsets and ground-truth records in shared memory ----
+    const int n_first = cta_cells > 0 ? cta_cell0 / cells : 0;
+    const int n_last = cta_cells > 0 ? (cta_cell1 - 1) / cells : -1;
+    const int n_imgs = n_last - n_first + 1;
+    const bool off_cached = n_imgs + 1 <= kOffCap;
+    if (off_cached)
+        for (int i = tid; i <= n_imgs; i += blockDim.x) s_off[i] = __ldg(p.gt_off + n_first + i);
+    __syncthreads();
+    const int rec0 = n_imgs > 0 ? (off_cached ? s_off[0] : __ldg(p.gt_off + n_first)) : 0;
+    const int rec1 = n_imgs > 0 ? (off_cached ? s_off[n_imgs] : __ldg(p.gt_off + n_last + 1)) : 0;
+    const bool gt_cached = rec1 - rec0 <= kGtCap;
+    if (gt_cached) {
+        const int4* src = reinterpret_cast<const int4*>(p.gt + rec0);
+        int4* dst = reinterpret_cast<int4*>(s_gt);
+        for (int i = tid; i < (rec1 - rec0) * 3; i += blockDim.x) {
+            const int4 v = __ldg(src + i);
+            dst[i] = v;
+            if (i % 3 == 0) {  // header: img, cy, cx, cls
+                const bool ok = v.y >= 0 && v.y < g.s_h && v.z >= 0 && v.z < g.s_w && v.x >= 0 && v.x < g.n;
+                s_cell[i / 3] = ok ? v.x * cells + v.y * g.s_w + v.z : -1;
+            }
+        }
+    }
+    __syncthreads();
+    auto off_at = [&](int n) -> int { return off_cached ? s_off[n - n_first] : __ldg(p.gt_off + n); };
 
-    for (int ci = 0; ci < nchunks; ++ci) {
-        const long long cell0 = cta_cell0 + (long long)ci * p.cells_per_chunk;
-        const int ncell = (int)min((long long)p.cells_per_chunk, cta_cell1 - cell0);
+    WarpSums sums = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    unsigned touched[kOutStages];  // cells of each output stage that hold sparse gradient rows
+#pragma unroll
+    for (int s = 0; s < kOutStages; ++s) touched[s] = 0u;
+
+    // running position of this warp's current chunk: image n0, first cell rem0 inside it
+    int cell0 = cta_cell0 + warp * mc;
+    int n0 = my_n > 0 ? cell0 / cells : 0;
+    int rem0 = cell0 - n0 * cells;
+    const int step = W * mc;
+    const int rows_per_cell = g.version == 2 ? A : 1;  // dense-pass rows: predictors (v2) / cells (v1)
+    const int row_floats = g.version == 2 ? bs : cf;
+
+    for (int k = 0; k < my_n; ++k) {
+        const int ncell = min(mc, cta_cell1 - cell0);
         const int nfl = ncell * cf;
-        const int nfl16 = nfl & ~3;  // floats covered by the bulk copy
-        float* in = in_ring + (size_t)(ci % STAGES_IN) * chunk_floats;
-        float* out = out_ring + (size_t)(ci % STAGES_OUT) * chunk_floats;
-        const float* ysrc = p.y + cell0 * cf;
-        const int n0 = (int)(cell0 / cells);                      // first image of the chunk
-        const int rem0 = (int)(cell0 - (long long)n0 * cells);    // its first cell inside that image
+        const int nfl16 = nfl & ~3;  // floats covered by the bulk copies
+        const int ist = k % kInStages, ost = k % kOutStages;
+        float* in = in_base + ist * S;
+        float* out = out_base + ost * S;
+        const float* ysrc = p.y + (size_t)cell0 * cf;
 
-        // the out slot is reused every STAGES_OUT chunks: its bulk store must have drained
-        if (WRITE_DY && p.tma_out && tid == 0) yh_bulk_wait_read<STAGES_OUT - 1>();
         if (p.tma_in) {
-            if (tid < nfl - nfl16) in[nfl16 + tid] = __ldg(ysrc + nfl16 + tid);  // <16-B tail
-            yh_mbar_wait(&bars[ci % STAGES_IN], (uint32_t)((ci / STAGES_IN) & 1));
+            if (lane < nfl - nfl16) in[nfl16 + lane] = __ldg(ysrc + nfl16 + lane);  // < 16-B tail
+            yh_mbar_wait(&bars[ist], (uint32_t)((k / kInStages) & 1));
         } else {
-            for (int i = tid; i < nfl; i += kThreads) in[i] = __ldg(ysrc + i);
+            for (int i = lane; i < nfl; i += 32) in[i] = __ldg(ysrc + i);
         }
-        __syncthreads();  // [A] chunk visible to everyone, out slot free
-
-        // ---------------- phase 1: dense no-object term, one row owner per thread ------------
-        if (g.version == 2) {
-            const int nrows = ncell * A;
-            for (int u = tid; u < nrows; u += kThreads) {
-                const int lcell = u / A;
-                const int n = n0 + (rem0 + lcell) / cells;
-                const float kn = (float)(__ldg(p.gt_off + n + 1) - __ldg(p.gt_off + n));
-                const float conf = yh_sigmoid(in[u * bs + 4]);
-                const float c2 = conf * conf;
-                s_no += kn * c2;
-                if (WRITE_DY) {
-                    float* row = out + u * bs;
-                    for (int k = 0; k < bs; ++k) row[k] = 0.f;
-                    row[4] = p.cno * kn * c2 * (1.f - conf);
-                }
+        if (WRITE_DY) {
+            // the out stage is reused every kOutStages chunks: its bulk store must have drained,
+            // then the sparse rows it carried are cleared again
+            if (p.tma_out && lane == 0) yh_bulk_wait_read<kOutStages - 1>();
+            __syncwarp();
+            unsigned m = touched[ost];
+            while (m) {
+                const int c = __ffs(m) - 1;
+                m &= m - 1;
+                for (int q = lane; q < cf; q += 32) out[c * cf + q] = 0.f;
             }
-        } else {
-            for (int u = tid; u < ncell; u += kThreads) {
-                const int n = n0 + (rem0 + u) / cells;
-                const float kn = (float)(__ldg(p.gt_off + n + 1) - __ldg(p.gt_off + n));
-                float* row = out + u * cf;
-                if (WRITE_DY)
-                    for (int k = 0; k < cf; ++k) row[k] = 0.f;
-                for (int b = 0; b < A; ++b) {
-                    const float conf = yh_sigmoid(in[u * cf + b * 5 + 4]);
-                    const float c2 = conf * conf;
-                    s_no += kn * c2;
-                    if (WRITE_DY) row[b * 5 + 4] = p.cno * kn * c2 * (1.f - conf);
-                }
-            }
+            touched[ost] = 0u;
         }
-        __syncthreads();  // [C] dense rows written before the sparse read-modify-writes
+        __syncwarp();
 
-        // ---------------- phase 2: ground-truth records of this chunk, one warp each ---------
+        // ---------------- dense pass: no-object term, one row owner per lane ----------------
         {
-            const int n_first = n0;
-            const int n_last = n0 + (rem0 + ncell - 1) / cells;
-            const int r0 = __ldg(p.gt_off + n_first), r1 = __ldg(p.gt_off + n_last + 1);
+            const int n1 = n0 < n_last ? n0 + 1 : n0;
+            const float kn0 = (float)(off_at(n0 + 1) - off_at(n0));
+            const float kn1 = n1 != n0 ? (float)(off_at(n1 + 1) - off_at(n1)) : kn0;
+            const int rows_in_n0 = (cells - rem0) * rows_per_cell;  // rows before the next image starts
+            const bool two_img = mc <= cells;                        // a chunk then touches <= 2 images
+            const int nrows = ncell * rows_per_cell;
+            for (int u = lane; u < nrows; u += 32) {
+                float kn;
+                if (two_img) kn = u < rows_in_n0 ? kn0 : kn1;
+                else { const int n = n0 + (rem0 + u / rows_per_cell) / cells; kn = (float)(off_at(n + 1) - off_at(n)); }
+                const float* irow = in + u * row_floats;
+                float* orow = out + u * row_floats;
+                if (g.version == 2) {
+                    const float conf = yh_sigmoid(irow[4]);
+                    const float c2 = conf * conf;
+                    sums.no += kn * c2;
+                    if (WRITE_DY) orow[4] = p.cno * kn * c2 * (1.f - conf);
+                } else {
+                    for (int b = 0; b < A; ++b) {
+                        const float conf = yh_sigmoid(irow[b * 5 + 4]);
+                        const float c2 = conf * conf;
+                        sums.no += kn * c2;
+                        if (WRITE_DY) orow[b * 5 + 4] = p.cno * kn * c2 * (1.f - conf);
+                    }
+                }
+            }
+        }
+        __syncwarp();  // dense rows written before the sparse read-modify-writes
+
+        // ---------------- sparse pass: ground-truth records of this chunk ----------------
+        {
+            const int n_hi = n0 + (rem0 + ncell - 1) / cells;
+            const int r0 = off_at(n0), r1 = off_at(n_hi + 1);
             for (int base = r0; base < r1; base += 32) {
                 const int j = base + lane;
                 int lc = -1;
-                bool mine = false;
                 if (j < r1) {
-                    const int4 h = __ldg(reinterpret_cast<const int4*>(p.gt + j));  // img,cy,cx,cls
-                    if (h.y >= 0 && h.y < g.s_h && h.z >= 0 && h.z < g.s_w) {
-                        const long long gc = (long long)h.x * cells + (long long)h.y * g.s_w + h.z - cell0;
-                        if (gc >= 0 && gc < ncell) {
-                            lc = (int)gc;
-                            mine = (lc % kWarps) == warp;
-                        }
+                    int gc;
+                    if (gt_cached) {
+                        gc = s_cell[j - rec0];
+                    } else {
+                        const int4 h = __ldg(reinterpret_cast<const int4*>(p.gt + j));
+                        const bool ok = h.y >= 0 && h.y < g.s_h && h.z >= 0 && h.z < g.s_w && h.x >= 0 && h.x < g.n;
+                        gc = ok ? h.x * cells + h.y * g.s_w + h.z : -1;
                     }
+                    if (gc >= cell0 && gc < cell0 + ncell) lc = gc - cell0;
                 }
-                unsigned bal = __ballot_sync(0xffffffffu, mine);
+                unsigned bal = __ballot_sync(0xffffffffu, lc >= 0);
                 while (bal) {
                     const int b = __ffs(bal) - 1;
                     bal &= bal - 1;
                     const int jj = base + b;
                     const int lcell = __shfl_sync(0xffffffffu, lc, b);
-                    const float4* gp = reinterpret_cast<const float4*>(p.gt + jj);
-                    const int4 hd = __ldg(reinterpret_cast<const int4*>(gp));
-                    const float4 tt = __ldg(gp + 1);  // stx, sty, tw, th
-                    const float4 bb = __ldg(gp + 2);  // x1, y1, x2, y2
-                    const float* cellp = in + lcell * cf;
-
-                    // lanes < A: decode the box of anchor `lane` and its IoU with the record
-                    float sx = 0.f, sy = 0.f, wa = 0.f, ha = 0.f, conf = 0.f;
-                    float iou = -INFINITY;
-                    int best = 1 << 20;
-                    if (lane < A) {
-                        const float* bp = cellp + lane * bs;
-                        sx = yh_sigmoid(bp[0]);
-                        sy = yh_sigmoid(bp[1]);
-                        if (g.version == 2) {
-                            wa = expf(bp[2]);
-                            ha = expf(bp[3]);
-                        } else {
-                            wa = yh_sigmoid(bp[2]);
-                            ha = yh_sigmoid(bp[3]);
-                        }
-                        conf = yh_sigmoid(bp[4]);
-                        const YhBox pb = yh_decode_box(sx, sy, wa, ha, g.pw[lane], g.ph[lane], hd.z, hd.y, g.gw, g.gh);
-                        const YhBox gb{bb.x, bb.y, bb.z, bb.w};
-                        iou = yh_iou_xyxy(pb, gb);
-                        best = lane;
-                    }
-                    float bv = iou;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                        const int oi = __shfl_xor_sync(0xffffffffu, best, o);
-                        if (yh_better(ov, oi, bv, best)) { bv = ov; best = oi; }
-                    }
-                    const int r = best;  // responsible predictor (uniform across the warp)
-                    sx = __shfl_sync(0xffffffffu, sx, r);
-                    sy = __shfl_sync(0xffffffffu, sy, r);
-                    wa = __shfl_sync(0xffffffffu, wa, r);
-                    ha = __shfl_sync(0xffffffffu, ha, r);
-                    conf = __shfl_sync(0xffffffffu, conf, r);
-                    const float iou_r = bv;
-
-                    if (lane == 0) {
-                        float tw_t, th_t;
-                        if (g.version == 2) {  // sqrt(bwbh / pwph), models/yolov2.py:946-947
-                            tw_t = __fsqrt_rn(__fdiv_rn(tt.z, g.pw[r]));
-                            th_t = __fsqrt_rn(__fdiv_rn(tt.w, g.ph[r]));
-                        } else {               // sqrt(sig_twth), models/yolov1.py:760-761
-                            tw_t = __fsqrt_rn(tt.z);
-                            th_t = __fsqrt_rn(tt.w);
-                        }
-                        const float sqw = __fsqrt_rn(wa), sqh = __fsqrt_rn(ha);
-                        const float dx = sx - tt.x, dyv = sy - tt.y;
-                        const float dw = sqw - tw_t, dh = sqh - th_t;
-                        const float dc = conf - iou_r;
-                        s_xy += dx * dx + dyv * dyv;
-                        s_wh += dw * dw + dh * dh;
-                        s_conf += dc * dc;
-                        s_nr += conf * conf;
-                        if (p.resp) p.resp[jj] = r;
-                        if (p.iou_resp) p.iou_resp[jj] = iou_r;
-                        if (WRITE_DY) {
-                            float* row = out + lcell * cf + r * bs;
-                            row[0] += p.cxy * dx * sx * (1.f - sx);
-                            row[1] += p.cxy * dyv * sy * (1.f - sy);
-                            if (g.version == 2) {
-                                row[2] += p.cwh * dw * sqw;
-                                row[3] += p.cwh * dh * sqh;
-                            } else {
-                                row[2] += p.cwh * dw * sqw * (1.f - wa);
-                                row[3] += p.cwh * dh * sqh * (1.f - ha);
-                            }
-                            row[4] += (p.cconf * dc - p.cno * conf) * conf * (1.f - conf);
-                        }
-                    }
-
-                    // class term: softmax over C logits, lanes stride the classes
-                    const int coff = g.version == 2 ? r * bs + 5 : 5 * A;
-                    const float* cl = cellp + coff;
-                    float mx = -INFINITY;
-                    for (int c = lane; c < C; c += 32) mx = fmaxf(mx, cl[c]);
-                    mx = yh_warp_max(mx);
-                    float se = 0.f;
-                    for (int c = lane; c < C; c += 32) se += expf(cl[c] - mx);
-                    se = yh_warp_sum(se);
-                    float sq = 0.f, dot = 0.f;
-                    for (int c = lane; c < C; c += 32) {
-                        const float pc = __fdiv_rn(expf(cl[c] - mx), se);
-                        const float gg = pc - (c == hd.w ? 1.f : 0.f);
-                        sq += gg * gg;
-                        dot += gg * pc;
-                    }
-                    sq = yh_warp_sum(sq);
-                    dot = yh_warp_sum(dot);
-                    if (lane == 0) s_cls += sq;
-                    if (WRITE_DY) {
-                        float* ocl = out + lcell * cf + coff;
-                        for (int c = lane; c < C; c += 32) {
-                            const float pc = __fdiv_rn(expf(cl[c] - mx), se);
-                            const float gg = pc - (c == hd.w ? 1.f : 0.f);
-                            ocl[c] += p.ccls * pc * (gg - dot);
-                        }
-                    }
-                    __syncwarp();
+                    const YhGt* rec = gt_cached ? s_gt + (jj - rec0) : p.gt + jj;
+                    process_record<WRITE_DY>(p, rec, jj, in + lcell * cf, out + lcell * cf, lane, sums);
+                    touched[ost] |= 1u << lcell;
                 }
             }
         }
-        __syncthreads();  // [D] dy chunk complete; nobody reads `in` any more
 
+        // ---------------- push the chunk's dL/dy, refill the input stage ----------------
         if (WRITE_DY) {
-            float* ydst = p.dy + cell0 * cf;
+            float* ydst = p.dy + (size_t)cell0 * cf;
             if (p.tma_out) {
-                if (tid == 0) {
-                    yh_fence_proxy_async();
+                yh_fence_proxy_async();  // every lane: its generic-proxy writes -> async proxy
+                __syncwarp();
+                if (lane == 0) {
                     if (nfl16) yh_bulk_store(ydst, out, (uint32_t)nfl16 * 4u);
                     yh_bulk_commit();
                 }
-                if (tid < nfl - nfl16) ydst[nfl16 + tid] = out[nfl16 + tid];
+                if (lane < nfl - nfl16) ydst[nfl16 + lane] = out[nfl16 + lane];
             } else {
-                for (int i = tid; i < nfl; i += kThreads) ydst[i] = out[i];
+                __syncwarp();
+                for (int i = lane; i < nfl; i += 32) ydst[i] = out[i];
             }
+        } else {
+            __syncwarp();
         }
-        if (p.tma_in && tid == 0 && ci + STAGES_IN < nchunks) issue_load(ci + STAGES_IN);
+        if (p.tma_in && lane == 0 && k + kInStages < my_n) issue_load(k + kInStages);
+
+        cell0 += step;
+        rem0 += step;
+        while (rem0 >= cells) { rem0 -= cells; ++n0; }
     }
-    if (WRITE_DY && p.tma_out && tid == 0) yh_bulk_wait_all<0>();
+    if (WRITE_DY && p.tma_out && lane == 0) yh_bulk_wait_all<0>();
 
     // ---------------- block reduction of the six partial sums ----------------
-    s_no = yh_warp_sum(s_no);
+    const float s_no = yh_warp_sum(sums.no);
     if (lane == 0) {
         float* r = red + warp * 6;
-        r[0] = s_xy; r[1] = s_wh; r[2] = s_conf; r[3] = s_no; r[4] = s_nr; r[5] = s_cls;
+        r[0] = sums.xy; r[1] = sums.wh; r[2] = sums.conf; r[3] = s_no; r[4] = sums.nr; r[5] = sums.cls;
     }
     __syncthreads();
-    __shared__ bool is_last;
     if (tid == 0) {
         float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int w = 0; w < kWarps; ++w)
-            for (int k = 0; k < 6; ++k) acc[k] += red[w * 6 + k];
+        for (int w = 0; w < W; ++w)
+            for (int q = 0; q < 6; ++q) acc[q] += red[w * 6 + q];
         float* dst = p.partials + (size_t)blockIdx.x * kPartials;
-        for (int k = 0; k < 6; ++k) dst[k] = acc[k];
+        for (int q = 0; q < 6; ++q) dst[q] = acc[q];
         __threadfence();
         const unsigned t = atomicAdd(p.ticket, 1u);
         is_last = (t == gridDim.x - 1);
@@ -341,10 +447,10 @@ yh_train_kernel(const TrainParams p) {
         double acc[6] = {0, 0, 0, 0, 0, 0};
         for (unsigned b = lane; b < gridDim.x; b += 32) {
             const float* src = p.partials + (size_t)b * kPartials;
-            for (int k = 0; k < 6; ++k) acc[k] += (double)__ldcg(src + k);
+            for (int q = 0; q < 6; ++q) acc[q] += (double)__ldcg(src + q);
         }
-        for (int k = 0; k < 6; ++k)
-            for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+        for (int q = 0; q < 6; ++q)
+            for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
         if (lane == 0) {
             const double t0 = acc[0] * p.inv_den[0];
             const double t1 = acc[1] * p.inv_den[1];
@@ -359,20 +465,19 @@ yh_train_kernel(const TrainParams p) {
     }
 }
 
-template <int SI, int SO, bool W>
+template <bool W>
 int launch_variant(const TrainParams& p, int grid, size_t smem, cudaStream_t stream) {
     static size_t configured[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) dev = 0;
     if (smem > configured[dev]) {
-        int rc = yh_check_cuda(cudaFuncSetAttribute(yh_train_kernel<SI, SO, W>,
-                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+        int rc = yh_check_cuda(cudaFuncSetAttribute(yh_train_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                                "cudaFuncSetAttribute(train)");
         if (rc) return rc;
         configured[dev] = smem;
     }
-    yh_train_kernel<SI, SO, W><<<grid, kThreads, smem, stream>>>(p);
+    yh_train_kernel<W><<<grid, p.warps * 32, smem, stream>>>(p);
     return yh_check_cuda(cudaGetLastError(), "yh_train launch");
 }
 
@@ -401,9 +506,11 @@ int train_impl(int version, const float* y, int n, int s_h, int s_w, int a, int 
     p.total_cells = (long long)n * p.g.cells;
     p.quads_total = (p.total_cells + 3) / 4;
     const int cf = p.g.cell_floats;
-    int qpc = kChunkBytes / (16 * cf);
+    int qpc = kStageBytesTarget / (16 * cf);  // quads of cells per mini-chunk
     if (qpc < 1) qpc = 1;
-    p.cells_per_chunk = qpc * 4;
+    if (qpc > 8) qpc = 8;  // <= 32 cells per mini-chunk: the kernel tracks touched cells in one word
+    p.mc = qpc * 4;
+    YH_REQUIRE(p.total_cells * cf < (1ll << 31), YH_ERR_UNSUPPORTED, "head tensor has 2^31 or more floats");
     p.tma_in = ((uintptr_t)y & 15) == 0;
     p.tma_out = dy && ((uintptr_t)dy & 15) == 0;
 
@@ -423,35 +530,24 @@ int train_impl(int version, const float* y, int n, int s_h, int s_w, int a, int 
     p.cno = (float)(lambdas_host[3] * 2.0 / (M * P1));
     p.ccls = (float)(lambdas_host[4] * 2.0 / M);
 
-    const size_t chunk_bytes = (size_t)p.cells_per_chunk * cf * 4;
-    const long long nchunks_total = (p.quads_total + qpc - 1) / qpc;
-    const int sms = yh_sm_count();
-    const size_t tail = 8 * 8 + kWarps * 6 * 4 + 64;
-    cudaStream_t st = (cudaStream_t)stream;
+    // warps per CTA: as many private pipelines as fit in shared memory
+    const size_t stage_bytes = (size_t)p.mc * cf * 4;
+    const int stages = kInStages + (dy ? kOutStages : 0);
+    const size_t budget = 200 * 1024;
+    int warps = kMaxWarps;
+    while (warps > 1 && (size_t)warps * stages * stage_bytes + 8 * kInStages * warps + 16 > budget) warps >>= 1;
+    const size_t smem = (size_t)warps * stages * stage_bytes + 8 * kInStages * warps + 16;
+    YH_REQUIRE(smem <= budget, YH_ERR_UNSUPPORTED, "cell too wide for shared memory (%d floats per cell)", cf);
+    p.warps = warps;
 
-    // ring depth: as deep as fits two CTAs per SM, shallower for very wide cells
-    if (dy) {
-        if ((4 + 2) * chunk_bytes + tail <= 110 * 1024) {
-            int grid = (int)min((long long)sms * 2, nchunks_total);
-            if (grid > kMaxGrid) grid = kMaxGrid;
-            return launch_variant<4, 2, true>(p, grid, 6 * chunk_bytes + tail, st);
-        }
-        YH_REQUIRE((2 + 2) * chunk_bytes + tail <= 227 * 1024, YH_ERR_UNSUPPORTED,
-                   "cell too wide for shared memory (%d floats per cell)", cf);
-        int grid = (int)min((long long)sms, nchunks_total);
-        if (grid > kMaxGrid) grid = kMaxGrid;
-        return launch_variant<2, 2, true>(p, grid, 4 * chunk_bytes + tail, st);
-    }
-    if (6 * chunk_bytes + tail <= 110 * 1024) {
-        int grid = (int)min((long long)sms * 2, nchunks_total);
-        if (grid > kMaxGrid) grid = kMaxGrid;
-        return launch_variant<6, 2, false>(p, grid, 6 * chunk_bytes + tail, st);
-    }
-    YH_REQUIRE(2 * chunk_bytes + tail <= 227 * 1024, YH_ERR_UNSUPPORTED,
-               "cell too wide for shared memory (%d floats per cell)", cf);
-    int grid = (int)min((long long)sms, nchunks_total);
+    const long long nmini_total = (p.quads_total + qpc - 1) / qpc;
+    long long grid = (nmini_total + warps - 1) / warps;  // at least one mini-chunk per warp
+    const int sms = yh_sm_count();
+    if (grid > sms) grid = sms;
     if (grid > kMaxGrid) grid = kMaxGrid;
-    return launch_variant<2, 2, false>(p, grid, 2 * chunk_bytes + tail, st);
+    if (grid < 1) grid = 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    return dy ? launch_variant<true>(p, (int)grid, smem, st) : launch_variant<false>(p, (int)grid, smem, st);
 }
 
 }  // namespace

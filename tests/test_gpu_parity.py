@@ -460,3 +460,28 @@ def test_cuda_graph_capture_of_a_step(cuda_device):
     cnt = eager_post["keep_cnt"].cpu().numpy()
     for n in range(case.n):
         assert torch.equal(post["keep_idx"][n, :cnt[n]], eager_post["keep_idx"][n, :cnt[n]])
+
+
+def test_postprocess_tail_and_unaligned_sources(cuda_device):
+    """Tensor sizes that are not a multiple of 16 bytes (the staged window needs a scalar tail),
+    in both the resident (13x13) and the ring (19x19) staging mode, and a 4-byte-aligned view of
+    y (no TMA: direct global reads)."""
+    for case, thr in ((synthetic.make_case("t13", 2, 1, 13, 13, 5, 20, 416, 416, seed=51, to_shift=-1.0), 0.5),
+                      (synthetic.make_case("t19", 2, 1, 19, 19, 5, 20, 608, 608, seed=52, to_shift=-1.0), 0.5),
+                      (synthetic.make_case("t19b", 2, 3, 19, 19, 5, 20, 608, 608, seed=53, to_shift=1.5), 0.6),
+                      (synthetic.make_case("tv1", 1, 3, 7, 7, 2, 20, 448, 448, seed=54, to_shift=0.3), 0.5)):
+        assert (case.y.numel() % 4 != 0) or case.n == 3
+        check_post_vs_oracle(case, thr, 0.45, cuda_device)
+    case = synthetic.cfg3(n=5)
+    base = run_post(case, 0.5, 0.45, cuda_device)
+    buf = torch.zeros(case.y.numel() + 1, device=cuda_device)
+    y = buf[1:].view(case.y.shape)
+    y.copy_(case.y)
+    assert y.data_ptr() % 16 == 4
+    r = ops.postprocess(y, version=2, img_hw=(case.height, case.width), conf_thre=0.5, iou_thre=0.45,
+                        anchors=case.anchors)
+    assert np.array_equal(r["keep_cnt"].cpu().numpy(), base["keep_cnt"])
+    for n in range(case.n):
+        k = base["keep_cnt"][n]
+        assert np.array_equal(r["keep_idx"][n, :k].cpu().numpy(), base["keep_idx"][n, :k])
+        assert np.array_equal(r["score"][n, :k].cpu().numpy(), base["score"][n, :k])
