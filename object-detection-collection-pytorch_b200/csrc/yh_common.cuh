@@ -68,8 +68,8 @@ __device__ __forceinline__ YhBox yh_decode_box(float sx, float sy, float wa, flo
     const float bh = __fmul_rn(ph, ha);
     const float bx = __fadd_rn(sx, (float)cx);
     const float by = __fadd_rn(sy, (float)cy);
-    const float hw = __fdiv_rn(bw, 2.0f);
-    const float hh = __fdiv_rn(bh, 2.0f);
+    const float hw = __fmul_rn(bw, 0.5f);  // bw / 2 of the reference, bit for bit (power of two)
+    const float hh = __fmul_rn(bh, 0.5f);
     YhBox b;
     b.x1 = __fmul_rn(__fsub_rn(bx, hw), gw);
     b.y1 = __fmul_rn(__fsub_rn(by, hh), gh);
