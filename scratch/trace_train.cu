@@ -86,6 +86,13 @@ int main() {
             printf("  slow cta %3d: %lld |", b, ends[i].first);
             for (int w = 0; w < 8; ++w) { long long* t = &tr[((size_t)b * 8 + w) * 64]; printf(" w%d pro %lld first-wait %lld loop %lld", w, t[1]-t[0], t[4]-t[1], t[2]-t[1]); }
             printf("\n");
+            // the slowest warp of this CTA, chunk by chunk
+            int sw = 0; long long best = 0;
+            for (int w = 0; w < 8; ++w) { long long* t = &tr[((size_t)b * 8 + w) * 64]; if (t[2] - t[1] > best) { best = t[2] - t[1]; sw = w; } }
+            long long* t = &tr[((size_t)b * 8 + sw) * 64];
+            printf("     slowest warp %d:", sw);
+            for (int k = 0; k < 9 && t[8 + 5 * k]; ++k) printf(" [w%lld z%lld d%lld s%lld p%lld]", t[4 + 5 * k] - (k == 0 ? t[1] : t[8 + 5 * (k - 1)]), t[5 + 5 * k] - t[4 + 5 * k], t[6 + 5 * k] - t[5 + 5 * k], t[7 + 5 * k] - t[6 + 5 * k], t[8 + 5 * k] - t[7 + 5 * k]);
+            printf("\n");
         }
     }
     printf("warps %d  avg cycles: kernel %.0f (max %lld) prologue %.0f loop %.0f drain %.0f tail %.0f\n", nw, tot_kernel / nw, maxend, tot_pro / nw, tot_loop / nw, tot_drain / nw, tot_tail / nw);

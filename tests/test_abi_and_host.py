@@ -1,0 +1,143 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/yolohead.h declares,
+argument validation works without a GPU, the host-side target/shard logic is right, and the
+N>1 recombination holds over a real 2-process gloo group.  No kernel runs here."""
+import ctypes as C
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+from odcp_b200 import _lib, dist as yh_dist, synthetic, targets
+from oracle import yolo_head_oracle as O
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "yolohead.h")).read()
+    return sorted(set(re.findall(r"YH_API\s+[\w\s\*]+?\b(yh_\w+)\s*\(", text)))
+
+
+def test_header_declares_the_expected_entry_points():
+    syms = header_symbols()
+    for name in ("yh_v2_train", "yh_v1_train", "yh_v2_decode", "yh_v1_decode", "yh_compact_targets",
+                 "yh_v2_postprocess", "yh_v1_postprocess", "yh_nms", "yh_iou", "yh_abi_version", "yh_last_error"):
+        assert name in syms
+    assert sorted(_lib.SIGNATURES) == syms  # the ctypes binding mirrors the header one to one
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.load()
+    raw = C.CDLL(_lib.LIB_PATH)
+    for name in header_symbols():
+        assert getattr(raw, name) is not None, name
+    assert lib.yh_abi_version() == _lib.ABI_VERSION
+    assert lib.yh_train_workspace_bytes() >= 1024
+    assert lib.yh_postprocess_workspace_bytes(4, 845) > 0
+    assert lib.yh_compact_workspace_bytes(10, 4) > 0
+
+
+def test_bad_arguments_are_reported_not_crashed():
+    """Validation happens before anything touches the device: negative code + message."""
+    lib = _lib.load()
+    null = C.c_void_p(0)
+    lam = (C.c_float * 5)(5, 5, 1, .5, 1)
+    anchors = (C.c_float * 10)(*[1.0] * 10)
+    rc = lib.yh_v2_train(null, 1, 13, 13, 5, 20, anchors, 416.0, 416.0, null, null, 0, 0, lam,
+                         null, null, null, null, null, null, 0, null)
+    assert rc < 0 and lib.yh_last_error()
+    rc = lib.yh_v2_train(null, 0, 13, 13, 5, 20, anchors, 416.0, 416.0, null, null, 0, 0, lam,
+                         null, null, null, null, null, null, 0, null)
+    assert rc == -1
+    with pytest.raises(_lib.YoloHeadError):
+        _lib.call("yh_nms", null, null, null, 1, 10, 0.5, 0.5, 10, null, null, null, 0, null)
+
+
+def test_missing_library_is_loud(monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", os.path.join(ROOT, "does_not_exist.so"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.load()
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "object-detection-collection-pytorch_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), (dirpath, f)
+
+
+def test_records_dense_round_trip_and_offsets():
+    case = synthetic.cfg2(n=6)
+    dense = targets.records_to_dense(case.rec, case.n, case.s_h, case.s_w, case.c, 2)
+    obj = dense[4].numpy()
+    assert obj.dtype == np.float64 and obj.sum() == case.m  # one cell per box, fp64 like the reference
+    j = np.arange(case.m)
+    assert np.array_equal(dense[0].numpy()[j, case.rec["cy"], case.rec["cx"], 0], case.rec["stx"])
+    assert np.array_equal(dense[3].numpy()[j, case.rec["cy"], case.rec["cx"]].argmax(-1), case.rec["cls"])
+    off = targets.csr_offsets(case.rec, case.n)
+    assert np.array_equal(off, case.gt_off) and off[-1] == case.m
+    t = targets.records_to_tensor(case.rec)
+    assert t.dtype == torch.int32 and tuple(t.shape) == (case.m, 12)
+    assert np.array_equal(targets.tensor_to_records(t), case.rec)
+    with pytest.raises(ValueError):
+        targets.csr_offsets(case.rec[::-1], case.n)
+
+
+def test_image_shards_cover_the_batch():
+    for n, w in ((256, 8), (7, 2), (5, 4), (3, 8)):
+        spans = [yh_dist.image_shard(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+
+
+def _gloo_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        case = synthetic.with_collisions(synthetic.cfg2(n=12), 6, seed=3)
+        lam = synthetic.DEFAULT_LAMBDAS
+        rec, off, (lo, hi) = yh_dist.shard_case(case.rec, case.gt_off, case.n, rank, world)
+        m_global = yh_dist.global_box_count(len(rec))
+        sub = synthetic.HeadCase("shard", 2, hi - lo, case.s_h, case.s_w, case.a, case.c, case.height,
+                                 case.width, case.y[lo:hi].contiguous(), rec, off, anchors=case.anchors)
+        r = O.train_head_compact(sub, lam, m_global=m_global)  # stands in for the kernel on this rank
+        terms, loss = yh_dist.reduce_terms(torch.tensor(r["terms"], dtype=torch.float32),
+                                           torch.tensor(r["loss"], dtype=torch.float32))
+        dys = [torch.zeros(1) for _ in range(world)] if rank == 0 else None
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (lo, hi, r["dy"]))
+        if rank == 0:
+            full = O.train_head_compact(case, lam)
+            dy = np.concatenate([g[2] for g in sorted(gathered, key=lambda g: g[0])], 0)
+            out.put(dict(m_global=m_global, m=case.m, loss=float(loss), want_loss=full["loss"],
+                         terms=terms.numpy(), want_terms=np.asarray(full["terms"]),
+                         dy_err=float(np.abs(dy - full["dy"]).max() / np.abs(full["dy"]).max())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_shards_recombine_to_the_unsharded_result():
+    """world_size 2 over gloo: shard by image, pass the global box count, all-reduce six floats."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = out.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res["m_global"] == res["m"]
+    assert abs(res["loss"] - res["want_loss"]) <= 1e-5 * abs(res["want_loss"])
+    assert np.allclose(res["terms"], res["want_terms"], rtol=1e-5, atol=0)
+    assert res["dy_err"] <= 1e-5
