@@ -4,60 +4,74 @@
 // Replaces YOLOv2.get_loss / YOLOv1.get_loss and their autograd backward
 // (reference models/yolov2.py:747-1140, models/yolov1.py:556-931, models/utils.py:5-65).
 //
-// The kernel is HBM-bound (~60 flop per 200 bytes), so it is organised around data movement:
-//   * one persistent CTA per SM owns a contiguous range of grid cells of the flattened batch;
-//   * the range is cut into mini-chunks of a few cells (<= ~4 KB, a multiple of 4 cells so that
-//     every chunk starts 16-byte aligned) that are dealt round-robin to the CTA's warps;
-//   * every warp runs its OWN pipeline with no block-wide barrier: 1-D TMA bulk loads
-//     (cp.async.bulk + mbarrier) fill a private ring of input stages three chunks ahead, the
-//     warp assembles dL/dy for the chunk in a private output stage and pushes it back with a
-//     TMA bulk store.  Every byte of y is read once and every byte of dy written once, fully
-//     coalesced, with no zero-fill pass over dy;
-//   * the CTA's slice of the CSR offsets and its ground-truth records are staged in shared
-//     memory once, so the per-chunk work never waits on global memory;
-//   * the partial sums go through a last-block-done reduction in a fixed order (deterministic).
-//
-// Per mini-chunk a warp does
-//   dense pass : one lane per predictor row (v2) / cell (v1): conf = sigmoid(to), the no-object
-//                term and its gradient, zeros elsewhere;
-//   sparse pass: ground-truth records whose cell lies in the chunk, in CSR order (so collisions
-//                on one predictor accumulate deterministically): lanes decode the A boxes of the
-//                cell, IoU against the record, shuffle-argmax picks the responsible predictor,
-//                lanes then cover the C classes for the softmax/class term.
+// The kernel is HBM-bound (~60 flop per 200 bytes) and, at the batch sizes the reference trains
+// with, only a few microseconds long.  Under a saturated memory system every dependent global
+// load costs microseconds (measured: 2-4 us per round trip once ~80 KB per SM are in flight), so
+// the kernel is organised around ONE round trip for everything the sparse part needs:
+//   * the flattened batch of grid cells is cut into tiles of a few dozen cells (a multiple of 4
+//     cells, so every tile starts 16-byte aligned; one tile per CTA at the headline size, a
+//     grid-stride loop over tiles for larger tensors; 4 CTAs of 8 streaming warps + 1 record warp
+//     per SM);
+//   * the record warp's first lane is the TMA producer: one bulk copy brings a speculative window
+//     of ground-truth records (placed where the tile's records sit if boxes are spread evenly over
+//     the images) and goes out FIRST, then the tile itself follows in chunks, each on its own
+//     mbarrier, a bounded number of chunks in flight;
+//   * dense pass (streaming warps): as chunks land, every thread reads float4s from shared memory
+//     and writes the matching float4 of dL/dy straight from registers with coalesced 16-byte
+//     stores.  dL/dy is zero everywhere except the objectness channel, whose no-object gradient
+//     depends only on the thread's own float4 (at most one objectness logit falls into any 4
+//     consecutive floats): every byte of y is read once and every byte of dy written once;
+//   * sparse pass (record warp, concurrently): the tile's records are picked from the window in
+//     CSR order; one record at a time, lanes decode the A boxes of the record's cell from shared
+//     memory, IoU against the record, redux-argmax picks the responsible predictor, the five
+//     lanes of that predictor finish one channel each, lanes then cover the C classes for the
+//     softmax/class term; the 5+C gradient values wait in a shared-memory patch;
+//   * after a CTA barrier the patches overwrite their rows (dense value + record gradient; in
+//     CSR order, so collisions on one predictor accumulate deterministically);
+//   * the six partial sums go through a last-block-done reduction in a fixed order.
 #include <limits.h>
 
 #include "yh_common.cuh"
 
 namespace {
 
-constexpr int kMaxWarps = 8;
-constexpr int kInStages = 3;
-constexpr int kOutStages = 2;
-constexpr int kStageBytesTarget = 4096;
-constexpr int kMaxGrid = 1024;
-constexpr int kPartials = 8;     // floats per CTA in the workspace (6 used)
-constexpr int kOffCap = 128;     // CSR offsets cached per CTA (images + 1)
-constexpr int kGtCap = 384;      // ground-truth records cached per CTA (18 KB)
-constexpr int kWinRegs = 5;      // int4 loads per thread of the speculative record window
-constexpr int kMaskWords = 16;   // chunk-has-records bitmask (<= 512 mini-chunks per CTA)
-constexpr int kClsRegs = 4;      // class logits per lane kept in registers (C <= 128)
-
-// Optional per-warp timeline (scratch/trace_train.cu builds this file with -DYH_TRACE).
-#ifdef YH_TRACE
-__device__ long long g_trace[1024 * kMaxWarps * 64];
-#define YH_TR(slot)                                                                              \
-    do {                                                                                         \
-        if (lane == 0 && (slot) < 64) g_trace[((size_t)blockIdx.x * kMaxWarps + warp) * 64 + (slot)] = clock64(); \
-    } while (0)
-#else
-#define YH_TR(slot) do { } while (0)
+constexpr int kDense = 256;               // streaming threads per CTA
+constexpr int kDenseWarps = kDense / 32;
+constexpr int kThreads = kDense + 32;     // + one record warp
+constexpr int kWarps = kThreads / 32;
+constexpr int kCtasPerSm = 4;
+#ifndef YH_X_CHUNKS
+#define YH_X_CHUNKS 4
 #endif
+#ifndef YH_X_AHEAD
+#define YH_X_AHEAD 2
+#endif
+constexpr int kChunks = YH_X_CHUNKS;      // TMA chunks (mbarriers) per tile
+constexpr int kAhead = YH_X_AHEAD;        // chunks in flight per CTA
+constexpr int kTileBytesMax = 40 * 1024;  // shared-memory stage of one tile
+constexpr int kMaxGrid = 2048;
+constexpr int kPartials = 8;              // floats per CTA in the workspace (6 used)
+constexpr int kClsRegs = 4;               // class logits per lane kept in registers (C <= 128)
+constexpr int kWindow = 128;              // speculative record window (records) per tile
+constexpr int kSlots = 24;                // patches (records processed during the dense pass) per tile
+constexpr int kPatchFloats = 32;          // floats per patch row: 5 + C must fit (else the record waits for the end)
 
-// cells per mini-chunk for a cell of `cf` floats: whole quads of cells, <= kStageBytesTarget bytes,
-// <= 32 cells (the kernel tracks touched cells of a stage in one 32-bit word)
-__host__ __device__ constexpr int mini_cells(int cf) {
-    return 4 * ((kStageBytesTarget / (16 * cf)) < 1 ? 1 : ((kStageBytesTarget / (16 * cf)) > 8 ? 8 : kStageBytesTarget / (16 * cf)));
+#ifdef YH_X_TRACE
+__device__ unsigned long long g_xtrace[4096 * 16];
+__device__ __forceinline__ unsigned long long xt_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
+#define XT_DECL unsigned long long xt_[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define XT(slot) do { if ((threadIdx.x & 31) == 0) xt_[slot] = xt_now(); } while (0)
+#define XT_FLUSH do { if (threadIdx.x == 0) for (int i_ = 0; i_ < 8; ++i_) g_xtrace[blockIdx.x * 16 + i_] = xt_[i_]; \
+                      if (threadIdx.x == kDense) for (int i_ = 0; i_ < 8; ++i_) g_xtrace[blockIdx.x * 16 + 8 + i_] = xt_[i_]; } while (0)
+#else
+#define XT_DECL
+#define XT(slot) do { } while (0)
+#define XT_FLUSH
+#endif
 
 struct TrainParams {
     YhGeom g;
@@ -71,16 +85,13 @@ struct TrainParams {
     float* iou_resp;
     float* partials;      // [gridDim][kPartials]
     unsigned int* ticket;
-    long long total_cells;
-    long long quads_total;  // ceil(total_cells / 4)
-    int mc;                 // cells per mini-chunk (multiple of 4)
-    int m_local;            // records in gt
-    int warps_log2;         // log2(warps per CTA)
-    int q_base, q_extra;    // quads of cells per CTA: q_base (+1 for the first q_extra CTAs)
-    float rec_per_cell;     // m_local / total_cells: where a CTA's records sit if spread evenly
-    int tma_in, tma_out;    // base pointers 16-byte aligned
+    int total_cells;
+    int tile_cells;       // cells per tile (multiple of 4)
+    int num_tiles;
+    int m_local;          // records in gt
+    float rec_per_cell;   // m_local / total_cells: where a tile's records sit if boxes are spread evenly
     float lam[5];
-    double inv_den[5];      // 1/(2M), 1/(2M), 1/M, 1/(M(P-1)), 1/M
+    double inv_den[5];    // 1/(2M), 1/(2M), 1/M, 1/(M(P-1)), 1/M
     float cxy, cwh, cconf, cno, ccls;  // gradient coefficients (see train_impl)
 };
 
@@ -95,50 +106,95 @@ __device__ __forceinline__ int yh_ordered(float f) {
 }
 __device__ __forceinline__ float yh_unordered(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
 
-// One ground-truth record against its cell; all 32 lanes cooperate and the work is laid out for
-// LATENCY (a record sits on the critical path of the warp that owns its chunk):
-//   * lane l < 5A owns ONE activation (anchor l/5, channel l%5), so the 5A exp/sigmoid chains run
-//     side by side; four shuffles hand every lane its anchor's box, the IoU is formed, and two
-//     redux.sync steps pick the responsible anchor (max IoU, then lowest index: torch's first max);
-//   * the five lanes of the responsible anchor then each finish THEIR channel (x, y, w, h, conf:
-//     target transform, squared error, gradient, read-modify-write of the output row) in parallel;
-//     their squared errors accumulate in per-lane registers by channel role (ChannelSums);
-//   * class softmax: lanes stride the classes, max through redux.sync on an order-preserving
-//     integer image, then ONE butterfly for (sum e, sum e^2): with p = e / sum e,
-//       sum_c (p_c - 1[c=t])^2 = S2 - 2 p_t + 1   and   sum_c (p_c - 1[c=t]) p_c = S2 - p_t,
-//     S2 = sum p^2, so no third reduction is needed.
-// `cellp` / `ocell` point at the cell's floats in the input / output stage; `my_pw/my_ph` are the
-// anchor multipliers of this lane's anchor (lane / 5).  Requires 5A <= 32.
+template <bool VEC>
+__device__ __forceinline__ float4 load4(const float* base, int idx4) {
+#ifdef YH_X_CS
+    if (VEC) return __ldcs(reinterpret_cast<const float4*>(base) + idx4);
+#endif
+    if (VEC) return __ldg(reinterpret_cast<const float4*>(base) + idx4);
+    const float* s = base + 4 * idx4;
+    return make_float4(__ldg(s), __ldg(s + 1), __ldg(s + 2), __ldg(s + 3));
+}
+template <bool VEC>
+__device__ __forceinline__ void store4(float* base, int idx4, const float4& v) {
+    if (VEC) {
+#ifdef YH_X_CS
+        __stcs(reinterpret_cast<float4*>(base) + idx4, v);
+#else
+        reinterpret_cast<float4*>(base)[idx4] = v;
+#endif
+    } else {
+        float* d = base + 4 * idx4;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+}
+__device__ __forceinline__ float pick4(const float4& v, int j) {
+    return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w));
+}
+__device__ __forceinline__ void put4(float4& v, int j, float x) {
+    if (j == 0) v.x = x; else if (j == 1) v.y = x; else if (j == 2) v.z = x; else v.w = x;
+}
+
+// No-object part of one objectness logit `t` in an image with `kn` boxes: the term kn * conf^2 and
+// its gradient cno * kn * conf^2 * (1 - conf).  Approximate sigmoid (no decision depends on it) and
+// explicitly rounded steps: the dense pass and the record warp must produce identical bits.
+__device__ __forceinline__ float noobj_term(float t, float kn, float* conf_out) {
+    const float conf = __fdividef(1.0f, __fadd_rn(1.0f, __expf(-t)));
+    *conf_out = conf;
+    return __fmul_rn(__fmul_rn(kn, conf), conf);
+}
+__device__ __forceinline__ float noobj_grad(float w, float conf, float cno) {
+    return __fmul_rn(__fmul_rn(cno, w), __fsub_rn(1.0f, conf));
+}
+
 struct RecordRegs {
     int4 hd;    // img, cy, cx, cls
     float4 tt;  // stx, sty, tw, th
     float4 bb;  // x1, y1, x2, y2
 };
 
-template <bool WRITE_DY>
-__device__ __forceinline__ void process_record(const TrainParams& p, const int version, const int A, const int C,
-                                               const RecordRegs& rr, int jj, const float* cellp, float* ocell,
-                                               int lane, float my_pw, float my_ph, WarpSums& s) {
+// One ground-truth record against its cell; all 32 lanes cooperate and the work is laid out for
+// LATENCY (records are the epilogue of a tile):
+//   * lane l < 5A owns ONE activation (anchor l/5, channel l%5), so the 5A exp/sigmoid chains run
+//     side by side; four shuffles hand every lane its anchor's box, the IoU is formed, and two
+//     redux.sync steps pick the responsible anchor (max IoU, then lowest index: torch's first max);
+//   * as soon as the anchor is known every lane issues its loads of the class logits and of the
+//     dL/dy values it will update, so their latency hides behind the channel arithmetic;
+//   * the five lanes of the responsible anchor each finish THEIR channel (x, y, w, h, conf:
+//     target transform, squared error, gradient) in parallel; their squared errors accumulate in
+//     per-lane registers by channel role;
+//   * class softmax: lanes stride the classes, max through redux.sync on an order-preserving
+//     integer image, then ONE butterfly for (sum e, sum e^2): with p = e / sum e,
+//       sum_c (p_c - 1[c=t])^2 = S2 - 2 p_t + 1   and   sum_c (p_c - 1[c=t]) p_c = S2 - p_t,
+//     S2 = sum p^2, so no third reduction is needed.
+// `ycell` points at the cell's floats of y (in the shared-memory tile), `dcell` at the cell's
+// floats of dy (global memory; holds the dense pass' values, visible after the CTA barrier);
+// `kn` is the box count of the cell's image; `my_pw/my_ph` are the anchor multipliers of this
+// lane's anchor (lane / 5).  Requires 5A <= 32.
+// MODE 0: loss only; 1: add the gradient onto dy in global memory (read-modify-write of the row
+// the dense pass wrote); 2: leave the gradient in the shared-memory patch row `patch` (+ the dense
+// objectness value of the row in *pdense), to be applied after the dense pass.
+template <int MODE>
+__device__ __forceinline__ int process_record(const TrainParams& p, const int version, const int A, const int C,
+                                              const RecordRegs& rr, int jj, const float* ycell,
+                                              float* dcell, float* patch, float* pdense, float kn,
+                                              int lane, float my_pw, float my_ph, WarpSums& s) {
     const YhGeom& g = p.g;
     const int bs = version == 2 ? 5 + C : 5;
-#ifdef YH_TRACE
-    const int warp = threadIdx.x >> 5;
-#endif
-    YH_TR(50);
     const int4 hd = rr.hd;
     const float4 tt = rr.tt;
     const float4 bb = rr.bb;
 
     const int a = lane / 5, q = lane - 5 * a;
     const bool mine = lane < 5 * A;
-    float act = 0.f;
+    float act = 0.f, t_raw = 0.f;
     if (mine) {
-        const float t = cellp[a * bs + q];
+        const float t = ycell[a * bs + q];
+        t_raw = t;
         const bool is_exp = version == 2 && (q == 2 || q == 3);
         const float e = expf(is_exp ? t : -t);
         act = is_exp ? e : __fdiv_rn(1.0f, __fadd_rn(1.0f, e));
     }
-    YH_TR(51);
     const int l0 = mine ? 5 * a : 0;
     const float bx_s = __shfl_sync(0xffffffffu, act, l0);
     const float by_s = __shfl_sync(0xffffffffu, act, l0 + 1);
@@ -152,13 +208,27 @@ __device__ __forceinline__ void process_record(const TrainParams& p, const int v
         iou = yh_iou_xyxy(pb, gb);
         key = iou != iou ? INT_MAX : yh_ordered(iou);
     }
-    YH_TR(52);
     const int best = __reduce_max_sync(0xffffffffu, key);
     const int r = __reduce_min_sync(0xffffffffu, (mine && key == best) ? a : 1 << 20);  // first max
+
+    // loads that depend on r go out now: class logits (and, MODE 1, the dL/dy values to be updated)
+    const int coff = version == 2 ? r * bs + 5 : 5 * A;
+    const float* cl = ycell + coff;
+    float* dcl = dcell + coff;
+    const bool resp_lane = mine && a == r;
+    float old_ch = 0.f;
+    if (MODE == 1 && resp_lane) old_ch = dcell[r * bs + q];
+    float lg[kClsRegs], oldc[kClsRegs];
+#pragma unroll
+    for (int k = 0; k < kClsRegs; ++k) {
+        const int c = lane + 32 * k;
+        lg[k] = c < C ? cl[c] : -INFINITY;
+        oldc[k] = (MODE == 1 && c < C) ? dcl[c] : 0.f;
+    }
     const float iou_r = __shfl_sync(0xffffffffu, iou, 5 * r);
 
     // the five lanes of the responsible anchor finish one channel each
-    if (mine && a == r) {
+    if (resp_lane) {
         float d, grad;
         if (q < 2) {            // x, y: (sigmoid(t) - target)^2, models/yolov2.py:1046-1050
             d = act - (q == 0 ? tt.x : tt.y);
@@ -179,25 +249,22 @@ __device__ __forceinline__ void process_record(const TrainParams& p, const int v
             s.nr += act * act;
             if (p.resp) p.resp[jj] = r;
             if (p.iou_resp) p.iou_resp[jj] = iou_r;
+            if (MODE == 2) {  // what the dense pass writes for this logit
+                float cf_;
+                const float w = noobj_term(t_raw, kn, &cf_);
+                *pdense = noobj_grad(w, cf_, p.cno);
+            }
         }
-        if (WRITE_DY) ocell[r * bs + q] += grad;
+        if (MODE == 1) dcell[r * bs + q] = __fadd_rn(old_ch, grad);  // (explicit add: MODE 1 and 2 must round alike)
+        if (MODE == 2) patch[q] = grad;
     }
-    YH_TR(53);
 
     // class term
-    const int coff = version == 2 ? r * bs + 5 : 5 * A;
-    const float* cl = cellp + coff;
-    float lg[kClsRegs];
     float mx = -INFINITY;
 #pragma unroll
-    for (int k = 0; k < kClsRegs; ++k) {
-        const int c = lane + 32 * k;
-        lg[k] = c < C ? cl[c] : -INFINITY;
-        mx = fmaxf(mx, lg[k]);
-    }
+    for (int k = 0; k < kClsRegs; ++k) mx = fmaxf(mx, lg[k]);
     for (int c = lane + 32 * kClsRegs; c < C; c += 32) mx = fmaxf(mx, cl[c]);
     mx = yh_unordered(__reduce_max_sync(0xffffffffu, yh_ordered(mx)));
-    YH_TR(54);
     float s1 = 0.f, s2 = 0.f, et = 0.f;  // sum e, sum e^2, e of the target class (owning lane only)
 #pragma unroll
     for (int k = 0; k < kClsRegs; ++k) {
@@ -218,7 +285,6 @@ __device__ __forceinline__ void process_record(const TrainParams& p, const int v
         s1 += __shfl_xor_sync(0xffffffffu, s1, o);
         s2 += __shfl_xor_sync(0xffffffffu, s2, o);
     }
-    YH_TR(55);
     const bool has_t = hd.w >= 0 && hd.w < C;
     et = __shfl_sync(0xffffffffu, et, has_t ? (hd.w & 31) : 0);
     const float inv = __fdiv_rn(1.0f, s1);
@@ -226,348 +292,351 @@ __device__ __forceinline__ void process_record(const TrainParams& p, const int v
     const float pt = has_t ? et * inv : 0.f;
     const float dot = S2 - pt;
     if (lane == 0) s.cls += S2 - 2.f * pt + (has_t ? 1.f : 0.f);
-    YH_TR(56);
-    if (WRITE_DY) {
-        float* ocl = ocell + coff;
+    if (MODE == 1) {
 #pragma unroll
         for (int k = 0; k < kClsRegs; ++k) {
             const int c = lane + 32 * k;
             if (c < C) {
                 const float pc = lg[k] * inv;
-                ocl[c] += p.ccls * pc * (pc - (c == hd.w ? 1.f : 0.f) - dot);
+                dcl[c] = __fadd_rn(oldc[k], p.ccls * pc * (pc - (c == hd.w ? 1.f : 0.f) - dot));
             }
         }
         for (int c = lane + 32 * kClsRegs; c < C; c += 32) {
             const float pc = expf(cl[c] - mx) * inv;
-            ocl[c] += p.ccls * pc * (pc - (c == hd.w ? 1.f : 0.f) - dot);
+            dcl[c] = __fadd_rn(dcl[c], p.ccls * pc * (pc - (c == hd.w ? 1.f : 0.f) - dot));
         }
     }
+    if (MODE == 2 && lane < C) {  // 5 + C <= kPatchFloats: one class per lane
+        const float pc = lg[0] * inv;
+        patch[5 + lane] = p.ccls * pc * (pc - (lane == hd.w ? 1.f : 0.f) - dot);
+    }
     __syncwarp();
-    YH_TR(57);
+    return r;
 }
 
 // TV/TA/TC != 0 fix version / boxes per cell / classes at compile time (index arithmetic folds,
-// divisions become shifts and multiplies); 0 keeps them as run-time values from the geometry.
-template <bool WRITE_DY, int TV, int TA, int TC>
-__global__ void __launch_bounds__(kMaxWarps * 32, 1) yh_train_kernel(const TrainParams p) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ int s_off[kOffCap];
-    __shared__ __align__(16) YhGt s_gt[kGtCap];
-    __shared__ unsigned int s_chunkmask[kMaskWords];  // mini-chunks of this CTA that contain records
-    __shared__ int s_cell[kGtCap];  // flat cell index (image * cells + cy * s_w + cx) of each cached record
-    __shared__ float red[kMaxWarps * 6];
+// divisions become multiplies); 0 keeps them as run-time values from the geometry.
+// VEC: y and dy are 16-byte aligned (float4 accesses); otherwise the same code with scalar accesses.
+template <bool WRITE_DY, bool VEC, int TV, int TA, int TC>
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const TrainParams p) {
+    extern __shared__ __align__(128) float s_tile[];  // the tile's slice of y
+    __shared__ __align__(16) int4 s_win[3 * kWindow];  // speculative window of ground-truth records
+    __shared__ __align__(8) uint64_t s_bar[kChunks + 1];  // one mbarrier per chunk, + the window's
+    __shared__ float red[kWarps * 6];
+    __shared__ double dred[kWarps * 6];
+    __shared__ int s_rjj[kWindow];   // the tile's records in CSR order: index into gt ...
+    __shared__ int s_rlc[kWindow];   // ... and tile-local cell
+    __shared__ __align__(16) float s_patch[kSlots * kPatchFloats];  // record gradients waiting for the dense pass
+    __shared__ float s_pdense[kSlots];                            // dense objectness value of a patched row
+    __shared__ int s_pr[kSlots];                                  // responsible anchor of a patch
+    __shared__ int s_nrec, s_npatch;  // records listed (-1: list incomplete, scan gt instead) / patched
+    __shared__ int s_ready;           // tile index + 1 once the record list of that tile is published
     __shared__ bool is_last;
 
     const YhGeom& g = p.g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    YH_TR(0);
-    constexpr bool kFixed = TV != 0 && TA != 0 && TC != 0;
     const int version = TV ? TV : g.version;
     const int A = TA ? TA : g.a, C = TC ? TC : g.c;
     const int bs = version == 2 ? 5 + C : 5;
     const int cf = version == 2 ? A * (5 + C) : 5 * A + C;
     const int cells = g.cells;
-    const int W = kFixed ? kMaxWarps : 1 << p.warps_log2;
-    const int wlog = kFixed ? 3 : p.warps_log2;
-    static_assert(kMaxWarps == 8, "wlog above assumes 8 warps");
-    const int mc = kFixed ? mini_cells(cf) : p.mc;
-    const int S = mc * cf;  // floats per stage (multiple of 4)
+    const int R = p.tile_cells;
+    const int nimg = g.n;
+    const bool record_warp = warp == kDenseWarps;
 
-    // this CTA's contiguous cell range (in quads of cells so chunk starts stay 16-B aligned);
-    // everything below is 32-bit: train_impl checks that the tensor has < 2^31 floats
-    const int bid = blockIdx.x;
-    const int q0 = bid * p.q_base + min(bid, p.q_extra);
-    const int q1 = q0 + p.q_base + (bid < p.q_extra ? 1 : 0);
-    const int cta_cell0 = q0 * 4;
-    const int cta_cell1 = min(q1 * 4, (int)p.total_cells);
-    const int cta_cells = cta_cell1 - cta_cell0;
-
-    // ---- metadata first (before the bulk loads flood the memory system): the CTA's slice of the
-    //      CSR offsets, and -- in the same round trip -- a speculative window of records placed
-    //      where the CTA's records sit if boxes are spread evenly over the images
-    const int n_first = cta_cells > 0 ? cta_cell0 / cells : 0;
-    const int n_last = cta_cells > 0 ? (cta_cell1 - 1) / cells : -1;
-    const int n_imgs = n_last - n_first + 1;
-    const bool off_cached = n_imgs + 1 <= min(kOffCap, (int)blockDim.x);
-    int w0 = 0, wn = 0;
-    if (cta_cells > 0 && p.m_local > 0) {
-        const int cap = min(kGtCap, (int)blockDim.x * kWinRegs / 3);
-        const int mid = (int)(p.rec_per_cell * (float)(cta_cell0 + (cta_cells >> 1)));
-        wn = min(cap, p.m_local);
-        w0 = max(0, min(mid - (cap >> 1), p.m_local - wn));
-    }
-    int4 wv[kWinRegs];
-    {
-        const int4* src = reinterpret_cast<const int4*>(p.gt + w0);
+    XT_DECL;
+    XT(0);
+    if (tid == kDense) {
 #pragma unroll
-        for (int q = 0; q < kWinRegs; ++q) {
-            const int i = tid + q * blockDim.x;
-            wv[q] = i < wn * 3 ? __ldg(src + i) : make_int4(0, 0, 0, 0);
-        }
-    }
-    const int offv = (off_cached && tid <= n_imgs) ? __ldg(p.gt_off + n_first + tid) : 0;
-    YH_TR(58);
-
-    // shared-memory carve-up: per warp kInStages input stages (+ kOutStages output stages)
-    float* in_base = reinterpret_cast<float*>(smem_raw) + warp * kInStages * S;
-    float* out_base = reinterpret_cast<float*>(smem_raw) + W * kInStages * S + warp * kOutStages * S;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(smem_raw) +
-                                                 W * (kInStages + (WRITE_DY ? kOutStages : 0)) * S) +
-                     warp * kInStages;
-    const int nmini = cta_cells > 0 ? (cta_cells + mc - 1) / mc : 0;
-    const int my_n = nmini > warp ? (nmini - warp + W - 1) >> wlog : 0;  // mini-chunks of this warp
-    const int step = W * mc;  // cells between consecutive mini-chunks of one warp
-
-    auto issue_load = [&](int k, int st) {  // lane 0 only: mini-chunk k of this warp into stage st
-        const int c0 = cta_cell0 + warp * mc + k * step;
-        const int nc = min(mc, cta_cell1 - c0);
-        const uint32_t bytes = ((uint32_t)nc * cf * 4u) & ~15u;
-        uint64_t* bar = &bars[st];
-        if (bytes) {
-            yh_mbar_expect_tx(bar, bytes);
-            yh_bulk_load(in_base + st * S, p.y + (size_t)c0 * cf, bytes, bar);
-        } else {
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(yh_smem_u32(bar)) : "memory");
-        }
-    };
-    // every warp's FIRST chunk goes out before anybody's second one: work can start sooner
-    if (p.tma_in && lane == 0) {
-#pragma unroll
-        for (int s = 0; s < kInStages; ++s) yh_mbar_init(&bars[s], 1);
+        for (int c = 0; c <= kChunks; ++c) yh_mbar_init(&s_bar[c], 1);
         yh_mbar_fence_init();
-        if (my_n > 0) issue_load(0, 0);
+        s_ready = 0;
     }
-    YH_TR(49);
-    if (WRITE_DY) {  // output stages start out all-zero and are kept that way between chunks
-        float4* o4 = reinterpret_cast<float4*>(out_base);
-        const int n4 = (kOutStages * S) >> 2;
-        for (int i = lane; i < n4; i += 32) o4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    if (p.tma_in && lane == 0) {
-#pragma unroll
-        for (int k = 1; k < kInStages; ++k)
-            if (k < my_n) issue_load(k, k);
-    }
-    if (tid < kMaskWords) s_chunkmask[tid] = 0u;
-    YH_TR(59);
     __syncthreads();
-    YH_TR(60);
-
-    const bool use_mask = nmini <= 32 * kMaskWords;
-    // flat cell index of a record header (or -1), and "this chunk has records" bookkeeping
-    auto note_record = [&](const int4& h, int slot) {
-        const bool ok = h.y >= 0 && h.y < g.s_h && h.z >= 0 && h.z < g.s_w && h.x >= 0 && h.x < g.n;
-        const int gc = ok ? h.x * cells + h.y * g.s_w + h.z : -1;
-        s_cell[slot] = gc;
-        if (use_mask && gc >= cta_cell0 && gc < cta_cell1) {
-            const int ch = (gc - cta_cell0) / mc;
-            atomicOr(&s_chunkmask[ch >> 5], 1u << (ch & 31));
-        }
-    };
-    if (off_cached && tid <= n_imgs) s_off[tid] = offv;
-#pragma unroll
-    for (int q = 0; q < kWinRegs; ++q) {
-        const int i = tid + q * blockDim.x;
-        if (i < wn * 3) {
-            reinterpret_cast<int4*>(s_gt)[i] = wv[q];
-            if (i % 3 == 0) note_record(wv[q], i / 3);
-        }
-    }
-    YH_TR(61);
-    __syncthreads();
-    YH_TR(62);
-    const int rec0 = n_imgs > 0 ? (off_cached ? s_off[0] : __ldg(p.gt_off + n_first)) : 0;
-    const int rec1 = n_imgs > 0 ? (off_cached ? s_off[n_imgs] : __ldg(p.gt_off + n_last + 1)) : 0;
-    int gt_base = w0;
-    bool gt_cached = rec0 >= w0 && rec1 <= w0 + wn;
-    if (!gt_cached && rec1 - rec0 <= kGtCap) {  // the guess missed: fetch exactly the CTA's records
-        __syncthreads();
-        if (tid < kMaskWords) s_chunkmask[tid] = 0u;
-        __syncthreads();
-        const int4* src = reinterpret_cast<const int4*>(p.gt + rec0);
-        for (int i = tid; i < (rec1 - rec0) * 3; i += blockDim.x) {
-            const int4 v = __ldg(src + i);
-            reinterpret_cast<int4*>(s_gt)[i] = v;
-            if (i % 3 == 0) note_record(v, i / 3);
-        }
-        gt_base = rec0;
-        gt_cached = true;
-        __syncthreads();
-    }
-    const bool have_mask = use_mask && gt_cached;
-    auto off_at = [&](int n) -> int { return off_cached ? s_off[n - n_first] : __ldg(p.gt_off + n); };
-    YH_TR(1);
 
     WarpSums sums = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const float my_pw = lane < 5 * A ? g.pw[lane / 5] : 0.f;  // anchor multipliers of lane / 5
     const float my_ph = lane < 5 * A ? g.ph[lane / 5] : 0.f;
-    unsigned touched0 = 0u, touched1 = 0u;  // cells of output stage 0 / 1 that hold sparse gradient rows
-    static_assert(kOutStages == 2, "touched0/touched1 track exactly two output stages");
+    const bool multi_tile = p.num_tiles > (int)gridDim.x;
+    // records can be processed during the dense pass when their 5+C gradients fit a patch row
+    const bool patchable = WRITE_DY && 5 + C <= kPatchFloats;
+    uint32_t phase = 0;  // parity of the mbarriers: every barrier completes once per tile
 
-    // running state of this warp's current chunk: image n0, first cell rem0 inside it, stages
-    int cell0 = cta_cell0 + warp * mc;
-    int n0 = my_n > 0 ? cell0 / cells : 0;
-    int rem0 = cell0 - n0 * cells;
-    int ist = 0, ost = 0;
-    uint32_t in_phase = 0;
-    const int rows_per_cell = version == 2 ? A : 1;  // dense-pass rows: predictors (v2) / cells (v1)
-    const bool two_img = mc <= cells;                   // a chunk then touches at most two images
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, phase ^= 1u) {
+        // everything is 32-bit: train_impl checks that the tensor has < 2^31 floats
+        const int c0 = t * R;
+        const int nc = min(R, p.total_cells - c0);
+        const int nfl = nc * cf;
+        const int nf4 = nfl >> 2;  // whole float4s; a tail (< 4 floats) exists only at the very end of y
+        const float* yt = p.y + (size_t)c0 * cf;
+        float* dt = p.dy + (size_t)c0 * cf;
+        const int n0 = c0 / cells;
+        const int cells_left = cells - (c0 - n0 * cells);  // cells of image n0 from c0 on
+        const int n_hi = (c0 + nc - 1) / cells;
+        const int ch4 = (nf4 + kChunks - 1) / kChunks;     // float4s per chunk
 
-    for (int k = 0; k < my_n; ++k) {
-        const int ncell = min(mc, cta_cell1 - cell0);
-        const int nfl = ncell * cf;
-        const int ntail = nfl & 3;  // floats past the last 16-byte boundary (last chunk of the tensor only)
-        const int nfl16 = nfl - ntail;
-        float* in = in_base + ist * S;
-        float* out = out_base + ost * S;
-        const float* ysrc = p.y + (size_t)cell0 * cf;
+        // speculative record window of this tile
+        int w0 = (int)(p.rec_per_cell * (float)(c0 + (nc >> 1))) - (kWindow >> 1);
+        w0 = max(0, min(w0, p.m_local - kWindow));
+        const int wn = min(kWindow, p.m_local - w0);
 
-        if (p.tma_in) {
-            if (lane < ntail) in[nfl16 + lane] = __ldg(ysrc + nfl16 + lane);
-            yh_mbar_wait(&bars[ist], in_phase);
-        } else {
-            for (int i = lane; i < nfl; i += 32) in[i] = __ldg(ysrc + i);
-        }
-        YH_TR(4 + 5 * k);
-        if (WRITE_DY) {
-            // the out stage is reused every kOutStages chunks: its bulk store must have drained,
-            // then the sparse rows it carried are cleared again
-            if (p.tma_out && lane == 0) yh_bulk_wait_read<kOutStages - 1>();
-            __syncwarp();
-            unsigned m = ost ? touched1 : touched0;
-            while (m) {
-                const int c = __ffs(m) - 1;
-                m &= m - 1;
-                for (int q = lane; q < cf; q += 32) out[c * cf + q] = 0.f;
-            }
-            if (ost) touched1 = 0u; else touched0 = 0u;
-        }
-        __syncwarp();
-        YH_TR(5 + 5 * k);
-
-        // ---------------- dense pass: no-object term, one row owner per lane ----------------
-        {
-            const int o0 = off_at(n0), o1 = off_at(n0 + 1);
-            const float kn0 = (float)(o1 - o0);
-            const float kn1 = n0 < n_last ? (float)(off_at(n0 + 2) - o1) : kn0;
-            const int rows_in_n0 = (cells - rem0) * rows_per_cell;  // rows before the next image starts
-            const int nrows = ncell * rows_per_cell;
-            auto kn_of = [&](int u) -> float {
-                if (two_img) return u < rows_in_n0 ? kn0 : kn1;
-                const int n = n0 + (rem0 + u / rows_per_cell) / cells;
-                return (float)(off_at(n + 1) - off_at(n));
-            };
-            if (version == 2) {
-                // two rows per lane and step: two independent exp/div chains in flight
-                float acc1 = 0.f;
-                for (int u = lane; u < nrows; u += 64) {
-                    const int u2 = u + 32;
-                    const bool has2 = u2 < nrows;
-                    const float ta = in[u * bs + 4];
-                    const float tb = has2 ? in[u2 * bs + 4] : 0.f;
-                    const float ca_ = yh_sigmoid(ta), cb_ = yh_sigmoid(tb);
-                    const float ka = kn_of(u), kb = has2 ? kn_of(u2) : 0.f;
-                    const float a2 = ca_ * ca_, b2 = cb_ * cb_;
-                    sums.no += ka * a2;
-                    acc1 += kb * b2;
-                    if (WRITE_DY) {
-                        out[u * bs + 4] = p.cno * ka * a2 * (1.f - ca_);
-                        if (has2) out[u2 * bs + 4] = p.cno * kb * b2 * (1.f - cb_);
-                    }
-                }
-                sums.no += acc1;
+        auto issue_chunk = [&](int c) {  // one thread: chunk c of the tile -> shared memory
+            const int lo = c * ch4, n4 = min(ch4, nf4 - lo);
+            if (VEC && n4 > 0) {
+                yh_mbar_expect_tx(&s_bar[c], (uint32_t)n4 * 16u);
+                yh_bulk_load(s_tile + 4 * lo, yt + 4 * lo, (uint32_t)n4 * 16u, &s_bar[c]);
             } else {
-                for (int u = lane; u < nrows; u += 32) {
-                    const float kn = kn_of(u);
-                    const float* irow = in + u * cf;
-                    float* orow = out + u * cf;
-                    for (int b = 0; b < A; ++b) {
-                        const float conf = yh_sigmoid(irow[b * 5 + 4]);
-                        const float c2 = conf * conf;
-                        sums.no += kn * c2;
-                        if (WRITE_DY) orow[b * 5 + 4] = p.cno * kn * c2 * (1.f - conf);
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(yh_smem_u32(&s_bar[c])) : "memory");
+            }
+        };
+        if (tid == kDense) {
+            // TMA producer: the window first (everything the record warp does hangs on it), then the
+            // first chunks of the tile
+            yh_fence_proxy_async();  // (multi-tile: the stage was read through the generic proxy)
+            if (wn > 0) {
+                yh_mbar_expect_tx(&s_bar[kChunks], (uint32_t)wn * 48u);
+                yh_bulk_load(s_win, p.gt + w0, (uint32_t)wn * 48u, &s_bar[kChunks]);
+            } else {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(yh_smem_u32(&s_bar[kChunks])) : "memory");
+            }
+#pragma unroll
+            for (int c = 0; c < kChunks && c < kAhead; ++c) issue_chunk(c);
+        }
+
+        // CSR offsets of the tile's images (every warp: the dense pass needs the box counts)
+#ifdef YH_X_NOMETA
+        const int o0 = 0, o1 = 3, o2 = 6, o3 = 0;
+#else
+        const int o0 = __ldg(p.gt_off + n0), o1 = __ldg(p.gt_off + n0 + 1);
+        const int o2 = __ldg(p.gt_off + min(n0 + 2, nimg));
+        const int o3 = (record_warp && n_hi > n0 + 1) ? __ldg(p.gt_off + n_hi + 1) : 0;
+#endif
+        const int thr0 = cells_left * cf;           // tile-local float index where image n0 + 1 starts
+        const bool two_img = R <= cells;            // a tile then touches at most two images
+        const float kn0 = (float)(o1 - o0), kn1 = (float)(o2 - o1);
+        // boxes in the image of tile-local float index f (the no-object term counts once per box)
+        auto kn_of = [&](int f) -> float {
+            if (f < thr0) return kn0;
+            if (two_img) return kn1;
+            const int n = min(n0 + 1 + (f - thr0) / (cells * cf), nimg - 1);  // (clamped: idle lanes pass garbage)
+            return (float)(__ldg(p.gt_off + n + 1) - __ldg(p.gt_off + n));
+        };
+        // record header -> tile-local cell if the record lies in this tile, else -1
+        auto local_cell = [&](const int4& h) -> int {
+            const bool ok = h.y >= 0 && h.y < g.s_h && h.z >= 0 && h.z < g.s_w && h.x >= 0 && h.x < nimg;
+            const int lc = ok ? h.x * cells + h.y * g.s_w + h.z - c0 : -1;
+            return (lc >= 0 && lc < nc) ? lc : -1;
+        };
+        if (!VEC) {  // unaligned y: the streaming warps copy the tile themselves
+            for (int i = tid; i < nfl; i += kThreads) s_tile[i] = __ldg(yt + i);
+            __syncthreads();
+        } else if (tid < (nfl & 3)) {
+            s_tile[4 * nf4 + tid] = __ldg(yt + 4 * nf4 + tid);  // floats past the last whole float4 of the tensor
+        }
+
+        // Patchable records are dealt round-robin to ALL warps (a record is ~3000 cycles of one warp's
+        // dependent arithmetic): warp w takes list entries w, w + kWarps, ...  Each goes into its own
+        // patch slot, so the order in which they are processed does not matter; the patches are applied
+        // in list (CSR) order afterwards.  try_records(c) processes this warp's records whose cells lie
+        // in chunks <= c, once the record warp has published the list; returns false if it has not yet.
+        unsigned rec_done = 0u;
+        int my_npatch = -1;
+        auto try_records = [&](int upto_chunk) -> bool {
+            if (my_npatch < 0) {
+                if (*reinterpret_cast<volatile int*>(&s_ready) != t + 1) return false;
+                __threadfence_block();
+                yh_mbar_wait(&s_bar[kChunks], phase);  // (complete by now: makes the window visible to this warp)
+                my_npatch = s_npatch;
+            }
+            for (int i = warp, k = 0; i < my_npatch; i += kWarps, ++k) {
+                if ((rec_done >> k) & 1u) continue;
+                const int jj = s_rjj[i], lcell = s_rlc[i];
+                const int cb = min(((lcell + 1) * cf - 1) / (4 * ch4), kChunks - 1);  // chunk of the cell's last float
+                if (cb > upto_chunk) continue;
+                rec_done |= 1u << k;
+                const int4* rp = s_win + 3 * (jj - w0);
+                RecordRegs rr;
+                rr.hd = rp[0];
+                rr.tt = *reinterpret_cast<const float4*>(rp + 1);
+                rr.bb = *reinterpret_cast<const float4*>(rp + 2);
+                const int r = process_record<2>(p, version, A, C, rr, jj, s_tile + lcell * cf, nullptr,
+                                                s_patch + i * kPatchFloats, s_pdense + i, kn_of(lcell * cf), lane,
+                                                my_pw, my_ph, sums);
+                if (lane == 0) s_pr[i] = r;
+            }
+            return true;
+        };
+
+        if (!record_warp) {
+            // ================= streaming warps: the dense pass =================
+            const float4* tile4 = reinterpret_cast<const float4*>(s_tile);
+            for (int c = 0; c < kChunks; ++c) {
+                const int lo = c * ch4, hi = min(lo + ch4, nf4);
+                yh_mbar_wait(&s_bar[c], phase);  // (empty chunks complete at once: every barrier flips once per tile)
+                if (tid == 0 && c + kAhead < kChunks) issue_chunk(c + kAhead);  // keep kAhead chunks in flight
+                for (int i4 = lo + tid; i4 < hi; i4 += kDense) {
+                    const float4 v = tile4[i4];
+                    const int lf = 4 * i4;
+                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (version == 2) {
+                        // floats lf..lf+3 sit at positions m..m+3 of a predictor row: the objectness
+                        // logit (position 4) is among them iff 1 <= m <= 4.  Branch-free.
+                        const int m = lf % bs;
+                        const bool has = (unsigned)(m - 1) < 4u;
+                        float tl = v.w;
+                        tl = m == 2 ? v.z : tl;
+                        tl = m == 3 ? v.y : tl;
+                        tl = m == 4 ? v.x : tl;
+                        float conf;
+                        float w = noobj_term(tl, kn_of(lf + 4 - m), &conf);
+                        w = has ? w : 0.f;
+                        sums.no += w;
+                        const float val = noobj_grad(w, conf, p.cno);
+                        o.x = m == 4 ? val : 0.f;
+                        o.y = m == 3 ? val : 0.f;
+                        o.z = m == 2 ? val : 0.f;
+                        o.w = m == 1 ? val : 0.f;
+                    } else {
+                        // v1 cell: B blocks of (tx,ty,tw,th,to), then C class logits
+                        const int pc = lf % cf;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            int qq = pc + j;
+                            if (qq >= cf) qq -= cf;
+                            if (qq < 5 * A && qq % 5 == 4) {
+                                float conf;
+                                const float w = noobj_term(pick4(v, j), kn_of(lf + j), &conf);
+                                sums.no += w;
+                                put4(o, j, noobj_grad(w, conf, p.cno));
+                            }
+                        }
                     }
+                    if (WRITE_DY) store4<VEC>(dt, i4, o);
+                }
+                try_records(c);
+            }
+            while (!try_records(kChunks - 1)) { }  // (the record warp publishes after one round trip)
+            if (tid < (nfl & 3)) {  // floats past the last whole float4 of the tensor
+                const int lf = 4 * nf4 + tid;
+                const int pc = lf % cf;
+                const bool is_to = version == 2 ? (pc % bs == 4) : (pc < 5 * A && pc % 5 == 4);
+                float o = 0.f;
+                if (is_to) {
+                    float conf;
+                    const float w = noobj_term(s_tile[lf], kn_of(lf), &conf);
+                    sums.no += w;
+                    o = noobj_grad(w, conf, p.cno);
+                }
+                if (WRITE_DY) dt[lf] = o;
+            }
+        } else {
+            // ================= record warp: the tile's ground-truth records =================
+            const int rec0 = o0;
+            int rec1 = min(n_hi == n0 ? o1 : (n_hi == n0 + 1 ? o2 : o3), p.m_local);
+#if defined(YH_X_NOSPARSE) || defined(YH_X_NOMETA)
+            rec1 = rec0;
+#endif
+            XT(4);  // record warp: offsets arrived
+            // the tile's records, in CSR order, into the shared list
+            int n = 0;
+            auto append = [&](int jj, int lc) {
+                const unsigned bal = __ballot_sync(0xffffffffu, lc >= 0);
+                if (lc >= 0) {
+                    const int idx = n + __popc(bal & ((1u << lane) - 1u));
+                    if (idx < kWindow) { s_rjj[idx] = jj; s_rlc[idx] = lc; }
+                }
+                n += __popc(bal);
+            };
+            const bool covered = rec0 >= w0 && rec1 <= w0 + wn;  // the window has them all
+            yh_mbar_wait(&s_bar[kChunks], phase);  // (always: the barrier's phase must be consumed)
+            if (covered) {
+                for (int base = rec0; base < rec1; base += 32) {
+                    const int jj = base + lane;
+                    append(jj, jj < rec1 ? local_cell(s_win[3 * (jj - w0)]) : -1);
+                }
+            } else {
+                for (int base = rec0; base < rec1; base += 32) {
+                    const int jj = base + lane;
+                    append(jj, jj < rec1 ? local_cell(__ldg(reinterpret_cast<const int4*>(p.gt + jj))) : -1);
                 }
             }
+            __syncwarp();
+            XT(5);  // record warp: list built
+            const bool complete = n <= kWindow;
+            const int n_patch = (patchable && complete && covered) ? min(n, kSlots) : 0;
+            if (lane == 0) { s_nrec = complete ? n : -1; s_npatch = n_patch; }
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0) *reinterpret_cast<volatile int*>(&s_ready) = t + 1;  // publish the list
+            __syncwarp();
+            for (int c = 0; c < kChunks; ++c) {  // this warp's share, as the chunks land
+                yh_mbar_wait(&s_bar[c], phase);
+                try_records(c);
+            }
+            XT(6);  // record warp: records processed
         }
-        __syncwarp();  // dense rows written before the sparse read-modify-writes
-        YH_TR(6 + 5 * k);
 
-        // ---------------- sparse pass: ground-truth records of this chunk ----------------
-        const int ci = warp + (k << wlog);  // index of this mini-chunk inside the CTA
-        if (!have_mask || ((s_chunkmask[ci >> 5] >> (ci & 31)) & 1u)) {
-            const int n_hi = two_img ? (rem0 + ncell > cells ? n0 + 1 : n0) : n0 + (rem0 + ncell - 1) / cells;
-            const int r0 = off_at(n0), r1 = off_at(n_hi + 1);
-            for (int base = r0; base < r1; base += 32) {
-                const int j = base + lane;
-                int lc = -1;
-                if (j < r1) {
-                    int gc;
-                    if (gt_cached) {
-                        gc = s_cell[j - gt_base];
-                    } else {
-                        const int4 h = __ldg(reinterpret_cast<const int4*>(p.gt + j));
-                        const bool ok = h.y >= 0 && h.y < g.s_h && h.z >= 0 && h.z < g.s_w && h.x >= 0 && h.x < g.n;
-                        gc = ok ? h.x * cells + h.y * g.s_w + h.z : -1;
-                    }
-                    if (gc >= cell0 && gc < cell0 + ncell) lc = gc - cell0;
+        // ---------------- the records' gradients go onto the dense rows ----------------
+        XT(1);
+        __syncthreads();  // the tile's dense dL/dy is written (and visible to the whole CTA); patches are ready
+        XT(2);
+        const int nrec = s_nrec, npatch = s_npatch;
+        if (record_warp) {
+            for (int i = 0; i < npatch; ++i) {
+                const int lcell = s_rlc[i], r = s_pr[i];
+                // an earlier record of this cell already updated it: read the row back.  Otherwise the
+                // row holds the dense pass' values, known without a load (zero but the objectness channel)
+                bool again = false;
+                for (int j0 = 0; j0 < i; j0 += 32) again = again || __any_sync(0xffffffffu, j0 + lane < i && s_rlc[j0 + lane] == lcell);
+                if (lane < 5 + C) {
+                    float* addr = dt + lcell * cf + (version == 2 ? r * bs + lane : (lane < 5 ? r * 5 + lane : 5 * A + lane - 5));
+                    float val = s_patch[i * kPatchFloats + lane];
+                    if (again) val = __fadd_rn(*addr, val);
+                    else if (lane == 4) val = __fadd_rn(s_pdense[i], val);
+                    *addr = val;
+                }
+                __syncwarp();
+            }
+        }
+        if (nrec < 0 || nrec > npatch) {
+            // records that were not patched during the dense pass (window miss, more than kSlots in
+            // the tile, wide class rows, loss-only call): now, by all warps, dealt by cell so that
+            // records of one cell stay on one warp in CSR order; read-modify-write on top of dense
+            // values and patches.  The tile is still in shared memory.
+            if (npatch > 0) __syncthreads();
+            const int rec0 = o0;
+            const int lim = nrec >= 0 ? nrec : min(__ldg(p.gt_off + n_hi + 1), p.m_local);
+            for (int base = nrec >= 0 ? npatch : rec0; base < lim; base += 32) {
+                int lc = -1, jj = 0;
+                if (base + lane < lim) {
+                    if (nrec >= 0) { jj = s_rjj[base + lane]; lc = s_rlc[base + lane]; }
+                    else { jj = base + lane; lc = local_cell(__ldg(reinterpret_cast<const int4*>(p.gt + jj))); }
+                    if (lc % kWarps != warp) lc = -1;
                 }
                 unsigned bal = __ballot_sync(0xffffffffu, lc >= 0);
                 while (bal) {
                     const int b = __ffs(bal) - 1;
                     bal &= bal - 1;
-                    const int jj = base + b;
+                    const int j = __shfl_sync(0xffffffffu, jj, b);
                     const int lcell = __shfl_sync(0xffffffffu, lc, b);
+                    const int4* rp = reinterpret_cast<const int4*>(p.gt + j);
                     RecordRegs rr;
-                    if (gt_cached) {
-                        const int4* rp = reinterpret_cast<const int4*>(s_gt + (jj - gt_base));
-                        rr.hd = rp[0];
-                        rr.tt = *reinterpret_cast<const float4*>(rp + 1);
-                        rr.bb = *reinterpret_cast<const float4*>(rp + 2);
-                    } else {
-                        const int4* rp = reinterpret_cast<const int4*>(p.gt + jj);
-                        rr.hd = __ldg(rp);
-                        rr.tt = __ldg(reinterpret_cast<const float4*>(rp + 1));
-                        rr.bb = __ldg(reinterpret_cast<const float4*>(rp + 2));
-                    }
-                    process_record<WRITE_DY>(p, version, A, C, rr, jj, in + lcell * cf, out + lcell * cf, lane, my_pw, my_ph, sums);
-                    if (ost) touched1 |= 1u << lcell; else touched0 |= 1u << lcell;
+                    rr.hd = __ldg(rp);
+                    rr.tt = __ldg(reinterpret_cast<const float4*>(rp + 1));
+                    rr.bb = __ldg(reinterpret_cast<const float4*>(rp + 2));
+                    process_record<WRITE_DY ? 1 : 0>(p, version, A, C, rr, j, s_tile + lcell * cf, dt + lcell * cf, nullptr,
+                                                     nullptr, kn_of(lcell * cf), lane, my_pw, my_ph, sums);
                 }
             }
         }
-
-        YH_TR(7 + 5 * k);
-        // ---------------- push the chunk's dL/dy, refill the input stage ----------------
-        if (WRITE_DY) {
-            float* ydst = p.dy + (size_t)cell0 * cf;
-            if (p.tma_out) {
-                yh_fence_proxy_async();  // every lane: its generic-proxy writes -> async proxy
-                __syncwarp();
-                if (lane == 0) {
-                    if (nfl16) yh_bulk_store(ydst, out, (uint32_t)nfl16 * 4u);
-                    yh_bulk_commit();
-                }
-                if (lane < ntail) ydst[nfl16 + lane] = out[nfl16 + lane];
-            } else {
-                __syncwarp();
-                for (int i = lane; i < nfl; i += 32) ydst[i] = out[i];
-            }
-        } else {
-            __syncwarp();
-        }
-        if (p.tma_in && lane == 0 && k + kInStages < my_n) issue_load(k + kInStages, ist);
-
-        YH_TR(8 + 5 * k);
-        cell0 += step;
-        rem0 += step;
-        while (rem0 >= cells) { rem0 -= cells; ++n0; }
-        ost ^= 1;
-        if (++ist == kInStages) { ist = 0; in_phase ^= 1u; }
+        if (multi_tile) __syncthreads();  // the stage and the lists are rewritten by the next tile
     }
-    YH_TR(2);
-    if (WRITE_DY && p.tma_out && lane == 0) yh_bulk_wait_all<0>();
-    YH_TR(3);
+    XT(3);
 
+#ifdef YH_X_NOREDUCE
+    if (sums.no == 123.456f) p.terms[0] = sums.no + sums.xy + sums.cls;
+    return;
+#endif
     // ---------------- block reduction of the six partial sums ----------------
     // every lane carries partial sums (dense rows; record channels by lane role): fold the warp
     const float s_no = yh_warp_sum(sums.no);
@@ -580,25 +649,50 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) yh_train_kernel(const Train
     __syncthreads();
     if (tid == 0) {
         float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int w = 0; w < W; ++w)
+        for (int w = 0; w < kWarps; ++w)
             for (int q = 0; q < 6; ++q) acc[q] += red[w * 6 + q];
-        float* dst = p.partials + (size_t)blockIdx.x * kPartials;
-        for (int q = 0; q < 6; ++q) dst[q] = acc[q];
+        float4* dst = reinterpret_cast<float4*>(p.partials) + 2 * blockIdx.x;
+        dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        dst[1] = make_float4(acc[4], acc[5], 0.f, 0.f);
+        XT(4);
         __threadfence();
+        XT(5);
         const unsigned t = atomicAdd(p.ticket, 1u);
         is_last = (t == gridDim.x - 1);
+        if (is_last) __threadfence();  // acquire side, once; the CTA barrier below extends it to the CTA
+        XT(6);
     }
     __syncthreads();
-    if (is_last && warp == 0) {
-        __threadfence();
+    if (is_last) {
+        // the whole last CTA folds the per-CTA partials: all loads in flight at once (one L2 round
+        // trip), fixed assignment and order -> deterministic
+        constexpr int kFold = 4;  // covers kFold * kThreads CTAs without a second round trip
+        const float4* part4 = reinterpret_cast<const float4*>(p.partials);
         double acc[6] = {0, 0, 0, 0, 0, 0};
-        for (unsigned b = lane; b < gridDim.x; b += 32) {
-            const float* src = p.partials + (size_t)b * kPartials;
-            for (int q = 0; q < 6; ++q) acc[q] += (double)__ldcg(src + q);
+        for (unsigned b0 = 0; b0 < gridDim.x; b0 += kFold * kThreads) {
+            float4 lo[kFold], hi[kFold];
+#pragma unroll
+            for (int u = 0; u < kFold; ++u) {
+                const unsigned b = b0 + u * kThreads + tid;
+                lo[u] = hi[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (b < gridDim.x) { lo[u] = __ldcg(part4 + 2 * b); hi[u] = __ldcg(part4 + 2 * b + 1); }
+            }
+#pragma unroll
+            for (int u = 0; u < kFold; ++u) {
+                acc[0] += (double)lo[u].x; acc[1] += (double)lo[u].y; acc[2] += (double)lo[u].z;
+                acc[3] += (double)lo[u].w; acc[4] += (double)hi[u].x; acc[5] += (double)hi[u].y;
+            }
         }
         for (int q = 0; q < 6; ++q)
             for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
-        if (lane == 0) {
+        if (lane == 0)
+            for (int q = 0; q < 6; ++q) dred[warp * 6 + q] = acc[q];
+        __syncthreads();
+        if (tid == 0) {
+            for (int q = 0; q < 6; ++q) {
+                acc[q] = 0.0;
+                for (int w = 0; w < kWarps; ++w) acc[q] += dred[w * 6 + q];
+            }
             const double t0 = acc[0] * p.inv_den[0];
             const double t1 = acc[1] * p.inv_den[1];
             const double t2 = acc[2] * p.inv_den[2];
@@ -608,39 +702,44 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) yh_train_kernel(const Train
             p.terms[3] = (float)t3; p.terms[4] = (float)t4;
             p.loss[0] = (float)(p.lam[0] * t0 + p.lam[1] * t1 + p.lam[2] * t2 + p.lam[3] * t3 + p.lam[4] * t4);
             *p.ticket = 0u;  // ready for the next launch
+            XT(7);
         }
     }
-    YH_TR(63);
+    XT_FLUSH;
 }
+#ifdef YH_X_TRACE
+extern "C" YH_API int yh_x_trace_copy(unsigned long long* host, int n) {
+    return (int)cudaMemcpyFromSymbol(host, g_xtrace, (size_t)n * 8);
+}
+#endif
 
-template <bool WDY, int TV, int TA, int TC>
-int launch_variant(const TrainParams& p, int grid, size_t smem, int warps, cudaStream_t stream) {
-    static size_t configured[64] = {0};
+template <bool WDY, bool VEC, int TV, int TA, int TC>
+int launch_variant(const TrainParams& p, int grid, cudaStream_t stream) {
+    static bool configured[64] = {false};  // per device: opt in to > 48 KB of dynamic shared memory
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) dev = 0;
-    if (smem > configured[dev]) {
-        int rc = yh_check_cuda(cudaFuncSetAttribute(yh_train_kernel<WDY, TV, TA, TC>,
-                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+    if (!configured[dev]) {
+        int rc = yh_check_cuda(cudaFuncSetAttribute(yh_train_kernel<WDY, VEC, TV, TA, TC>,
+                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, kTileBytesMax + 64),
                                "cudaFuncSetAttribute(train)");
         if (rc) return rc;
-        configured[dev] = smem;
+        configured[dev] = true;
     }
-    yh_train_kernel<WDY, TV, TA, TC><<<grid, warps * 32, smem, stream>>>(p);
+    const size_t smem = (((size_t)p.tile_cells * p.g.cell_floats * 4 + 15) & ~(size_t)15) + 16;
+    yh_train_kernel<WDY, VEC, TV, TA, TC><<<grid, kThreads, smem, stream>>>(p);
     return yh_check_cuda(cudaGetLastError(), "yh_train launch");
 }
 
-template <bool WDY>
-int launch_geometry(const TrainParams& p, int grid, size_t smem, int warps, cudaStream_t stream) {
+template <bool WDY, bool VEC>
+int launch_geometry(const TrainParams& p, int grid, cudaStream_t stream) {
     const YhGeom& g = p.g;
     // compile-time geometries for the shapes the reference trains: YOLOv2 5 anchors x 20 classes
     // (VOC, models/yolov2.py:49-70) and YOLOv1 B=2, C=20 (config.py:7-11); anything else runs the
     // same kernel with run-time geometry
-    if (warps == kMaxWarps && p.mc == mini_cells(g.cell_floats)) {
-        if (g.version == 2 && g.a == 5 && g.c == 20) return launch_variant<WDY, 2, 5, 20>(p, grid, smem, warps, stream);
-        if (g.version == 1 && g.a == 2 && g.c == 20) return launch_variant<WDY, 1, 2, 20>(p, grid, smem, warps, stream);
-    }
-    return launch_variant<WDY, 0, 0, 0>(p, grid, smem, warps, stream);
+    if (g.version == 2 && g.a == 5 && g.c == 20) return launch_variant<WDY, VEC, 2, 5, 20>(p, grid, stream);
+    if (g.version == 1 && g.a == 2 && g.c == 20) return launch_variant<WDY, VEC, 1, 2, 20>(p, grid, stream);
+    return launch_variant<WDY, VEC, 0, 0, 0>(p, grid, stream);
 }
 
 int train_impl(int version, const float* y, int n, int s_h, int s_w, int a, int c,
@@ -666,15 +765,12 @@ int train_impl(int version, const float* y, int n, int s_h, int s_w, int a, int 
     p.terms = terms; p.loss = loss; p.resp = resp; p.iou_resp = iou_resp;
     p.partials = reinterpret_cast<float*>(ws);
     p.ticket = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(ws) + (size_t)kMaxGrid * kPartials * 4);
-    p.total_cells = (long long)n * p.g.cells;
-    p.m_local = m_local;
-    p.quads_total = (p.total_cells + 3) / 4;
+    const long long total_cells = (long long)n * p.g.cells;
     const int cf = p.g.cell_floats;
-    p.mc = mini_cells(cf);
-    const int qpc = p.mc / 4;  // quads of cells per mini-chunk
-    YH_REQUIRE(p.total_cells * cf < (1ll << 31), YH_ERR_UNSUPPORTED, "head tensor has 2^31 or more floats");
-    p.tma_in = ((uintptr_t)y & 15) == 0;
-    p.tma_out = dy && ((uintptr_t)dy & 15) == 0;
+    YH_REQUIRE(total_cells * cf < (1ll << 31), YH_ERR_UNSUPPORTED, "head tensor has 2^31 or more floats");
+    p.total_cells = (int)total_cells;
+    p.m_local = m_local;
+    p.rec_per_cell = (float)((double)m_local / (double)total_cells);
 
     const double M = (double)m_global;
     const double P1 = (double)p.g.preds - 1.0;
@@ -692,28 +788,26 @@ int train_impl(int version, const float* y, int n, int s_h, int s_w, int a, int 
     p.cno = (float)(lambdas_host[3] * 2.0 / (M * P1));
     p.ccls = (float)(lambdas_host[4] * 2.0 / M);
 
-    // warps per CTA: as many private pipelines as fit in shared memory
-    const size_t stage_bytes = (size_t)p.mc * cf * 4;
-    const int stages = kInStages + (dy ? kOutStages : 0);
-    const size_t budget = 200 * 1024;
-    int warps = kMaxWarps;
-    while (warps > 1 && (size_t)warps * stages * stage_bytes + 8 * kInStages * warps + 16 > budget) warps >>= 1;
-    const size_t smem = (size_t)warps * stages * stage_bytes + 8 * kInStages * warps + 16;
-    YH_REQUIRE(smem <= budget, YH_ERR_UNSUPPORTED, "cell too wide for shared memory (%d floats per cell)", cf);
-    p.warps_log2 = 0;
-    while ((1 << p.warps_log2) < warps) ++p.warps_log2;
+    // tiles: whole quads of cells (16-byte aligned starts), at most kTileBytesMax bytes, and a tile
+    // count that fills the resident CTA slots evenly (one tile per CTA when the tensor is small)
+    int slots = yh_sm_count() * kCtasPerSm;
+    if (slots > kMaxGrid) slots = kMaxGrid;
+    const long long quads_total = (total_cells + 3) / 4;
+    const long long max_q = kTileBytesMax / (16ll * cf);
+    YH_REQUIRE(max_q >= 1, YH_ERR_UNSUPPORTED, "cell too wide for the shared-memory stage (%d floats per cell)", cf);
+    long long rounds = (quads_total + slots * max_q - 1) / (slots * max_q);  // tiles per CTA
+    if (rounds < 1) rounds = 1;
+    long long qpt = (quads_total + slots * rounds - 1) / (slots * rounds);    // quads per tile
+    if (qpt < 1) qpt = 1;
+    const long long tiles = (quads_total + qpt - 1) / qpt;
+    p.tile_cells = (int)(qpt * 4);
+    p.num_tiles = (int)tiles;
+    const int grid = (int)(tiles < slots ? tiles : slots);
 
-    const long long nmini_total = (p.quads_total + qpc - 1) / qpc;
-    long long grid = (nmini_total + warps - 1) / warps;  // at least one mini-chunk per warp
-    const int sms = yh_sm_count();
-    if (grid > sms) grid = sms;
-    if (grid > kMaxGrid) grid = kMaxGrid;
-    if (grid < 1) grid = 1;
-    p.q_base = (int)(p.quads_total / grid);
-    p.q_extra = (int)(p.quads_total % grid);
-    p.rec_per_cell = (float)((double)m_local / (double)p.total_cells);
+    const bool vec = ((uintptr_t)y & 15) == 0 && ((uintptr_t)dy & 15) == 0;
     cudaStream_t st = (cudaStream_t)stream;
-    return dy ? launch_geometry<true>(p, (int)grid, smem, warps, st) : launch_geometry<false>(p, (int)grid, smem, warps, st);
+    if (dy) return vec ? launch_geometry<true, true>(p, grid, st) : launch_geometry<true, false>(p, grid, st);
+    return vec ? launch_geometry<false, true>(p, grid, st) : launch_geometry<false, false>(p, grid, st);
 }
 
 }  // namespace
