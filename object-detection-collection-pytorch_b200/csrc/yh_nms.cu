@@ -5,30 +5,33 @@
 // predict -> nms -> argmax chain of detect() (reference models/yolov2.py:694-731,
 // models/yolov1.py:491-534).
 //
-// One CTA per image, one launch for the whole batch, no sort:
-//   A  stage+threshold : the image's slice of the head tensor is pulled into shared memory with
-//                  1-D TMA bulk copies (16 KB stages, one mbarrier each; the whole image stays
-//                  resident when it fits, otherwise a 4-stage ring is recycled and candidate rows
-//                  are copied aside).  As stages land, every thread tests
-//                  `sigmoid(to) >= conf_thre` for its predictors and appends survivors to a
-//                  candidate list (order irrelevant).  All later phases read shared memory only.
+// One CTA (512 threads) per image, one launch for the whole batch, no sort.  The kernel is
+// latency-bound (a few microseconds end to end), so it is organised around TWO overlapped global
+// round trips:
+//   A  threshold : every thread reads the objectness logit of its predictors (strided 4-byte
+//                  loads, all in flight at once) and tests `sigmoid(to) >= conf_thre`.  A survivor
+//                  reserves a candidate slot and immediately stages its row (5 box logits + C class
+//                  logits) in shared memory with a 1-D TMA bulk copy of the 16-byte aligned window
+//                  around it; every thread then arrives ONCE on one mbarrier, carrying the bytes it
+//                  asked for, so a single wait covers "all candidates found" and "all rows landed".
+//                  All later phases read shared memory only;
 //   B  rank      : a candidate's position in the descending-confidence order is the number of
 //                  candidates that beat it (ties: lower predictor index first) -> the order is
-//                  unique and deterministic without a sort;
-//   C  decode    : each candidate's box is decoded from its 5 logits directly into its ranked
-//                  slot (same rounding sequence as the train head / predict kernels);
+//                  unique and deterministic without a sort; one warp per candidate, ballot/popc;
+//                  the same warp decodes the candidate's box into its ranked slot (same rounding
+//                  sequence as the train head / predict kernels);
 //   D  suppress  : tiles of 256 ranked candidates: (1) test the tile against the boxes kept so
 //                  far, (2) build the intra-tile suppression bitmask with one ballot per 32
 //                  pairs, (3) one warp walks the KEPT boxes of the tile (ffs over the live bits),
 //                  OR-ing their mask rows;
-//   E  emit      : one warp per kept box: class softmax of its row, cls_spec = p * conf, argmax
-//                  label / max score, and the box record.
+//   E  emit      : four lanes per kept box: class softmax of its staged row, cls_spec = p * conf,
+//                  argmax label / max score, and the box record.
 // The reference's greedy rule (models/utils.py:124-158): candidate j is dropped iff an earlier
 // KEPT candidate i has iou(i, j) >= iou_thre.  class_aware additionally requires equal labels.
 //
-// Candidate lists live in shared memory up to 256 candidates per image (the common case by a wide
-// margin); images with more spill to the caller's workspace and take the same code path through
-// generic pointers.
+// Candidate lists and staged rows live in shared memory up to 256 candidates per image (the
+// common case by a wide margin); images with more spill to the caller's workspace, read their
+// rows from global memory, and take the same code path through generic pointers.
 #include <math.h>
 #include <string.h>
 
@@ -36,20 +39,33 @@
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int kTile = 256;             // ranked candidates per suppression tile
 constexpr int kTileWords = kTile / 32;
 constexpr int kSmemCand = 256;         // candidates held in shared memory
-constexpr int kRowCache = 256;         // candidate rows copied aside in ring mode
-constexpr int kStageFloats = 4096;     // 16 KB TMA stages
-constexpr int kRingStages = 4;
-constexpr int kMaxStages = 8;          // resident mode: image <= 8 stages (128 KB)
+constexpr int kStageBytesMax = 64 * 1024;  // shared memory for staged candidate rows
+constexpr int kLoadUnroll = 4;         // objectness loads in flight per thread
 
-enum { SRC_TMA = 0, SRC_GLOBAL = 1, SRC_DECODED = 2 };
+enum { SRC_HEAD = 0, SRC_DECODED = 2 };
+
+#ifdef YH_X_TRACE
+__device__ unsigned long long g_ntrace[4096 * 16];
+__device__ __forceinline__ unsigned long long nt_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define NT(slot) do { if (threadIdx.x == 0) g_ntrace[blockIdx.x * 16 + (slot)] = nt_now(); } while (0)
+extern "C" YH_API int yh_x_ntrace_copy(unsigned long long* host, int n) {
+    return (int)cudaMemcpyFromSymbol(host, g_ntrace, (size_t)n * 8);
+}
+#else
+#define NT(slot) do { } while (0)
+#endif
 
 struct NmsParams {
-    YhGeom g;                // head sources only
+    YhGeom g;                // head source only
     int src;
     const float* y;
     long long total_floats;  // of the head tensor
@@ -69,15 +85,10 @@ struct NmsParams {
     float* out_score;
     unsigned char* ws;       // global candidate storage for images with > kSmemCand candidates
     size_t ws_per_image;
-    // SRC_TMA staging
-    int resident;            // whole image stays in shared memory
-    int nst;                 // shared-memory stages
-    int img_smem_floats;     // floats of shared memory set aside for the staged image
     int img_floats;          // floats per image
-    int unit_floats;         // v2: 5+C (a predictor row); v1: 5B+C (a cell)
-    int units;               // v2: P; v1: cells
-    int row_floats;          // 5 + C
-    int row_cache;           // rows cached in ring mode
+    int use_tma;             // y is 16-byte aligned: candidate rows are staged with bulk copies
+    int stage_slots;         // candidate rows staged in shared memory (<= kSmemCand)
+    int slot_floats;         // floats per staged row slot (multiple of 4)
 };
 
 struct Cand {
@@ -87,13 +98,14 @@ struct Cand {
     int32_t* s_idx;    // ranked
     float* s_conf;
     float4* s_box;
+    float* s_area;     // ranked: (x2-x1)*(y2-y1), the rounding yh_iou_xyxy uses
     int32_t* s_lab;
     int32_t* keep;     // ranked positions of kept boxes
 };
 
 __host__ __device__ inline size_t cand_bytes(int cap) {
     const size_t c = ((size_t)cap + 3) & ~(size_t)3;
-    return c * (16 + 4 * 7);
+    return c * (16 + 4 * 8);
 }
 
 __device__ __forceinline__ Cand carve(unsigned char* base, int cap) {
@@ -105,39 +117,70 @@ __device__ __forceinline__ Cand carve(unsigned char* base, int cap) {
     a.s_slot = a.u_idx + c;
     a.s_idx = a.s_slot + c;
     a.s_conf = reinterpret_cast<float*>(a.s_idx + c);
-    a.s_lab = reinterpret_cast<int32_t*>(a.s_conf + c);
+    a.s_area = a.s_conf + c;
+    a.s_lab = reinterpret_cast<int32_t*>(a.s_area + c);
     a.keep = a.s_lab + c;
     return a;
 }
 
-// Class pick of one predictor by a group of 4 adjacent lanes (8 predictors per warp at a time):
+// Class pick of one predictor by a group of G adjacent lanes (32 / G predictors per warp at a time):
 // softmax over its C logits, cls_spec = p * conf (reference models/yolov2.py:625-640),
 // label = first argmax of cls_spec, score = its max (models/yolov2.py:726-731).  Optionally stores
 // the cls_spec row.  `cl` may point to shared or global memory; inactive groups pass active=false
-// (they still take part in the shuffles).
-__device__ __forceinline__ void quad_class_pick(const float* cl, int C, float conf, int sub, bool active,
-                                                float* spec_out, int* label, float* score) {
+// (they still take part in the shuffles).  The exponentials of up to G*kQuadRegs classes stay in
+// registers between the two passes.
+constexpr int kQuadRegs = 4;
+template <int G>
+__device__ __forceinline__ void group_class_pick(const float* cl, int C, float conf, int sub, bool active,
+                                                 float* spec_out, int* label, float* score) {
+    float e[kQuadRegs];
     float mx = -INFINITY;
-    if (active)
-        for (int c = sub; c < C; c += 4) mx = fmaxf(mx, cl[c]);
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    if (active) {
+#pragma unroll
+        for (int k = 0; k < kQuadRegs; ++k) {
+            const int c = sub + G * k;
+            e[k] = c < C ? cl[c] : -INFINITY;
+            mx = fmaxf(mx, e[k]);
+        }
+        for (int c = sub + G * kQuadRegs; c < C; c += G) mx = fmaxf(mx, cl[c]);
+    }
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     float se = 0.f;
-    if (active)
-        for (int c = sub; c < C; c += 4) se += expf(cl[c] - mx);
-    se += __shfl_xor_sync(0xffffffffu, se, 1);
-    se += __shfl_xor_sync(0xffffffffu, se, 2);
+    if (active) {
+#pragma unroll
+        for (int k = 0; k < kQuadRegs; ++k) {
+            const int c = sub + G * k;
+            e[k] = c < C ? expf(e[k] - mx) : 0.f;
+        }
+        // (same summation order as a plain loop over c = sub, sub + 4, ...)
+#pragma unroll
+        for (int k = 0; k < kQuadRegs; ++k)
+            if (sub + G * k < C) se += e[k];
+        for (int c = sub + G * kQuadRegs; c < C; c += G) se += expf(cl[c] - mx);
+    }
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
     float bv = -INFINITY;
     int bi = 1 << 30;
     if (active) {
-        for (int c = sub; c < C; c += 4) {
+#pragma unroll
+        for (int k = 0; k < kQuadRegs; ++k) {
+            const int c = sub + G * k;
+            if (c < C) {
+                const float sp = __fmul_rn(__fdiv_rn(e[k], se), conf);
+                if (spec_out) spec_out[c] = sp;
+                if (sp > bv || (sp != sp && bv == bv)) { bv = sp; bi = c; }  // first max per lane (c ascending)
+            }
+        }
+        for (int c = sub + G * kQuadRegs; c < C; c += G) {
             const float sp = __fmul_rn(__fdiv_rn(expf(cl[c] - mx), se), conf);
             if (spec_out) spec_out[c] = sp;
-            if (sp > bv || (sp != sp && bv == bv)) { bv = sp; bi = c; }  // first max per lane (c ascending)
+            if (sp > bv || (sp != sp && bv == bv)) { bv = sp; bi = c; }
         }
     }
 #pragma unroll
-    for (int o = 1; o <= 2; o <<= 1) {
+    for (int o = 1; o < G; o <<= 1) {
         const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         const bool on = ov != ov, bn = bv != bv;
@@ -150,171 +193,154 @@ __device__ __forceinline__ void quad_class_pick(const float* cl, int C, float co
     *score = bv;
 }
 
-// bit = "box i suppresses box j" (models/utils.py:133: j survives iff iou < thr).  Boxes that do
-// not overlap have iou == 0 exactly, which skips the division for the vast majority of pairs.
-__device__ __forceinline__ bool suppresses(const float4& bi, const float4& bj, float thr) {
-    if (thr > 0.f) {
-        const float iw = __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x));
-        const float ih = __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y));
-        if (!(iw > 0.f) || !(ih > 0.f)) {
-            // inter == 0 (or NaN coordinates): iou is 0, -0 or NaN, none of which reaches thr > 0
-            if (iw == iw && ih == ih) return false;
-        }
+// bit = "box i suppresses box j": iou(i, j) >= thr with the reference's arithmetic
+// (models/utils.py:47-63, 133: j survives iff iou < thr).  ai/aj are the boxes' areas as yh_iou_xyxy
+// rounds them.  Boxes that do not overlap have iou == 0 exactly, and away from the threshold the
+// comparison is decided by one multiplication (margin 2^-20 >> the rounding of the product); the
+// IEEE division only runs for ratios within that margin of thr, so the result is bit-exact.
+__device__ __forceinline__ bool suppresses(const float4& bi, float ai, const float4& bj, float aj, float thr) {
+    const float iw = __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x));
+    const float ih = __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y));
+    if (thr > 0.f && (!(iw > 0.f) || !(ih > 0.f)) && iw == iw && ih == ih) return false;  // inter == 0 -> iou is 0 / -0
+    const float inter = __fmul_rn(fmaxf(iw, 0.0f), fmaxf(ih, 0.0f));
+    const float den = __fadd_rn(__fsub_rn(__fadd_rn(ai, aj), inter), 1e-6f);
+    const float t = __fmul_rn(thr, den);
+    if (den > 0.f && thr > 0.f && t < INFINITY) {
+        if (inter > __fmul_rn(t, 1.000001f)) return true;
+        if (inter < __fmul_rn(t, 0.999999f)) return false;
     }
-    const YhBox qi{bi.x, bi.y, bi.z, bi.w}, qj{bj.x, bj.y, bj.z, bj.w};
-    return yh_iou_xyxy(qi, qj) >= thr;
+    return __fdiv_rn(inter, den) >= thr;
 }
 
-__global__ void __launch_bounds__(kThreads) yh_nms_kernel(const NmsParams p) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+// TV/TA/TC != 0 fix version / boxes per cell / classes at compile time (index arithmetic folds,
+// divisions become multiplies); 0 keeps them as run-time values from the geometry.
+template <int TV, int TA, int TC>
+__global__ void __launch_bounds__(kThreads, 2) yh_nms_kernel(const NmsParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];  // [staged rows | candidate arrays]
     __shared__ unsigned int mask[kTile * kTileWords];
     __shared__ unsigned int rem0[kTileWords];
-    __shared__ unsigned int nzrow[kTileWords];  // rows of `mask` with at least one bit set
-    __shared__ __align__(8) uint64_t bars[kMaxStages];
+    __shared__ __align__(8) uint64_t bar;      // staged rows have landed (transaction bytes)
+    __shared__ __align__(8) uint64_t bar_list; // every thread has listed its candidates
     __shared__ int s_count, s_kept;
 
     const YhGeom& g = p.g;
     const int img = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int P = p.p;
+    const bool head = p.src == SRC_HEAD;
+    const int A = TA ? TA : g.a, C = TC ? TC : p.c;
+    const bool v2 = (TV ? TV : g.version) == 2;
+    const int bs = v2 ? 5 + C : 5, cf = v2 ? A * (5 + C) : 5 * A + C;
 
-    // dynamic shared memory: [image stages | candidate arrays (kSmemCand) | row cache (ring mode)]
-    float* sm_img = reinterpret_cast<float*>(smem_raw);
-    const size_t img_smem_floats = p.src == SRC_TMA ? (size_t)p.img_smem_floats : 0;
-    unsigned char* cand_smem = smem_raw + img_smem_floats * 4;
-    float* row_cache = reinterpret_cast<float*>(cand_smem + cand_bytes(kSmemCand));
+    float* stage = reinterpret_cast<float*>(smem_raw);
+    unsigned char* cand_smem = smem_raw + (size_t)p.stage_slots * p.slot_floats * 4;
     Cand ca = carve(cand_smem, kSmemCand);
     Cand cw = ca;  // workspace copy for images that overflow shared memory
     if (p.ws) cw = carve(p.ws + (size_t)img * p.ws_per_image, P);
 
-    if (tid == 0) { s_count = 0; s_kept = 0; }
+    NT(0);
+    if (tid == 0) {
+        s_count = 0;
+        s_kept = 0;
+        yh_mbar_init(&bar, kThreads);
+        yh_mbar_init(&bar_list, kThreads);
+        yh_mbar_fence_init();
+    }
+    __syncthreads();
 
-    // candidate append: warp-aggregated slot reservation; first kSmemCand slots in shared memory
-    auto append = [&](bool pass, float conf, int idx) -> int {
-        const unsigned bal = __ballot_sync(0xffffffffu, pass);
-        int slot = -1;
-        if (bal) {
-            int slot0 = 0;
-            if (lane == 0) slot0 = atomicAdd(&s_count, __popc(bal));
-            slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-            if (pass) {
-                slot = slot0 + __popc(bal & ((1u << lane) - 1u));
-                if (slot < kSmemCand) { ca.u_conf[slot] = conf; ca.u_idx[slot] = idx; }
-                else { cw.u_conf[slot] = conf; cw.u_idx[slot] = idx; }
-            }
+    // float offsets (inside the whole head tensor) of a predictor's 5 box logits and C class logits
+    const long long fimg = (long long)img * p.img_floats;
+    auto box_off = [&](int idx) -> long long {
+        return fimg + (v2 ? (long long)idx * bs : (long long)(idx / A) * cf + (idx % A) * 5);
+    };
+    auto cls_off = [&](int idx) -> long long {
+        return fimg + (v2 ? (long long)idx * bs + 5 : (long long)(idx / A) * cf + 5 * A);
+    };
+    // where the logits of unsorted candidate `slot` (predictor idx) can be read: its staged row, or
+    // global memory for candidates beyond the staged slots
+    auto box_ptr = [&](int slot, int idx) -> const float* {
+        const long long f = box_off(idx);
+        if (slot < p.stage_slots) return stage + (size_t)slot * p.slot_floats + (int)(f & 3);
+        return p.y + f;
+    };
+    auto cls_ptr = [&](int slot, int idx) -> const float* {
+        if (slot < p.stage_slots) {
+            if (v2) return stage + (size_t)slot * p.slot_floats + (int)(box_off(idx) & 3) + 5;
+            return stage + (size_t)slot * p.slot_floats + 8 + (int)(cls_off(idx) & 3);
         }
-        return slot;
+        return p.y + cls_off(idx);
+    };
+    // stage `len` floats starting at tensor offset f into dst (+ the shift of f inside its 16-byte
+    // window): one bulk copy of the aligned window; returns the bytes the mbarrier has to expect
+    const long long lim4 = p.total_floats & ~3ll;
+    auto stage_span = [&](float* dst, long long f, int len) -> uint32_t {
+        const int shift = (int)(f & 3);
+        const int win = (shift + len + 3) & ~3;
+        if (p.use_tma && f - shift + win <= lim4) {
+            yh_bulk_load(dst, p.y + (f - shift), (uint32_t)win * 4u, &bar);
+            return (uint32_t)win * 4u;
+        }
+        for (int q = 0; q < len; ++q) dst[shift + q] = __ldg(p.y + f + q);  // unaligned tensor / its very end
+        return 0u;
     };
 
-    // ---------------- A: stage + threshold ----------------
-    int shift = 0;  // float offset of the image inside the staged (16-byte aligned) window
-    if (p.src == SRC_TMA) {
-        const long long f_start = (long long)img * p.img_floats;
-        const long long f_end = f_start + p.img_floats;
-        const long long a0 = f_start & ~3ll;
-        long long a1 = (f_end + 3) & ~3ll;
-        const long long lim = p.total_floats & ~3ll;
-        if (a1 > lim) a1 = lim;
-        shift = (int)(f_start - a0);
-        const int win = (int)(a1 - a0);  // floats the bulk copies bring in
-        const int nstages = (win + kStageFloats - 1) / kStageFloats;
-        const unsigned ring_mask = p.resident ? 0xffffffffu : (unsigned)(p.nst * kStageFloats - 1);
-        auto issue = [&](int s) {  // thread 0
-            const int fl = min(kStageFloats, win - s * kStageFloats);
-            uint64_t* bar = &bars[s % p.nst];
-            yh_mbar_expect_tx(bar, (uint32_t)fl * 4u);
-            yh_bulk_load(sm_img + (size_t)(s % p.nst) * kStageFloats, p.y + a0 + (long long)s * kStageFloats,
-                         (uint32_t)fl * 4u, bar);
-        };
-        if (tid == 0) {
-            for (int s = 0; s < p.nst; ++s) yh_mbar_init(&bars[s], 1);
-            yh_mbar_fence_init();
-            for (int s = 0; s < min(p.nst, nstages); ++s) issue(s);
+    NT(1);
+    // ---------------- A: threshold + stage the survivors' rows ----------------
+    uint32_t tx = 0;
+    for (int base = 0; base < P; base += kThreads * kLoadUnroll) {
+        float val[kLoadUnroll];
+#pragma unroll
+        for (int u = 0; u < kLoadUnroll; ++u) {
+            const int i = base + u * kThreads + tid;
+            val[u] = 0.f;
+            if (i < P) val[u] = head ? __ldg(p.y + box_off(i) + 4) : __ldg(p.conf + (size_t)img * P + i);
         }
-        // floats past the last 16-byte boundary of the tensor (last image only, < 4 of them)
-        if (tid < (int)(f_end - a1) && p.resident) sm_img[win + tid] = __ldg(p.y + a1 + tid);
-        __syncthreads();
-
-        const int UF = p.unit_floats;
-        const int upp = g.version == 2 ? 1 : g.a;
-        int u_begin = 0;
-        for (int s = 0; s < nstages; ++s) {
-            yh_mbar_wait(&bars[s % p.nst], (uint32_t)((s / p.nst) & 1));
-            int u_end = p.units;
-            if (s + 1 < nstages) {
-                u_end = ((s + 1) * kStageFloats - shift) / UF;
-                if (u_end > p.units) u_end = p.units;
-            } else if (f_end > a1 && !p.resident) {
-                u_end = (win - shift) / UF;  // ring mode: the unit holding the tail is read from global below
-            }
-            for (int base = u_begin; base < u_end; base += kThreads) {
-                const int u = base + tid;
-                const unsigned rel = (unsigned)(shift + u * UF);
-                for (int b = 0; b < upp; ++b) {
-                    float conf = 0.f;
-                    bool pass = false;
-                    if (u < u_end) {
-                        const float to = sm_img[(rel + 5 * b + 4) & ring_mask];
-                        if (!(to < p.to_reject)) {  // far below the threshold: sigmoid not needed
-                            conf = yh_sigmoid(to);
-                            pass = conf >= p.conf_thre;  // models/utils.py:92
-                        }
-                    }
-                    const int slot = append(pass, conf, u * upp + b);
-                    if (!p.resident && slot >= 0 && slot < p.row_cache) {  // copy the row aside
-                        float* dst = row_cache + (size_t)slot * p.row_floats;
-                        for (int q = 0; q < 5; ++q) dst[q] = sm_img[(rel + 5 * b + q) & ring_mask];
-                        const unsigned coff = rel + (g.version == 2 ? 5 : 5 * g.a);
-                        for (int q = 0; q < p.c; ++q) dst[5 + q] = sm_img[(coff + q) & ring_mask];
-                    }
-                }
-            }
-            u_begin = u_end;
-            if (!p.resident && s >= 1 && s - 1 + p.nst < nstages) {
-                __syncthreads();  // everyone is done with stage s-1 (rows may straddle s-1 | s)
-                if (tid == 0) issue(s - 1 + p.nst);
-            }
-        }
-        // ring mode, last image of an unaligned tensor: its final unit straight from global memory
-        for (int u = u_begin + tid; u < p.units; u += kThreads) {  // at most one unit
-            const float* up = p.y + f_start + (long long)u * UF;
-            for (int b = 0; b < upp; ++b) {
-                const float conf = yh_sigmoid(__ldg(up + 5 * b + 4));
-                if (conf >= p.conf_thre) {
-                    const int slot = atomicAdd(&s_count, 1);
-                    if (slot < kSmemCand) { ca.u_conf[slot] = conf; ca.u_idx[slot] = u * upp + b; }
-                    else { cw.u_conf[slot] = conf; cw.u_idx[slot] = u * upp + b; }
-                    // slot >= row_cache semantics: rows of such slots are re-read from global memory
-                    if (slot < p.row_cache) {
-                        float* dst = row_cache + (size_t)slot * p.row_floats;
-                        for (int q = 0; q < 5; ++q) dst[q] = __ldg(up + 5 * b + q);
-                        const float* cp = up + (g.version == 2 ? 5 : 5 * g.a);
-                        for (int q = 0; q < p.c; ++q) dst[5 + q] = __ldg(cp + q);
-                    }
-                }
-            }
-        }
-    } else {
-        __syncthreads();
-        for (int base = 0; base < P; base += kThreads) {
-            const int i = base + tid;
+#pragma unroll
+        for (int u = 0; u < kLoadUnroll; ++u) {
+            const int i = base + u * kThreads + tid;
             float conf = 0.f;
             bool pass = false;
             if (i < P) {
-                if (p.src == SRC_GLOBAL) {
-                    const float* bp = g.version == 2
-                        ? p.y + ((size_t)img * g.preds + i) * g.box_stride
-                        : p.y + ((size_t)img * g.cells + i / g.a) * g.cell_floats + (i % g.a) * 5;
-                    conf = yh_sigmoid(__ldg(bp + 4));
-                } else {
-                    conf = __ldg(p.conf + (size_t)img * P + i);
+                if (!head) {
+                    conf = val[u];
+                    pass = conf >= p.conf_thre;
+                } else if (!(val[u] < p.to_reject)) {  // far below the threshold: sigmoid not needed
+                    conf = yh_sigmoid(val[u]);
+                    pass = conf >= p.conf_thre;  // models/utils.py:92
                 }
-                pass = conf >= p.conf_thre;
             }
-            append(pass, conf, i);
+            // warp-aggregated slot reservation; the first kSmemCand slots live in shared memory
+            const unsigned bal = __ballot_sync(0xffffffffu, pass);
+            if (bal) {
+                int slot0 = 0;
+                if (lane == 0) slot0 = atomicAdd(&s_count, __popc(bal));
+                slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+                if (pass) {
+                    const int slot = slot0 + __popc(bal & ((1u << lane) - 1u));
+                    if (slot < kSmemCand) { ca.u_conf[slot] = conf; ca.u_idx[slot] = i; }
+                    else { cw.u_conf[slot] = conf; cw.u_idx[slot] = i; }
+                    if (head && slot < p.stage_slots) {
+                        float* dst = stage + (size_t)slot * p.slot_floats;
+                        if (v2) {
+                            tx += stage_span(dst, box_off(i), 5 + C);
+                        } else {
+                            tx += stage_span(dst, box_off(i), 5);
+                            tx += stage_span(dst + 8, cls_off(i), C);
+                        }
+                    }
+                }
+            }
         }
     }
-    __syncthreads();
+    // two arrivals per thread: "my candidates are listed" and, carrying the bytes its bulk copies
+    // will deliver, "my rows are on their way".  Ranking only needs the list, so it runs while the
+    // rows are still in flight.
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(yh_smem_u32(&bar_list)) : "memory");
+    if (tx) yh_mbar_expect_tx(&bar, tx);
+    else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(yh_smem_u32(&bar)) : "memory");
+    NT(2);
+    yh_mbar_wait(&bar_list, 0);
+
     const int K = s_count;
     if (K > kSmemCand) {  // overflow: continue in the workspace arrays
         for (int k = tid; k < kSmemCand; k += kThreads) { cw.u_conf[k] = ca.u_conf[k]; cw.u_idx[k] = ca.u_idx[k]; }
@@ -322,76 +348,75 @@ __global__ void __launch_bounds__(kThreads) yh_nms_kernel(const NmsParams p) {
         __syncthreads();
     }
 
-    // pointers to the 5 box logits / C class logits of unsorted candidate `slot` (predictor idx)
-    auto box_ptr = [&](int slot, int idx) -> const float* {
-        if (p.src == SRC_TMA) {
-            if (p.resident) {
-                return g.version == 2 ? sm_img + shift + idx * p.unit_floats
-                                      : sm_img + shift + (idx / g.a) * p.unit_floats + (idx % g.a) * 5;
-            }
-            if (slot < p.row_cache) return row_cache + (size_t)slot * p.row_floats;
-        }
-        return g.version == 2 ? p.y + ((size_t)img * g.preds + idx) * g.box_stride
-                              : p.y + ((size_t)img * g.cells + idx / g.a) * g.cell_floats + (idx % g.a) * 5;
-    };
-    auto cls_ptr = [&](int slot, int idx) -> const float* {
-        if (p.src == SRC_TMA) {
-            if (p.resident) {
-                return g.version == 2 ? sm_img + shift + idx * p.unit_floats + 5
-                                      : sm_img + shift + (idx / g.a) * p.unit_floats + 5 * g.a;
-            }
-            if (slot < p.row_cache) return row_cache + (size_t)slot * p.row_floats + 5;
-        }
-        return g.version == 2 ? p.y + ((size_t)img * g.preds + idx) * g.box_stride + 5
-                              : p.y + ((size_t)img * g.cells + idx / g.a) * g.cell_floats + 5 * g.a;
-    };
-
-    // ---------------- B + C: rank, then decode into the ranked slot ----------------
-    for (int k = tid; k < K; k += kThreads) {
-        const float ck = ca.u_conf[k];
-        const int ik = ca.u_idx[k];
+    // ---------------- B: rank + decode, eight lanes per candidate ----------------
+    // A candidate's rank = how many candidates beat it: the eight lanes split the comparisons and
+    // fold with three shuffles.  Then (rows landed) four of them activate one box logit each and the
+    // group's first lane decodes the box into the ranked slot.
+    const int sub8 = tid & 7;
+    for (int k0 = 0; k0 < K; k0 += kThreads / 8) {
+        const int k = k0 + (tid >> 3);
+        const bool on = k < K;
+        const float ck = on ? ca.u_conf[k] : 0.f;
+        const int ik = on ? ca.u_idx[k] : 0;
         int rank = 0;
-        for (int j = 0; j < K; ++j) {
-            const float cj = ca.u_conf[j];
-            rank += (cj > ck || (cj == ck && ca.u_idx[j] < ik)) ? 1 : 0;
-        }
-        ca.s_slot[rank] = k;
-        ca.s_idx[rank] = ik;
-        ca.s_conf[rank] = ck;
-        float4 bx;
-        if (p.src != SRC_DECODED) {
-            const float* bp = box_ptr(k, ik);
-            const int cell = ik / g.a, a = ik - cell * g.a;
-            const int cy = cell / g.s_w, cx = cell - cy * g.s_w;
-            const float sx = yh_sigmoid(bp[0]), sy = yh_sigmoid(bp[1]);
-            float wa, ha;
-            if (g.version == 2) {
-                wa = expf(bp[2]);
-                ha = expf(bp[3]);
-            } else {
-                wa = yh_sigmoid(bp[2]);
-                ha = yh_sigmoid(bp[3]);
+        if (on) {
+            for (int j = sub8; j < K; j += 8) {
+                const float cj = ca.u_conf[j];
+                rank += (cj > ck || (cj == ck && ca.u_idx[j] < ik)) ? 1 : 0;
             }
-            const YhBox b = yh_decode_box(sx, sy, wa, ha, g.pw[a], g.ph[a], cx, cy, g.gw, g.gh);
-            bx = make_float4(b.x1, b.y1, b.x2, b.y2);
-        } else {
-            bx = __ldg(p.bbox + (size_t)img * P + ik);
-            if (p.labels) ca.s_lab[rank] = __ldg(p.labels + (size_t)img * P + ik);
         }
-        ca.s_box[rank] = bx;
+        rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+        rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+        rank += __shfl_xor_sync(0xffffffffu, rank, 4);
+        if (k0 == 0) {
+            NT(3);
+            yh_mbar_wait(&bar, 0);  // the staged rows
+        }
+        float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+        int lab = 0;
+        if (head) {
+            float act = 0.f;
+            if (on && sub8 < 4) {
+                const float tq = box_ptr(k, ik)[sub8];
+                act = (sub8 < 2 || !v2) ? yh_sigmoid(tq) : expf(tq);
+            }
+            const int l0 = lane & ~7;
+            const float sx = __shfl_sync(0xffffffffu, act, l0), sy = __shfl_sync(0xffffffffu, act, l0 + 1);
+            const float wa = __shfl_sync(0xffffffffu, act, l0 + 2), ha = __shfl_sync(0xffffffffu, act, l0 + 3);
+            if (on && sub8 == 0) {
+                const int cell = ik / A, a = ik - cell * A;
+                const int cy = cell / g.s_w, cx = cell - cy * g.s_w;
+                const YhBox b = yh_decode_box(sx, sy, wa, ha, g.pw[a], g.ph[a], cx, cy, g.gw, g.gh);
+                bx = make_float4(b.x1, b.y1, b.x2, b.y2);
+            }
+        } else if (on && sub8 == 0) {
+            bx = __ldg(p.bbox + (size_t)img * P + ik);
+            if (p.labels) lab = __ldg(p.labels + (size_t)img * P + ik);
+        }
+        if (on && sub8 == 0) {
+            ca.s_box[rank] = bx;
+            ca.s_area[rank] = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
+            ca.s_slot[rank] = k;
+            ca.s_idx[rank] = ik;
+            ca.s_conf[rank] = ck;
+            if (!head && p.labels) ca.s_lab[rank] = lab;
+        }
     }
+    if (K == 0) yh_mbar_wait(&bar, 0);
     __syncthreads();
 
-    const bool use_lab = p.src != SRC_DECODED ? (p.class_aware != 0) : (p.labels != nullptr);
-    const int sub = tid & 3;
-    if (use_lab && p.src != SRC_DECODED) {  // label of every candidate (argmax of cls_spec)
-        for (int k0 = 0; k0 < K; k0 += kThreads / 4) {
-            const int k = k0 + (tid >> 2);
+    NT(4);
+    const bool use_lab = head ? (p.class_aware != 0) : (p.labels != nullptr);
+    constexpr int kPick = 8;  // lanes per class pick
+    const int sub = tid & (kPick - 1);
+    if (use_lab && head) {  // label of every candidate (argmax of cls_spec)
+        for (int k0 = 0; k0 < K; k0 += kThreads / kPick) {
+            const int k = k0 + tid / kPick;
             const bool act = k < K;
             int lab;
             float sc;
-            quad_class_pick(act ? cls_ptr(ca.s_slot[k], ca.s_idx[k]) : nullptr, p.c, act ? ca.s_conf[k] : 0.f, sub,
-                            act, nullptr, &lab, &sc);
+            group_class_pick<kPick>(act ? cls_ptr(ca.s_slot[k], ca.s_idx[k]) : nullptr, C, act ? ca.s_conf[k] : 0.f, sub,
+                                    act, nullptr, &lab, &sc);
             if (act && sub == 0) ca.s_lab[k] = lab;
         }
         __syncthreads();
@@ -403,7 +428,7 @@ __global__ void __launch_bounds__(kThreads) yh_nms_kernel(const NmsParams p) {
         const int tn = min(kTile, K - base);
         const int W = (tn + 31) >> 5;
         // (1) against the boxes kept in earlier tiles
-        {
+        if (warp < kTileWords) {
             bool dead = false;
             if (tid < tn && base > 0) {
                 const float4 bj = ca.s_box[base + tid];
@@ -418,77 +443,102 @@ __global__ void __launch_bounds__(kThreads) yh_nms_kernel(const NmsParams p) {
                 }
             }
             const unsigned bal = __ballot_sync(0xffffffffu, dead);
-            if (lane == 0) rem0[warp] = bal;  // kThreads == kTile: warp w covers word w
+            if (lane == 0) rem0[warp] = bal;  // warp w < kTileWords covers word w of the tile
         }
-        if (tid < kTileWords) nzrow[tid] = 0u;
         __syncthreads();
-        // (2) intra-tile mask: word (i, w) = candidates j in [32w, 32w+32) suppressed by i; each
-        //     warp takes rows i = warp, warp + 8, ... and walks the words to the right of i
-        for (int i = warp; i < tn; i += kWarps) {
-            const float4 bi = ca.s_box[base + i];
-            const int li = use_lab ? ca.s_lab[base + i] : 0;
-            unsigned any = 0u;
-            for (int w = i >> 5; w < W; ++w) {
-                const int j = w * 32 + lane;
+        // (2) intra-tile mask, by column: word (j, w) = candidates i in [32w, 32w+32), ranked before j,
+        //     that suppress j if kept; each warp takes columns j = warp, warp + kWarps, ... and walks
+        //     the words up to j's own (two at a time: the tests are independent)
+        if (base == 0) NT(5);
+        for (int j = warp; j < tn; j += kWarps) {
+            const float4 bj = ca.s_box[base + j];
+            const float aj = ca.s_area[base + j];
+            const int lj = use_lab ? ca.s_lab[base + j] : 0;
+#pragma unroll 2
+            for (int w = 0; w <= (j >> 5); ++w) {
+                const int i = w * 32 + lane;
                 bool bit = false;
-                if (j > i && j < tn) {
-                    bit = suppresses(bi, ca.s_box[base + j], thr);
-                    if (use_lab) bit = bit && li == ca.s_lab[base + j];
+                if (i < j) {
+                    bit = suppresses(ca.s_box[base + i], ca.s_area[base + i], bj, aj, thr);
+                    if (use_lab) bit = bit && lj == ca.s_lab[base + i];
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, bit);
-                if (lane == 0) mask[i * kTileWords + w] = m;
-                any |= m;
+                if (lane == 0) mask[j * kTileWords + w] = m;
             }
-            if (any && lane == 0) atomicOr(&nzrow[i >> 5], 1u << (i & 31));
         }
         __syncthreads();
-        // (3) one warp resolves the greedy order: only rows that are still alive AND suppress
-        //     something need a sequential step; lane l < W owns removed-word l
+        if (base == 0) NT(7);
+        // (3) one warp resolves the greedy order by fixed-point iteration instead of a serial walk:
+        //     alive[j] = !dead0[j] && no alive i < j suppresses j.  Candidate j's value is final once
+        //     all i < j are final, so after t sweeps the first t candidates are right; in practice the
+        //     suppression chains are 2-3 deep and the sweep converges in as many steps (<= tn + 1).
+        //     The same warp then appends the survivors, in rank order, to the keep list.
         if (warp == 0) {
-            unsigned rem = lane < W ? rem0[lane] : 0xffffffffu;
-            if (lane == W - 1 && (tn & 31)) rem |= ~0u << (tn & 31);  // bits past the tile end
-            const unsigned nz = lane < W ? nzrow[lane] : 0u;
-            for (int w = 0; w < W; ++w) {
-                const unsigned nzw = __shfl_sync(0xffffffffu, nz, w);
-                unsigned done = 0u;
-                while (true) {
-                    const unsigned cur = __shfl_sync(0xffffffffu, rem, w);
-                    const unsigned todo = ~cur & nzw & ~done;
-                    if (!todo) break;
-                    const int b = __ffs(todo) - 1;
-                    done |= 1u << b;
-                    const int i = w * 32 + b;
-                    if (lane >= w && lane < W) rem |= mask[i * kTileWords + lane];
+            unsigned alive[kTileWords], dead0[kTileWords];
+#pragma unroll
+            for (int w = 0; w < kTileWords; ++w) {
+                dead0[w] = w < W ? rem0[w] : 0xffffffffu;
+                if (w == W - 1 && (tn & 31)) dead0[w] |= ~0u << (tn & 31);  // bits past the tile end
+                alive[w] = ~dead0[w];
+            }
+            if (W <= 2) {
+                // common case (<= 64 candidates): the lane's two columns live in registers
+                const unsigned c00 = lane < tn ? mask[lane * kTileWords] : 0u;
+                const unsigned c10 = 32 + lane < tn ? mask[(32 + lane) * kTileWords] : 0u;
+                const unsigned c11 = 32 + lane < tn ? mask[(32 + lane) * kTileWords + 1] : 0u;
+                for (int sweep = 0; sweep <= tn; ++sweep) {
+                    const unsigned n0 = __ballot_sync(0xffffffffu, (c00 & alive[0]) == 0u) & ~dead0[0];
+                    const unsigned n1 = __ballot_sync(0xffffffffu, ((c10 & n0) | (c11 & alive[1])) == 0u) & ~dead0[1];
+                    const bool same = n0 == alive[0] && n1 == alive[1];
+                    alive[0] = n0;
+                    alive[1] = n1;
+                    if (same) break;
+                }
+            } else {
+                for (int sweep = 0; sweep <= tn; ++sweep) {
+                    bool changed = false;
+#pragma unroll
+                    for (int m = 0; m < kTileWords; ++m) {
+                        if (m < W) {  // (warp-uniform)
+                            const int j = 32 * m + lane;
+                            bool a = false;
+                            if (j < tn) {
+                                unsigned hit = 0u;
+#pragma unroll
+                                for (int w = 0; w < kTileWords; ++w)
+                                    if (w <= m) hit |= mask[j * kTileWords + w] & alive[w];
+                                a = hit == 0u;
+                            }
+                            const unsigned nw = __ballot_sync(0xffffffffu, a) & ~dead0[m];
+                            changed = changed || nw != alive[m];
+                            alive[m] = nw;  // (later words of this sweep already see it)
+                        }
+                    }
+                    if (!changed) break;
                 }
             }
-            if (lane < W) rem0[lane] = rem;
+            int kept_n = s_kept;
+#pragma unroll
+            for (int m = 0; m < kTileWords; ++m) {
+                if (m < W) {
+                    if ((alive[m] >> lane) & 1u) ca.keep[kept_n + __popc(alive[m] & ((1u << lane) - 1u))] = base + 32 * m + lane;
+                    kept_n += __popc(alive[m]);
+                }
+            }
+            if (lane == 0) s_kept = kept_n;
         }
         __syncthreads();
-        // survivors of the tile, in rank order, appended to the keep list
-        {
-            int before = s_kept, total = 0;
-            for (int w = 0; w < W; ++w) {
-                const int cnt = __popc(~rem0[w]);
-                if (w < (tid >> 5)) before += cnt;
-                total += cnt;
-            }
-            if (tid < tn) {
-                const unsigned word = rem0[tid >> 5];
-                if (!((word >> (tid & 31)) & 1u)) ca.keep[before + __popc(~word & ((1u << (tid & 31)) - 1u))] = base + tid;
-            }
-            __syncthreads();
-            if (tid == 0) s_kept += total;
-            __syncthreads();
-        }
+        if (base == 0) NT(8);
     }
 
+    NT(12);
     // ---------------- E: emit ----------------
     const int kept = s_kept;
     if (tid == 0) p.keep_cnt[img] = kept;
     const int nout = min(kept, p.max_out);
-    const bool want_cls = p.src != SRC_DECODED && (p.out_cls_spec || p.out_label || p.out_score);
-    for (int t0 = 0; t0 < nout; t0 += kThreads / 4) {
-        const int t = t0 + (tid >> 2);
+    const bool want_cls = head && (p.out_cls_spec || p.out_label || p.out_score);
+    for (int t0 = 0; t0 < nout; t0 += kThreads / kPick) {
+        const int t = t0 + tid / kPick;
         const bool act = t < nout;
         int i = 0, idx = 0;
         float conf = 0.f;
@@ -508,14 +558,31 @@ __global__ void __launch_bounds__(kThreads) yh_nms_kernel(const NmsParams p) {
         if (want_cls) {
             int lab;
             float sc;
-            quad_class_pick(act ? cls_ptr(ca.s_slot[i], idx) : nullptr, p.c, conf, sub, act,
-                            (act && p.out_cls_spec) ? p.out_cls_spec + o * p.c : nullptr, &lab, &sc);
+            group_class_pick<kPick>(act ? cls_ptr(ca.s_slot[i], idx) : nullptr, C, conf, sub, act,
+                                    (act && p.out_cls_spec) ? p.out_cls_spec + o * C : nullptr, &lab, &sc);
             if (act && sub == 2) {
                 if (p.out_label) p.out_label[o] = lab;
                 if (p.out_score) p.out_score[o] = sc;
             }
         }
     }
+    NT(13);
+}
+
+template <int TV, int TA, int TC>
+int launch_variant(const NmsParams& p, size_t smem, void* stream) {
+    static size_t configured[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (smem > 32 * 1024 && smem > configured[dev]) {
+        int rc = yh_check_cuda(cudaFuncSetAttribute(yh_nms_kernel<TV, TA, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                               "cudaFuncSetAttribute(nms)");
+        if (rc) return rc;
+        configured[dev] = smem;
+    }
+    yh_nms_kernel<TV, TA, TC><<<(unsigned)p.n, kThreads, smem, (cudaStream_t)stream>>>(p);
+    return yh_check_cuda(cudaGetLastError(), "yh_nms launch");
 }
 
 int launch(NmsParams& p, void* ws, size_t ws_bytes, void* stream) {
@@ -532,23 +599,12 @@ int launch(NmsParams& p, void* ws, size_t ws_bytes, void* stream) {
         p.ws = reinterpret_cast<unsigned char*>(ws);
         p.ws_per_image = cand_bytes(p.p);
     }
-    size_t smem = cand_bytes(kSmemCand);
-    if (p.src == SRC_TMA) {
-        smem += (size_t)p.img_smem_floats * 4;
-        if (!p.resident) smem += (size_t)p.row_cache * p.row_floats * 4;
-    }
-    static size_t configured[64] = {0};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64) dev = 0;
-    if (smem > 32 * 1024 && smem > configured[dev]) {
-        int rc = yh_check_cuda(cudaFuncSetAttribute(yh_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                               "cudaFuncSetAttribute(nms)");
-        if (rc) return rc;
-        configured[dev] = smem;
-    }
-    yh_nms_kernel<<<(unsigned)p.n, kThreads, smem, (cudaStream_t)stream>>>(p);
-    return yh_check_cuda(cudaGetLastError(), "yh_nms launch");
+    const size_t smem = (size_t)p.stage_slots * p.slot_floats * 4 + cand_bytes(kSmemCand);
+    // compile-time geometries for the shapes the reference uses (VOC: YOLOv2 5 anchors x 20 classes,
+    // YOLOv1 B=2, C=20); anything else, and decoded-box input, runs the run-time-geometry variant
+    if (p.src == SRC_HEAD && p.g.version == 2 && p.g.a == 5 && p.c == 20) return launch_variant<2, 5, 20>(p, smem, stream);
+    if (p.src == SRC_HEAD && p.g.version == 1 && p.g.a == 2 && p.c == 20) return launch_variant<1, 2, 20>(p, smem, stream);
+    return launch_variant<0, 0, 0>(p, smem, stream);
 }
 
 int postprocess_impl(int version, const float* y, int n, int s_h, int s_w, int a, int c,
@@ -562,6 +618,7 @@ int postprocess_impl(int version, const float* y, int n, int s_h, int s_w, int a
     if (rc) return rc;
     YH_REQUIRE(y, YH_ERR_INVALID, "y is NULL");
     YH_REQUIRE(((uintptr_t)y & 3) == 0, YH_ERR_INVALID, "y must be 4-byte aligned");
+    p.src = SRC_HEAD;
     p.y = y;
     p.n = n; p.p = p.g.preds; p.c = c;
     p.conf_thre = conf_thre; p.iou_thre = iou_thre;
@@ -579,27 +636,12 @@ int postprocess_impl(int version, const float* y, int n, int s_h, int s_w, int a
 
     p.img_floats = p.g.cells * p.g.cell_floats;
     p.total_floats = (long long)n * p.img_floats;
-    p.unit_floats = version == 2 ? p.g.box_stride : p.g.cell_floats;
-    p.units = version == 2 ? p.g.preds : p.g.cells;
-    p.row_floats = 5 + c;
-    // staged (TMA) source needs a 16-byte aligned tensor and units that fit one stage
-    p.src = SRC_GLOBAL;
-    if (((uintptr_t)y & 15) == 0 && p.unit_floats * 2 <= kStageFloats) {
-        p.src = SRC_TMA;
-        const int stages_needed = (p.img_floats + 3 + 4 + kStageFloats - 1) / kStageFloats;
-        if (stages_needed <= 6) {  // <= 96 KB: keep the whole image resident (two CTAs per SM)
-            p.resident = 1;
-            p.nst = stages_needed;
-            p.img_smem_floats = (p.img_floats + 8 + 31) & ~31;  // window + tail, not whole stages
-        } else {
-            p.resident = 0;
-            p.nst = kRingStages;
-            p.img_smem_floats = kRingStages * kStageFloats;
-            int rows = kRowCache;
-            while (rows > 32 && (size_t)rows * p.row_floats * 4 > 32 * 1024) rows >>= 1;
-            p.row_cache = rows;
-        }
-    }
+    p.use_tma = ((uintptr_t)y & 15) == 0;
+    // a staged row: [<= 3 floats of alignment shift | 5 box logits | C class logits], for v1 the box
+    // logits (slot floats 0..7) and the cell's class logits (from float 8) are two separate windows
+    p.slot_floats = 8 + ((c + 3 + 3) & ~3);
+    int slots = kStageBytesMax / (p.slot_floats * 4);
+    p.stage_slots = slots < kSmemCand ? slots : kSmemCand;
     return launch(p, ws, ws_bytes, stream);
 }
 

@@ -16,6 +16,7 @@
 
 #ifdef YH_X_TRACE
 extern "C" int yh_x_trace_copy(unsigned long long*, int);
+extern "C" int yh_x_ntrace_copy(unsigned long long*, int);
 #endif
 
 int main(int argc, char** argv) {
@@ -109,6 +110,22 @@ int main(int argc, char** argv) {
         for (int sl = 0; sl < 16; ++sl) {
             std::vector<double> v; for (int b = 0; b < G; ++b) if (tr[b * 16 + sl] >= t0 && tr[b*16+sl] < t0 + 1000000) v.push_back((double)(tr[b * 16 + sl] - t0));
             if (v.empty()) continue; std::sort(v.begin(), v.end());
+            printf("  %-22s n=%3zu min %6.0f  p10 %6.0f  med %6.0f  p90 %6.0f  max %6.0f ns\n", nm[sl], v.size(), v[0], v[v.size() / 10], v[v.size() / 2], v[v.size() * 9 / 10], v.back());
+        }
+    }
+#endif
+#ifdef YH_X_TRACE
+    {
+        for (int rep = 0; rep < 3; ++rep) { post(sets[rep]); CK(cudaStreamSynchronize(st)); }
+        std::vector<unsigned long long> tr(4096 * 16);
+        yh_x_ntrace_copy(tr.data(), 4096 * 16);
+        const int G = N;
+        unsigned long long t0 = ~0ull; for (int b = 0; b < G; ++b) t0 = std::min(t0, tr[b * 16]);
+        const char* nm[16] = {"nms start", "init done", "A issued+arrived", "rank done", "B decode done", "D1 done", "D mask zeroed", "D pairs done", "D fixed point done", "-", "-", "-", "D done", "E emit done", "-", "-"};
+        for (int sl = 0; sl < 14; ++sl) {
+            if (nm[sl][0] == '-') continue;
+            std::vector<double> v; for (int b = 0; b < G; ++b) v.push_back((double)(tr[b * 16 + sl] - t0));
+            std::sort(v.begin(), v.end());
             printf("  %-22s n=%3zu min %6.0f  p10 %6.0f  med %6.0f  p90 %6.0f  max %6.0f ns\n", nm[sl], v.size(), v[0], v[v.size() / 10], v[v.size() / 2], v[v.size() * 9 / 10], v.back());
         }
     }
