@@ -50,23 +50,24 @@ constexpr int kChunks = YH_X_CHUNKS;      // TMA chunks (mbarriers) per tile
 constexpr int kAhead = YH_X_AHEAD;        // chunks in flight per CTA
 constexpr int kTileBytesMax = 40 * 1024;  // shared-memory stage of one tile
 constexpr int kMaxGrid = 2048;
-constexpr int kPartials = 8;              // floats per CTA in the workspace (6 used)
 constexpr int kClsRegs = 4;               // class logits per lane kept in registers (C <= 128)
 constexpr int kWindow = 128;              // speculative record window (records) per tile
 constexpr int kSlots = 24;                // patches (records processed during the dense pass) per tile
 constexpr int kPatchFloats = 32;          // floats per patch row: 5 + C must fit (else the record waits for the end)
 
 #ifdef YH_X_TRACE
-__device__ unsigned long long g_xtrace[4096 * 16];
+__device__ unsigned long long g_xtrace[4096 * 24];
+__device__ unsigned int g_rcycles[4096 * 16];
 __device__ __forceinline__ unsigned long long xt_now() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
 #define XT_DECL unsigned long long xt_[8] = {0, 0, 0, 0, 0, 0, 0, 0}
-#define XT(slot) do { if ((threadIdx.x & 31) == 0) xt_[slot] = xt_now(); } while (0)
-#define XT_FLUSH do { if (threadIdx.x == 0) for (int i_ = 0; i_ < 8; ++i_) g_xtrace[blockIdx.x * 16 + i_] = xt_[i_]; \
-                      if (threadIdx.x == kDense) for (int i_ = 0; i_ < 8; ++i_) g_xtrace[blockIdx.x * 16 + 8 + i_] = xt_[i_]; } while (0)
+#define XT(slot) do { if ((threadIdx.x & 31) == 0 || threadIdx.x == kThreads - 1) xt_[slot] = xt_now(); } while (0)
+#define XT_FLUSH do { if (threadIdx.x == 0) for (int i_ = 0; i_ < 8; ++i_) g_xtrace[blockIdx.x * 24 + i_] = xt_[i_]; \
+                      if (threadIdx.x == kDense) for (int i_ = 0; i_ < 8; ++i_) g_xtrace[blockIdx.x * 24 + 8 + i_] = xt_[i_]; \
+                      if (threadIdx.x == kThreads - 1) for (int i_ = 0; i_ < 8; ++i_) g_xtrace[blockIdx.x * 24 + 16 + i_] = xt_[i_]; } while (0)
 #else
 #define XT_DECL
 #define XT(slot) do { } while (0)
@@ -83,8 +84,7 @@ struct TrainParams {
     float* loss;
     int32_t* resp;
     float* iou_resp;
-    float* partials;      // [gridDim][kPartials]
-    unsigned int* ticket;
+    unsigned long long* acc;  // [8]: six fixed-point sums, [6] non-finite flags, [7] ticket
     int total_cells;
     int tile_cells;       // cells per tile (multiple of 4)
     int num_tiles;
@@ -323,7 +323,6 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
     __shared__ __align__(16) int4 s_win[3 * kWindow];  // speculative window of ground-truth records
     __shared__ __align__(8) uint64_t s_bar[kChunks + 1];  // one mbarrier per chunk, + the window's
     __shared__ float red[kWarps * 6];
-    __shared__ double dred[kWarps * 6];
     __shared__ int s_rjj[kWindow];   // the tile's records in CSR order: index into gt ...
     __shared__ int s_rlc[kWindow];   // ... and tile-local cell
     __shared__ __align__(16) float s_patch[kSlots * kPatchFloats];  // record gradients waiting for the dense pass
@@ -331,7 +330,6 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
     __shared__ int s_pr[kSlots];                                  // responsible anchor of a patch
     __shared__ int s_nrec, s_npatch;  // records listed (-1: list incomplete, scan gt instead) / patched
     __shared__ int s_ready;           // tile index + 1 once the record list of that tile is published
-    __shared__ bool is_last;
 
     const YhGeom& g = p.g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -361,6 +359,61 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
     // records can be processed during the dense pass when their 5+C gradients fit a patch row
     const bool patchable = WRITE_DY && 5 + C <= kPatchFloats;
     uint32_t phase = 0;  // parity of the mbarriers: every barrier completes once per tile
+
+    // ---- the six partial sums of the CTA -> global totals -> (last CTA) terms and loss.
+    // Every lane carries partial sums (dense rows; record channels by lane role): the warps fold
+    // theirs into shared memory, ONE thread folds the warps in a fixed order and adds the CTA's sums
+    // onto six 64-bit fixed-point accumulators with integer atomics (exact and order-independent, so
+    // the totals are deterministic), then takes a ticket; the last ticket holder reads the totals
+    // back and writes terms and loss.  The publishing thread is one that never stores to dy, so its
+    // fence only waits for its own six atomics, not for the CTA's gradient stores to drain.
+    constexpr int kPublisher = kThreads - 1;
+    auto write_warp_sums = [&]() {
+        const float s_no = yh_warp_sum(sums.no);
+        const float s_xy = yh_warp_sum(sums.xy), s_wh = yh_warp_sum(sums.wh), s_conf = yh_warp_sum(sums.conf);
+        const float s_nr = yh_warp_sum(sums.nr), s_cls = yh_warp_sum(sums.cls);
+        if (lane == 0) {
+            float* r = red + warp * 6;
+            r[0] = s_xy; r[1] = s_wh; r[2] = s_conf; r[3] = s_no; r[4] = s_nr; r[5] = s_cls;
+        }
+    };
+    auto publish = [&]() {
+        constexpr double kFix = 4294967296.0;  // 2^32: 2.3e-10 resolution, totals up to 2^31
+        XT(4);
+        unsigned flags = 0u;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            float a = 0.f;
+            for (int w = 0; w < kWarps; ++w) a += red[w * 6 + q];
+            if (a >= 0.f && a < 1073741824.f) atomicAdd(p.acc + q, (unsigned long long)((double)a * kFix + 0.5));
+            else flags |= 1u << q;  // NaN / inf / out of range: the term becomes NaN, like the reference's
+        }
+        if (flags) atomicOr(p.acc + 6, (unsigned long long)flags);
+        __threadfence();
+        XT(5);
+        const unsigned long long tk = atomicAdd(p.acc + 7, 1ull);
+        XT(6);
+        if (tk == gridDim.x - 1) {
+            __threadfence();
+            double tot[6];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) tot[q] = (double)__ldcg(p.acc + q) / kFix;
+            const unsigned bad = (unsigned)__ldcg(p.acc + 6);
+            const double nan = __longlong_as_double(0x7ff8000000000000ll);
+            const double t0 = (bad & 1u) ? nan : tot[0] * p.inv_den[0];
+            const double t1 = (bad & 2u) ? nan : tot[1] * p.inv_den[1];
+            const double t2 = (bad & 4u) ? nan : tot[2] * p.inv_den[2];
+            const double t3 = (bad & 24u) ? nan : (tot[3] - tot[4]) * p.inv_den[3];
+            const double t4 = (bad & 32u) ? nan : tot[5] * p.inv_den[4];
+            p.terms[0] = (float)t0; p.terms[1] = (float)t1; p.terms[2] = (float)t2;
+            p.terms[3] = (float)t3; p.terms[4] = (float)t4;
+            p.loss[0] = (float)(p.lam[0] * t0 + p.lam[1] * t1 + p.lam[2] * t2 + p.lam[3] * t3 + p.lam[4] * t4);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) p.acc[q] = 0ull;  // ready for the next launch
+            XT(7);
+        }
+    };
+    bool sums_final = false;
 
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, phase ^= 1u) {
         // everything is 32-bit: train_impl checks that the tensor has < 2^31 floats
@@ -459,10 +512,16 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
                 rr.hd = rp[0];
                 rr.tt = *reinterpret_cast<const float4*>(rp + 1);
                 rr.bb = *reinterpret_cast<const float4*>(rp + 2);
+#ifdef YH_X_TRACE
+                const long long rc0 = clock64();
+#endif
                 const int r = process_record<2>(p, version, A, C, rr, jj, s_tile + lcell * cf, nullptr,
                                                 s_patch + i * kPatchFloats, s_pdense + i, kn_of(lcell * cf), lane,
                                                 my_pw, my_ph, sums);
                 if (lane == 0) s_pr[i] = r;
+#ifdef YH_X_TRACE
+                if (lane == 0) g_rcycles[blockIdx.x * 16 + warp] = (unsigned int)(clock64() - rc0);
+#endif
             }
             return true;
         };
@@ -577,10 +636,15 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
         }
 
         // ---------------- the records' gradients go onto the dense rows ----------------
+        const bool last_tile = t + (int)gridDim.x >= p.num_tiles;
+        if (last_tile) write_warp_sums();  // (final unless records are left over, see below)
         XT(1);
         __syncthreads();  // the tile's dense dL/dy is written (and visible to the whole CTA); patches are ready
         XT(2);
         const int nrec = s_nrec, npatch = s_npatch;
+        // (no records left over: the sums folded before the barrier are final and get published
+        //  right after the patch stores, without another CTA barrier)
+        if (last_tile && !(nrec < 0 || nrec > npatch)) sums_final = true;
         if (record_warp) {
             for (int i = 0; i < npatch; ++i) {
                 const int lcell = s_rlc[i], r = s_pr[i];
@@ -637,79 +701,19 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
     if (sums.no == 123.456f) p.terms[0] = sums.no + sums.xy + sums.cls;
     return;
 #endif
-    // ---------------- block reduction of the six partial sums ----------------
-    // every lane carries partial sums (dense rows; record channels by lane role): fold the warp
-    const float s_no = yh_warp_sum(sums.no);
-    const float s_xy = yh_warp_sum(sums.xy), s_wh = yh_warp_sum(sums.wh), s_conf = yh_warp_sum(sums.conf);
-    const float s_nr = yh_warp_sum(sums.nr), s_cls = yh_warp_sum(sums.cls);
-    if (lane == 0) {
-        float* r = red + warp * 6;
-        r[0] = s_xy; r[1] = s_wh; r[2] = s_conf; r[3] = s_no; r[4] = s_nr; r[5] = s_cls;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int w = 0; w < kWarps; ++w)
-            for (int q = 0; q < 6; ++q) acc[q] += red[w * 6 + q];
-        float4* dst = reinterpret_cast<float4*>(p.partials) + 2 * blockIdx.x;
-        dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        dst[1] = make_float4(acc[4], acc[5], 0.f, 0.f);
-        XT(4);
-        __threadfence();
-        XT(5);
-        const unsigned t = atomicAdd(p.ticket, 1u);
-        is_last = (t == gridDim.x - 1);
-        if (is_last) __threadfence();  // acquire side, once; the CTA barrier below extends it to the CTA
-        XT(6);
-    }
-    __syncthreads();
-    if (is_last) {
-        // the whole last CTA folds the per-CTA partials: all loads in flight at once (one L2 round
-        // trip), fixed assignment and order -> deterministic
-        constexpr int kFold = 4;  // covers kFold * kThreads CTAs without a second round trip
-        const float4* part4 = reinterpret_cast<const float4*>(p.partials);
-        double acc[6] = {0, 0, 0, 0, 0, 0};
-        for (unsigned b0 = 0; b0 < gridDim.x; b0 += kFold * kThreads) {
-            float4 lo[kFold], hi[kFold];
-#pragma unroll
-            for (int u = 0; u < kFold; ++u) {
-                const unsigned b = b0 + u * kThreads + tid;
-                lo[u] = hi[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (b < gridDim.x) { lo[u] = __ldcg(part4 + 2 * b); hi[u] = __ldcg(part4 + 2 * b + 1); }
-            }
-#pragma unroll
-            for (int u = 0; u < kFold; ++u) {
-                acc[0] += (double)lo[u].x; acc[1] += (double)lo[u].y; acc[2] += (double)lo[u].z;
-                acc[3] += (double)lo[u].w; acc[4] += (double)hi[u].x; acc[5] += (double)hi[u].y;
-            }
-        }
-        for (int q = 0; q < 6; ++q)
-            for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
-        if (lane == 0)
-            for (int q = 0; q < 6; ++q) dred[warp * 6 + q] = acc[q];
+    if (!sums_final) {  // (records were left over in the last tile)
+        write_warp_sums();
         __syncthreads();
-        if (tid == 0) {
-            for (int q = 0; q < 6; ++q) {
-                acc[q] = 0.0;
-                for (int w = 0; w < kWarps; ++w) acc[q] += dred[w * 6 + q];
-            }
-            const double t0 = acc[0] * p.inv_den[0];
-            const double t1 = acc[1] * p.inv_den[1];
-            const double t2 = acc[2] * p.inv_den[2];
-            const double t3 = (acc[3] - acc[4]) * p.inv_den[3];
-            const double t4 = acc[5] * p.inv_den[4];
-            p.terms[0] = (float)t0; p.terms[1] = (float)t1; p.terms[2] = (float)t2;
-            p.terms[3] = (float)t3; p.terms[4] = (float)t4;
-            p.loss[0] = (float)(p.lam[0] * t0 + p.lam[1] * t1 + p.lam[2] * t2 + p.lam[3] * t3 + p.lam[4] * t4);
-            *p.ticket = 0u;  // ready for the next launch
-            XT(7);
-        }
     }
+    if (tid == kPublisher) publish();
     XT_FLUSH;
 }
 #ifdef YH_X_TRACE
 extern "C" YH_API int yh_x_trace_copy(unsigned long long* host, int n) {
     return (int)cudaMemcpyFromSymbol(host, g_xtrace, (size_t)n * 8);
+}
+extern "C" YH_API int yh_x_rcycles_copy(unsigned int* host, int n) {
+    return (int)cudaMemcpyFromSymbol(host, g_rcycles, (size_t)n * 4);
 }
 #endif
 
@@ -763,8 +767,8 @@ int train_impl(int version, const float* y, int n, int s_h, int s_w, int a, int 
 
     p.y = y; p.dy = dy; p.gt = gt; p.gt_off = gt_off;
     p.terms = terms; p.loss = loss; p.resp = resp; p.iou_resp = iou_resp;
-    p.partials = reinterpret_cast<float*>(ws);
-    p.ticket = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(ws) + (size_t)kMaxGrid * kPartials * 4);
+    YH_REQUIRE(((uintptr_t)ws & 7) == 0, YH_ERR_INVALID, "workspace must be 8-byte aligned");
+    p.acc = reinterpret_cast<unsigned long long*>(ws);
     const long long total_cells = (long long)n * p.g.cells;
     const int cf = p.g.cell_floats;
     YH_REQUIRE(total_cells * cf < (1ll << 31), YH_ERR_UNSUPPORTED, "head tensor has 2^31 or more floats");
@@ -814,7 +818,7 @@ int train_impl(int version, const float* y, int n, int s_h, int s_w, int a, int 
 
 extern "C" {
 
-size_t yh_train_workspace_bytes(void) { return (size_t)kMaxGrid * kPartials * 4 + 128; }
+size_t yh_train_workspace_bytes(void) { return 256; }
 
 int yh_v2_train(const float* y, int n, int s_h, int s_w, int a, int c, const float* anchors_wh_host,
                 float img_h, float img_w, const YhGt* gt, const int32_t* gt_off, int m_local,

@@ -17,6 +17,7 @@
 #ifdef YH_X_TRACE
 extern "C" int yh_x_trace_copy(unsigned long long*, int);
 extern "C" int yh_x_ntrace_copy(unsigned long long*, int);
+extern "C" int yh_x_rcycles_copy(unsigned int*, int);
 #endif
 
 int main(int argc, char** argv) {
@@ -101,20 +102,29 @@ int main(int argc, char** argv) {
     {
         CK(cudaMemset(sets[0].dy, 0, 16));
         for (int rep = 0; rep < 3; ++rep) { train(sets[rep]); CK(cudaStreamSynchronize(st)); }
-        std::vector<unsigned long long> tr(4096 * 16);
-        yh_x_trace_copy(tr.data(), 4096 * 16);
+        std::vector<unsigned long long> tr(4096 * 24);
+        yh_x_trace_copy(tr.data(), 4096 * 24);
         const int G = 570;
-        unsigned long long t0 = ~0ull; for (int b = 0; b < G; ++b) t0 = std::min(t0, tr[b * 16]);
-        const char* nm[16] = {"t0 start", "t0 dense done", "t0 after sync B", "t0 tile loop done", "t0 partial stored", "t0 fence done", "t0 ticket done", "t0 final (last only)",
-                              "rw start", "rw before sync B", "rw after sync B", "rw tile loop done", "rw offsets arrived", "rw list built", "rw records done", "rw -"};
-        for (int sl = 0; sl < 16; ++sl) {
-            std::vector<double> v; for (int b = 0; b < G; ++b) if (tr[b * 16 + sl] >= t0 && tr[b*16+sl] < t0 + 1000000) v.push_back((double)(tr[b * 16 + sl] - t0));
+        unsigned long long t0 = ~0ull; for (int b = 0; b < G; ++b) t0 = std::min(t0, tr[b * 24]);
+        const char* nm[24] = {"t0 start", "t0 dense done", "t0 after sync B", "t0 tile loop done", "-", "-", "-", "-",
+                              "rw start", "rw before sync B", "rw after sync B", "rw tile loop done", "rw offsets arrived", "rw list built", "rw records done", "-",
+                              "pub start", "-", "-", "pub tile loop done", "pub publish begins", "pub fence done", "pub ticket done", "pub final (last only)"};
+        for (int sl = 0; sl < 24; ++sl) {
+            if (nm[sl][0] == '-') continue;
+            std::vector<double> v; for (int b = 0; b < G; ++b) if (tr[b * 24 + sl] >= t0 && tr[b*24+sl] < t0 + 1000000) v.push_back((double)(tr[b * 24 + sl] - t0));
             if (v.empty()) continue; std::sort(v.begin(), v.end());
             printf("  %-22s n=%3zu min %6.0f  p10 %6.0f  med %6.0f  p90 %6.0f  max %6.0f ns\n", nm[sl], v.size(), v[0], v[v.size() / 10], v[v.size() / 2], v[v.size() * 9 / 10], v.back());
         }
     }
 #endif
 #ifdef YH_X_TRACE
+    {
+        std::vector<unsigned int> rc(4096 * 16);
+        yh_x_rcycles_copy(rc.data(), 4096 * 16);
+        std::vector<unsigned int> v; for (unsigned x : rc) if (x) v.push_back(x);
+        std::sort(v.begin(), v.end());
+        if (!v.empty()) printf("  process_record cycles: n=%zu min %u p10 %u med %u p90 %u max %u\n", v.size(), v[0], v[v.size()/10], v[v.size()/2], v[v.size()*9/10], v.back());
+    }
     {
         for (int rep = 0; rep < 3; ++rep) { post(sets[rep]); CK(cudaStreamSynchronize(st)); }
         std::vector<unsigned long long> tr(4096 * 16);
