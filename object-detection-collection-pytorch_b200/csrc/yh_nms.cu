@@ -353,7 +353,9 @@ __global__ void __launch_bounds__(kThreads, 2) yh_nms_kernel(const NmsParams p) 
     // fold with three shuffles.  Then (rows landed) four of them activate one box logit each and the
     // group's first lane decodes the box into the ranked slot.
     const int sub8 = tid & 7;
+    bool rows_in = false;
     for (int k0 = 0; k0 < K; k0 += kThreads / 8) {
+        if (k0 + 4 * warp >= K) break;  // no candidate left for this warp: it stays out of the issue slots
         const int k = k0 + (tid >> 3);
         const bool on = k < K;
         const float ck = on ? ca.u_conf[k] : 0.f;
@@ -368,9 +370,10 @@ __global__ void __launch_bounds__(kThreads, 2) yh_nms_kernel(const NmsParams p) 
         rank += __shfl_xor_sync(0xffffffffu, rank, 1);
         rank += __shfl_xor_sync(0xffffffffu, rank, 2);
         rank += __shfl_xor_sync(0xffffffffu, rank, 4);
-        if (k0 == 0) {
+        if (!rows_in) {
             NT(3);
             yh_mbar_wait(&bar, 0);  // the staged rows
+            rows_in = true;
         }
         float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
         int lab = 0;
@@ -402,7 +405,6 @@ __global__ void __launch_bounds__(kThreads, 2) yh_nms_kernel(const NmsParams p) 
             if (!head && p.labels) ca.s_lab[rank] = lab;
         }
     }
-    if (K == 0) yh_mbar_wait(&bar, 0);
     __syncthreads();
 
     NT(4);
@@ -411,6 +413,7 @@ __global__ void __launch_bounds__(kThreads, 2) yh_nms_kernel(const NmsParams p) 
     const int sub = tid & (kPick - 1);
     if (use_lab && head) {  // label of every candidate (argmax of cls_spec)
         for (int k0 = 0; k0 < K; k0 += kThreads / kPick) {
+            if (k0 + (32 / kPick) * warp >= K) break;
             const int k = k0 + tid / kPick;
             const bool act = k < K;
             int lab;
@@ -538,6 +541,7 @@ __global__ void __launch_bounds__(kThreads, 2) yh_nms_kernel(const NmsParams p) 
     const int nout = min(kept, p.max_out);
     const bool want_cls = head && (p.out_cls_spec || p.out_label || p.out_score);
     for (int t0 = 0; t0 < nout; t0 += kThreads / kPick) {
+        if (t0 + (32 / kPick) * warp >= nout) break;
         const int t = t0 + tid / kPick;
         const bool act = t < nout;
         int i = 0, idx = 0;

@@ -389,12 +389,14 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
             else flags |= 1u << q;  // NaN / inf / out of range: the term becomes NaN, like the reference's
         }
         if (flags) atomicOr(p.acc + 6, (unsigned long long)flags);
-        __threadfence();
         XT(5);
-        const unsigned long long tk = atomicAdd(p.acc + 7, 1ull);
+        // release (this thread's atomics above are performed before the ticket is visible) and acquire
+        // (the last ticket holder sees every CTA's sums) in ONE acq_rel atomic: no sequentially
+        // consistent fence, which costs about a microsecond while the gradient stores drain
+        unsigned long long tk;
+        asm volatile("atom.acq_rel.gpu.global.add.u64 %0, [%1], %2;" : "=l"(tk) : "l"(p.acc + 7), "l"(1ull) : "memory");
         XT(6);
         if (tk == gridDim.x - 1) {
-            __threadfence();
             double tot[6];
 #pragma unroll
             for (int q = 0; q < 6; ++q) tot[q] = (double)__ldcg(p.acc + q) / kFix;
