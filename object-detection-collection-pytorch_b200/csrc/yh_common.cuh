@@ -128,6 +128,20 @@ __device__ __forceinline__ void yh_mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// non-blocking: has the phase with this parity completed?
+__device__ __forceinline__ bool yh_mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(yh_smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // global -> shared, completion signalled on `bar` (bytes: multiple of 16, both 16-B aligned)
 __device__ __forceinline__ void yh_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes,
                                              uint64_t* bar) {

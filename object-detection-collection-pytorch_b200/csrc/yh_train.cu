@@ -54,6 +54,7 @@ constexpr int kClsRegs = 4;               // class logits per lane kept in regis
 constexpr int kWindow = 128;              // speculative record window (records) per tile
 constexpr int kSlots = 24;                // patches (records processed during the dense pass) per tile
 constexpr int kPatchFloats = 32;          // floats per patch row: 5 + C must fit (else the record waits for the end)
+constexpr int kCellSlots = 12;            // records whose cell gets a private early copy (the others wait for their chunk)
 
 #ifdef YH_X_TRACE
 __device__ unsigned long long g_xtrace[4096 * 24];
@@ -89,6 +90,9 @@ struct TrainParams {
     int tile_cells;       // cells per tile (multiple of 4)
     int num_tiles;
     int m_local;          // records in gt
+    int cell_slots;       // private cell copies per tile that fit in shared memory (<= kCellSlots)
+    int cell_slot_floats; // floats per private cell copy (cell + alignment slack, multiple of 4)
+    long long total_floats;
     float rec_per_cell;   // m_local / total_cells: where a tile's records sit if boxes are spread evenly
     float lam[5];
     double inv_den[5];    // 1/(2M), 1/(2M), 1/M, 1/(M(P-1)), 1/M
@@ -321,7 +325,7 @@ template <bool WRITE_DY, bool VEC, int TV, int TA, int TC>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const TrainParams p) {
     extern __shared__ __align__(128) float s_tile[];  // the tile's slice of y
     __shared__ __align__(16) int4 s_win[3 * kWindow];  // speculative window of ground-truth records
-    __shared__ __align__(8) uint64_t s_bar[kChunks + 1];  // one mbarrier per chunk, + the window's
+    __shared__ __align__(8) uint64_t s_bar[kChunks + 2];  // one mbarrier per chunk, + the window's, + the private cell copies'
     __shared__ float red[kWarps * 6];
     __shared__ int s_rjj[kWindow];   // the tile's records in CSR order: index into gt ...
     __shared__ int s_rlc[kWindow];   // ... and tile-local cell
@@ -329,6 +333,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
     __shared__ float s_pdense[kSlots];                            // dense objectness value of a patched row
     __shared__ int s_pr[kSlots];                                  // responsible anchor of a patch
     __shared__ int s_nrec, s_npatch;  // records listed (-1: list incomplete, scan gt instead) / patched
+    __shared__ int s_ncell;           // records of the list with a private cell copy
+    __shared__ int s_collide;         // two patched records share a cell: patches must be applied in order
     __shared__ int s_ready;           // tile index + 1 once the record list of that tile is published
 
     const YhGeom& g = p.g;
@@ -346,7 +352,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
     XT(0);
     if (tid == kDense) {
 #pragma unroll
-        for (int c = 0; c <= kChunks; ++c) yh_mbar_init(&s_bar[c], 1);
+        for (int c = 0; c <= kChunks + 1; ++c) yh_mbar_init(&s_bar[c], 1);
         yh_mbar_fence_init();
         s_ready = 0;
     }
@@ -489,25 +495,43 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
             s_tile[4 * nf4 + tid] = __ldg(yt + 4 * nf4 + tid);  // floats past the last whole float4 of the tensor
         }
 
-        // Patchable records are dealt round-robin to ALL warps (a record is ~3000 cycles of one warp's
-        // dependent arithmetic): warp w takes list entries w, w + kWarps, ...  Each goes into its own
-        // patch slot, so the order in which they are processed does not matter; the patches are applied
-        // in list (CSR) order afterwards.  try_records(c) processes this warp's records whose cells lie
-        // in chunks <= c, once the record warp has published the list; returns false if it has not yet.
+        // Patchable records are dealt round-robin to the warps (a record is ~2700 cycles of one warp's
+        // dependent arithmetic); warp 0 is left out, it keeps the tile's chunks flowing.  Each record
+        // goes into its own patch slot, so the order in which they are processed does not matter; the
+        // patches are applied in list (CSR) order afterwards.  The first cell_slots records of the list
+        // read their cell from a private early copy (see the record warp), the others from the tile
+        // once their chunk has landed.  try_records(c, block) processes what is ready: records with a
+        // private copy once those copies have landed (block: wait for them), the others if their cell
+        // lies in chunks <= c.  Returns false if the record warp has not published the list yet.
+        float* s_cell = s_tile + (((size_t)R * cf + 3) & ~(size_t)3) + 4;  // private cell copies, after the tile
         unsigned rec_done = 0u;
-        int my_npatch = -1;
-        auto try_records = [&](int upto_chunk) -> bool {
+        int my_npatch = -1, my_ncell = 0;
+        bool cells_in = false;
+        auto try_records = [&](int upto_chunk, bool block) -> bool {
+            if (warp == 0) return true;
             if (my_npatch < 0) {
                 if (*reinterpret_cast<volatile int*>(&s_ready) != t + 1) return false;
                 __threadfence_block();
                 yh_mbar_wait(&s_bar[kChunks], phase);  // (complete by now: makes the window visible to this warp)
                 my_npatch = s_npatch;
+                my_ncell = s_ncell;
             }
-            for (int i = warp, k = 0; i < my_npatch; i += kWarps, ++k) {
+            if (!cells_in && my_ncell > 0) {
+                if (block) { yh_mbar_wait(&s_bar[kChunks + 1], phase); cells_in = true; }
+                else cells_in = yh_mbar_test(&s_bar[kChunks + 1], phase);
+            }
+            for (int i = warp - 1, k = 0; i < my_npatch; i += kWarps - 1, ++k) {
                 if ((rec_done >> k) & 1u) continue;
                 const int jj = s_rjj[i], lcell = s_rlc[i];
-                const int cb = min(((lcell + 1) * cf - 1) / (4 * ch4), kChunks - 1);  // chunk of the cell's last float
-                if (cb > upto_chunk) continue;
+                const float* ycell;
+                if (i < my_ncell) {
+                    if (!cells_in) continue;
+                    ycell = s_cell + (size_t)i * p.cell_slot_floats + (int)(((long long)(c0 + lcell) * cf) & 3);
+                } else {
+                    const int cb = min(((lcell + 1) * cf - 1) / (4 * ch4), kChunks - 1);  // chunk of the cell's last float
+                    if (cb > upto_chunk) continue;
+                    ycell = s_tile + lcell * cf;
+                }
                 rec_done |= 1u << k;
                 const int4* rp = s_win + 3 * (jj - w0);
                 RecordRegs rr;
@@ -517,7 +541,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
 #ifdef YH_X_TRACE
                 const long long rc0 = clock64();
 #endif
-                const int r = process_record<2>(p, version, A, C, rr, jj, s_tile + lcell * cf, nullptr,
+                const int r = process_record<2>(p, version, A, C, rr, jj, ycell, nullptr,
                                                 s_patch + i * kPatchFloats, s_pdense + i, kn_of(lcell * cf), lane,
                                                 my_pw, my_ph, sums);
                 if (lane == 0) s_pr[i] = r;
@@ -574,9 +598,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
                     }
                     if (WRITE_DY) store4<VEC>(dt, i4, o);
                 }
-                try_records(c);
+                try_records(c, false);
             }
-            while (!try_records(kChunks - 1)) { }  // (the record warp publishes after one round trip)
+            while (!try_records(kChunks - 1, true)) { }  // (the record warp publishes after one round trip)
             if (tid < (nfl & 3)) {  // floats past the last whole float4 of the tensor
                 const int lf = 4 * nf4 + tid;
                 const int pc = lf % cf;
@@ -625,15 +649,46 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
             XT(5);  // record warp: list built
             const bool complete = n <= kWindow;
             const int n_patch = (patchable && complete && covered) ? min(n, kSlots) : 0;
-            if (lane == 0) { s_nrec = complete ? n : -1; s_npatch = n_patch; }
+            // Private early copies of the first records' cells: the tile's last chunk lands when the
+            // stream ends, and a record found in it would add its ~1.4 us to the CTA's critical path;
+            // a 16-byte aligned bulk copy of just the cell, asked for now, is back long before that.
+            const int n_cell = VEC ? min(n_patch, p.cell_slots) : 0;
+            uint32_t cbytes = 0;
+            if (lane < n_cell) {
+                const long long f = (long long)(c0 + s_rlc[lane]) * cf;  // first float of the cell in y
+                const int shift = (int)(f & 3);
+                const int win = (shift + cf + 3) & ~3;
+                if (f - shift + win <= (p.total_floats & ~3ll)) {
+                    cbytes = (uint32_t)win * 4u;
+                    yh_bulk_load(s_cell + (size_t)lane * p.cell_slot_floats, p.y + (f - shift), cbytes, &s_bar[kChunks + 1]);
+                } else {  // the very last cells of the tensor: plain loads
+                    for (int q = 0; q < cf; ++q) s_cell[(size_t)lane * p.cell_slot_floats + shift + q] = __ldg(p.y + f + q);
+                }
+            }
+            for (int o = 16; o > 0; o >>= 1) cbytes += __shfl_xor_sync(0xffffffffu, cbytes, o);
+            if (lane == 0) {
+                if (cbytes) yh_mbar_expect_tx(&s_bar[kChunks + 1], cbytes);
+                else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(yh_smem_u32(&s_bar[kChunks + 1])) : "memory");
+                s_nrec = complete ? n : -1;
+                s_npatch = n_patch;
+                s_ncell = n_cell;
+            }
             __syncwarp();
             __threadfence_block();
             if (lane == 0) *reinterpret_cast<volatile int*>(&s_ready) = t + 1;  // publish the list
             __syncwarp();
-            for (int c = 0; c < kChunks; ++c) {  // this warp's share, as the chunks land
-                yh_mbar_wait(&s_bar[c], phase);
-                try_records(c);
+            {   // do two patched records share a cell?  (then the patches are applied one by one, in order)
+                bool dup = false;
+                if (lane < n_patch)
+                    for (int j = 0; j < lane; ++j) dup = dup || s_rlc[j] == s_rlc[lane];
+                const bool any = __any_sync(0xffffffffu, dup);
+                if (lane == 0) s_collide = any ? 1 : 0;
             }
+            for (int c = 0; c < kChunks; ++c) {  // this warp's share, as copies and chunks land
+                try_records(c - 1, false);
+                yh_mbar_wait(&s_bar[c], phase);
+            }
+            try_records(kChunks - 1, true);
             XT(6);  // record warp: records processed
         }
 
@@ -647,7 +702,19 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
         // (no records left over: the sums folded before the barrier are final and get published
         //  right after the patch stores, without another CTA barrier)
         if (last_tile && !(nrec < 0 || nrec > npatch)) sums_final = true;
-        if (record_warp) {
+        if (!s_collide) {
+            // every warp applies the patches it produced: a plain overwrite of the 5+C floats of the row
+            // (the dense pass' values there are zero but the objectness channel, kept in s_pdense)
+            for (int i = warp - 1; i < npatch && warp > 0; i += kWarps - 1) {
+                const int lcell = s_rlc[i], r = s_pr[i];
+                if (lane < 5 + C) {
+                    float* addr = dt + lcell * cf + (version == 2 ? r * bs + lane : (lane < 5 ? r * 5 + lane : 5 * A + lane - 5));
+                    float val = s_patch[i * kPatchFloats + lane];
+                    if (lane == 4) val = __fadd_rn(s_pdense[i], val);
+                    *addr = val;
+                }
+            }
+        } else if (record_warp) {
             for (int i = 0; i < npatch; ++i) {
                 const int lcell = s_rlc[i], r = s_pr[i];
                 // an earlier record of this cell already updated it: read the row back.  Otherwise the
@@ -721,18 +788,19 @@ extern "C" YH_API int yh_x_rcycles_copy(unsigned int* host, int n) {
 
 template <bool WDY, bool VEC, int TV, int TA, int TC>
 int launch_variant(const TrainParams& p, int grid, cudaStream_t stream) {
-    static bool configured[64] = {false};  // per device: opt in to > 48 KB of dynamic shared memory
+    const size_t smem = (((size_t)p.tile_cells * p.g.cell_floats + 3) & ~(size_t)3) * 4 + 16 +
+                        (size_t)p.cell_slots * p.cell_slot_floats * 4;
+    static size_t configured[64] = {0};  // per device: opt in to > 48 KB of dynamic shared memory
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) dev = 0;
-    if (!configured[dev]) {
+    if (smem > configured[dev]) {
         int rc = yh_check_cuda(cudaFuncSetAttribute(yh_train_kernel<WDY, VEC, TV, TA, TC>,
-                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, kTileBytesMax + 64),
+                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                                "cudaFuncSetAttribute(train)");
         if (rc) return rc;
-        configured[dev] = true;
+        configured[dev] = smem;
     }
-    const size_t smem = (((size_t)p.tile_cells * p.g.cell_floats * 4 + 15) & ~(size_t)15) + 16;
     yh_train_kernel<WDY, VEC, TV, TA, TC><<<grid, kThreads, smem, stream>>>(p);
     return yh_check_cuda(cudaGetLastError(), "yh_train launch");
 }
@@ -810,6 +878,15 @@ int train_impl(int version, const float* y, int n, int s_h, int s_w, int a, int 
     p.num_tiles = (int)tiles;
     const int grid = (int)(tiles < slots ? tiles : slots);
 
+    // private cell copies: as many as fit next to 4 CTAs' tiles in the SM's shared memory
+    p.total_floats = total_cells * cf;
+    p.cell_slot_floats = (cf + 6 + 3) & ~3;
+    {
+        const long long per_cta = (224ll * 1024) / kCtasPerSm - 1024 - 12 * 1024;  // minus reserve and static arrays
+        const long long left = per_cta - ((long long)p.tile_cells * cf * 4 + 32);
+        long long slots = left > 0 ? left / (p.cell_slot_floats * 4ll) : 0;
+        p.cell_slots = (int)(slots < kCellSlots ? slots : kCellSlots);
+    }
     const bool vec = ((uintptr_t)y & 15) == 0 && ((uintptr_t)dy & 15) == 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (dy) return vec ? launch_geometry<true, true>(p, grid, st) : launch_geometry<true, false>(p, grid, st);
