@@ -50,11 +50,14 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=32, help="images in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--serial", action="store_true",
+                    help="launch post-process after the train head on one stream (default: two streams, "
+                         "the two calls of a step are independent and become parallel graph branches)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 200)")
     return ap.parse_args()
 
 
-def workload_config(batch, sets=None):
+def workload_config(batch, sets=None, serial=False):
     cfg = {
         "workload": "yolov2_head_13x13x5_c20_b%d_train(decode+assign+loss+bwd)+postprocess(conf%.2f,nms_iou%.2f)"
                     % (batch, CONF_THRE, IOU_THRE),
@@ -64,6 +67,8 @@ def workload_config(batch, sets=None):
     if sets is not None:
         cfg["l2"] = "%d rotating input/output buffer sets per GPU (inputs+outputs %.0f MB > 126 MB L2)" % (
             sets, sets * 2 * batch * 84500 / 1e6)
+        cfg["streams"] = "train head and post-process of a step on one stream" if serial else \
+            "train head and post-process of a step on two streams (parallel graph branches), steps in order"
     return cfg
 
 
@@ -206,6 +211,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     dist = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
@@ -227,13 +234,30 @@ def main():
         sets.append(s)
 
     stream = torch.cuda.Stream(dev)
+    side = torch.cuda.Stream(dev)
+    fork_ev = [torch.cuda.Event() for _ in range(2)]
+
+    def run_post(s):
+        s["post"] = ops.postprocess(s["y"], conf_thre=CONF_THRE, iou_thre=IOU_THRE, max_out=MAX_OUT,
+                                    want_cls_spec=False, out=s.get("post"), **kw)
 
     def step(s, post=True, train=True):
+        """One step = one train-head call + one post-process call on the same head tensor.  The two
+        calls are independent, so unless --serial they go to two streams (fork/join inside the step:
+        parallel branches of the captured graph); consecutive steps stay ordered."""
+        both = post and train and not args.serial
+        if both:
+            fork_ev[0].record(stream)
+            side.wait_event(fork_ev[0])
+            with torch.cuda.stream(side):
+                run_post(s)
+                fork_ev[1].record(side)
         if train:
             ops.train_head(s["y"], s["gt"], s["off"], lambdas=lam, m_global=m_global, out=s["out"], **kw)
-        if post:
-            s["post"] = ops.postprocess(s["y"], conf_thre=CONF_THRE, iou_thre=IOU_THRE, max_out=MAX_OUT,
-                                        want_cls_spec=False, out=s.get("post"), **kw)
+        if both:
+            stream.wait_event(fork_ev[1])
+        elif post:
+            run_post(s)
 
     def capture(fn):
         g = torch.cuda.CUDAGraph()
@@ -398,7 +422,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(B, R),
+            "dtype": "f32", "data": "synthetic", "config": workload_config(B, R, args.serial),
             "clocks": sampler.summary(window), "e2e": e2e, "gpu_launches": 2 * K,
             "roofline": roofline, "cpu_baseline": cpu, "loss": loss_value,
         }

@@ -128,6 +128,18 @@ YH_API int yh_compact_targets(const float* sig_txty, const float* twth, const fl
                        YhGt* gt_out, int32_t* gt_off_out, int32_t* status,
                        void* ws, size_t ws_bytes, void* stream);
 
+/* Device-side target builder: pixel boxes -> compact records + CSR offsets, the float64 arithmetic
+ * of collate_fn (reference models/yolov2.py:1440-1512, models/yolov1.py:1238-1312) without its
+ * dense per-box grids.
+ *   boxes_xyxy[M,4] float64 pixels, labels[M], img_index[M] = position of the owning image in the
+ *   batch, non-decreasing (collate_fn appends boxes image by image); img_h/img_w the network input
+ *   size.  gt_out[M] in the same order, gt_off_out[N+1].
+ *   status[2] (device): [0] boxes out of image order, [1] boxes whose image index or cell is out of
+ *   range (such records are ignored by the train head). */
+YH_API int yh_build_targets(const double* boxes_xyxy, const int32_t* labels, const int32_t* img_index,
+                     int m, int n, int version, int s_h, int s_w, double img_h, double img_w,
+                     YhGt* gt_out, int32_t* gt_off_out, int32_t* status, void* stream);
+
 /* Inference post-process straight from the head tensor: decode + `conf >= conf_thre` +
  * descending-confidence greedy NMS per image + class pick.
  * Replaces the predict -> nms -> argmax chain of detect() (reference models/yolov2.py:694-731,

@@ -31,6 +31,7 @@ SIGNATURES = {
     "yh_v1_decode": (_i, [_p, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p, _p, _p, _p, _p]),
     "yh_compact_workspace_bytes": (_sz, [_i, _i]),
     "yh_compact_targets": (_i, [_p, _p, _p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
+    "yh_build_targets": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, C.c_double, C.c_double, _p, _p, _p, _p]),
     "yh_postprocess_workspace_bytes": (_sz, [_i, _i]),
     "yh_v2_postprocess": (_i, [_p, _i, _i, _i, _i, _i, _p, _f, _f, _f, _f, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "yh_v1_postprocess": (_i, [_p, _i, _i, _i, _i, _i, _f, _f, _f, _f, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),

@@ -178,6 +178,29 @@ def compact_targets(sig_txty, twth, coord, cls_tgt, obj_mask, x_img_id, bbox_img
     return gt, gt_off, status
 
 
+def build_targets(boxes_xyxy, labels, img_index, *, num_images, version, img_hw, grid):
+    """Pixel boxes -> (gt [M,12] int32 records, gt_off [N+1] int32, status [2] int32) on the device --
+    yh_build_targets.  boxes_xyxy float64 [M,4], labels / img_index integer [M] with img_index
+    non-decreasing (boxes grouped by image, the order collate_fn produces)."""
+    if not (isinstance(boxes_xyxy, torch.Tensor) and boxes_xyxy.is_cuda):
+        raise ValueError("boxes_xyxy must be a CUDA tensor (this path has no CPU implementation)")
+    dev = boxes_xyxy.device
+    boxes = boxes_xyxy.to(torch.float64).reshape(-1, 4).contiguous()
+    m = int(boxes.shape[0])
+    labels = labels.to(device=dev, dtype=torch.int32).contiguous()
+    img_index = img_index.to(device=dev, dtype=torch.int32).contiguous()
+    if labels.numel() != m or img_index.numel() != m:
+        raise ValueError("labels / img_index must have one entry per box")
+    with torch.cuda.device(dev):
+        gt = torch.empty(m, 12, dtype=torch.int32, device=dev)
+        gt_off = torch.empty(int(num_images) + 1, dtype=torch.int32, device=dev)
+        status = torch.empty(2, dtype=torch.int32, device=dev)
+        _lib.call("yh_build_targets", _ptr(boxes), _ptr(labels), _ptr(img_index), m, int(num_images),
+                  int(version), int(grid[0]), int(grid[1]), float(img_hw[0]), float(img_hw[1]),
+                  _ptr(gt), _ptr(gt_off), _ptr(status), _stream())
+    return gt, gt_off, status
+
+
 def postprocess(y, *, version, img_hw, conf_thre, iou_thre, anchors=None, boxes_per_cell=None,
                 class_aware=False, max_out=None, want_cls_spec=True, out=None):
     """Decode + threshold + per-image greedy NMS + class pick -- yh_v{1,2}_postprocess.

@@ -139,8 +139,49 @@ def pack_nms(res):
                 nms_cls_spec=cat("cls_spec"))
 
 
+def run_collate(version, n, height, width, seed, num_cls=20):
+    """The reference's own collate_fn (models/yolov2.py:1380-1555, models/yolov1.py:1160-1355,
+    augmentation off; v1's albumentations resize replaced by the identity: the images already have the
+    network size) on synthetic boxes; its dense per-box grids are read back at the cell it filled."""
+    rng = np.random.default_rng(seed)
+    boxes, labels, img = synthetic.make_boxes(rng, n, height, width, 1, 5, num_cls)
+    if version == 2:
+        m = HeadOnlyV2(num_cls)
+    else:
+        m = HeadOnlyV1(height // 32, width // 32, 2, num_cls)
+        m.resize = lambda image, bboxes, labels: dict(image=image, bboxes=bboxes, labels=labels)
+    batch = []
+    for i in range(n):
+        sel = img == i
+        batch.append((i, np.zeros((height, width, 3), np.uint8),
+                      {"bbox_list": [list(b) for b in boxes[sel]], "lbl_list": [str(l) for l in labels[sel]]}))
+    out = m.collate_fn(batch, augmentation=False)
+    _, sig_txty, twth, coord, cls_tgt, obj, x_img_id, bbox_img_id = [np.asarray(t) for t in out]
+    mm = len(boxes)
+    flat = obj.reshape(mm, -1)
+    assert (flat.sum(1) == 1).all()
+    cell = flat.argmax(1)
+    s_w = obj.shape[2]
+    cy, cx = cell // s_w, cell % s_w
+    j = np.arange(mm)
+    rec = np.zeros(mm, dtype=targets.GT_DTYPE)
+    rec["img"] = bbox_img_id
+    rec["cy"], rec["cx"] = cy, cx
+    rec["cls"] = cls_tgt[j, cy, cx].argmax(-1)
+    rec["stx"], rec["sty"] = sig_txty[j, cy, cx, 0], sig_txty[j, cy, cx, 1]
+    rec["tw"], rec["th"] = twth[j, cy, cx, 0], twth[j, cy, cx, 1]
+    for c, k in enumerate(("x1", "y1", "x2", "y2")):
+        rec[k] = coord[j, cy, cx, c]
+    return dict(version=version, n=n, height=height, width=width, s_h=obj.shape[1], s_w=s_w, boxes=boxes,
+                labels=labels.astype(np.int32), img=img.astype(np.int32),
+                rec=rec.view(np.int32).reshape(-1, 12), obj_dtype=str(obj.dtype), sig_dtype=str(sig_txty.dtype))
+
+
 def main():
     lam = synthetic.DEFAULT_LAMBDAS
+    np.savez_compressed(os.path.join(HERE, "v2_collate.npz"), **run_collate(2, 6, 416, 416, 201))
+    np.savez_compressed(os.path.join(HERE, "v2_collate_nonsquare.npz"), **run_collate(2, 3, 352, 480, 202))
+    np.savez_compressed(os.path.join(HERE, "v1_collate.npz"), **run_collate(1, 5, 224, 224, 203))
     torch.set_num_threads(1)  # single-threaded reductions: the most reproducible reference run
 
     # --- v2 loss/grad, small, with same-cell collisions

@@ -7,11 +7,13 @@ Tolerances (north-star): responsible-predictor and kept-box indices bit-exact, e
 whose two best candidates are within a few ulp of each other (those are listed in the assertion
 message, never silently skipped); loss and dL/dy within 1e-5 relative in fp32.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
 
-from conftest import golden_lambdas, load_golden, rel_err
+from conftest import GOLDEN, golden_lambdas, load_golden, rel_err
 from odcp_b200 import ops, synthetic, targets
 from oracle import yolo_head_oracle as O
 
@@ -215,6 +217,43 @@ def test_train_head_full_size_properties_cfg5(cuda_device):
         tot += r["loss"]
         assert np.array_equal(r["dy"], full["dy"][a:b])
     assert abs(tot - full["loss"]) <= TOL * abs(full["loss"])
+
+
+# ------------------------------------------------------------------------------------------
+# device-side target builder
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["v2_collate.npz", "v2_collate_nonsquare.npz", "v1_collate.npz"])
+def test_build_targets_matches_reference_collate_fn(name, cuda_device):
+    """yh_build_targets vs the records read back from the reference's own collate_fn grids: bit-exact."""
+    z = dict(np.load(os.path.join(GOLDEN, name)))
+    want = np.ascontiguousarray(z["rec"]).reshape(-1).view(targets.GT_DTYPE)
+    gt, off, status = ops.build_targets(torch.from_numpy(z["boxes"]).to(cuda_device), torch.from_numpy(z["labels"]),
+                                        torch.from_numpy(z["img"]), num_images=int(z["n"]), version=int(z["version"]),
+                                        img_hw=(int(z["height"]), int(z["width"])), grid=(int(z["s_h"]), int(z["s_w"])))
+    assert status.cpu().tolist() == [0, 0]
+    assert targets.tensor_to_records(gt).tobytes() == want.tobytes()
+    assert np.array_equal(off.cpu().numpy(), targets.csr_offsets(want, int(z["n"])))
+
+
+def test_build_targets_full_size_and_bad_input(cuda_device):
+    """cfg 5 sized input (tens of thousands of boxes) against the host builder, images without boxes,
+    and the status counters for out-of-order / out-of-range boxes."""
+    rng = np.random.default_rng(7)
+    boxes, labels, img = synthetic.make_boxes(rng, 512, 608, 608, 0, 100, 20)
+    want = targets.boxes_to_records(boxes, labels, img, 608, 608, 19, 19, 2)
+    gt, off, status = ops.build_targets(torch.from_numpy(boxes).to(cuda_device), torch.from_numpy(labels),
+                                        torch.from_numpy(img), num_images=512, version=2, img_hw=(608, 608), grid=(19, 19))
+    assert status.cpu().tolist() == [0, 0]
+    assert targets.tensor_to_records(gt).tobytes() == want.tobytes()
+    assert np.array_equal(off.cpu().numpy(), targets.csr_offsets(want, 512))
+    bad_img = img.copy()
+    bad_img[[5, 6]] = bad_img[[6, 5]] if bad_img[5] != bad_img[6] else (bad_img[6] + 1, bad_img[5])
+    bad_boxes = boxes.copy()
+    bad_boxes[0] = [700.0, 10.0, 800.0, 50.0]  # outside the 608-pixel image: cell out of range
+    _, _, status = ops.build_targets(torch.from_numpy(bad_boxes).to(cuda_device), torch.from_numpy(labels),
+                                     torch.from_numpy(bad_img), num_images=512, version=2, img_hw=(608, 608), grid=(19, 19))
+    st = status.cpu().tolist()
+    assert st[0] >= 1 and st[1] >= 1
 
 
 # ------------------------------------------------------------------------------------------
