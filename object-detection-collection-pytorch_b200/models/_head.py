@@ -89,6 +89,24 @@ class HeadOps:
         self._yh_last = dict(terms=terms, **{k: cfg["last"][k] for k in ("resp", "iou_resp")})
         return loss
 
+    def get_loss_from_boxes(self, x_batch, boxes_xyxy, labels, img_index, *, m_global=None, lambda_xy=5.0,
+                            lambda_wh=5.0, lambda_conf=1.0, lambda_noobj=0.5, lambda_cls=1.0):
+        """Fast path from raw annotations: float64 pixel boxes [M,4], class indices [M] and the batch
+        position of each box's image [M] (grouped by image, the order collate_fn walks them).  The
+        targets are built on the device with collate_fn's float64 arithmetic (yh_build_targets), so
+        neither the dense grids nor their M*5 host-to-device copies exist."""
+        y = self(x_batch)
+        dev = y.device
+        s_h, s_w = int(y.shape[1]), int(y.shape[2])
+        gt, gt_off, status = ops.build_targets(
+            torch.as_tensor(boxes_xyxy, dtype=torch.float64).to(dev), torch.as_tensor(labels), torch.as_tensor(img_index),
+            num_images=int(y.shape[0]), version=self._yh_version,
+            img_hw=(int(x_batch.shape[1]), int(x_batch.shape[2])), grid=(s_h, s_w))
+        self._yh_target_status = status  # device int32[2]: boxes out of image order, out-of-range boxes
+        return self.get_loss_compact(x_batch, gt, gt_off, y=y, m_global=m_global, lambda_xy=lambda_xy,
+                                     lambda_wh=lambda_wh, lambda_conf=lambda_conf, lambda_noobj=lambda_noobj,
+                                     lambda_cls=lambda_cls)
+
     # -- detect ------------------------------------------------------------------------------
     def _yh_image_batch(self, img):
         dev = next(self.parameters(), torch.empty(0, device="cuda")).device

@@ -1,0 +1,70 @@
+"""Kernel times of the BASELINE.json configurations (CUDA events, CUDA-graph replay over rotating
+buffer sets sized to exceed L2), for the table in DESIGN.md.  Not part of the product."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from odcp_b200 import ops, synthetic, targets
+
+dev = torch.device("cuda:0")
+lam = synthetic.DEFAULT_LAMBDAS
+PEAK = 6552.6
+
+
+def time_graph(fn, sets, reps=50):
+    st = torch.cuda.Stream(dev)
+    with torch.cuda.stream(st):
+        for s in sets:
+            fn(s)
+        st.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            for s in sets:
+                fn(s)
+        for _ in range(3):
+            g.replay()
+        st.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        for _ in range(reps):
+            g.replay()
+        b.record(st)
+        st.synchronize()
+    return a.elapsed_time(b) * 1e3 / (reps * len(sets))
+
+
+def run(name, case, conf_thre, iou_thre=0.45):
+    nsets = max(2, min(8, int(400e6 // max(1, 2 * case.n * case.image_bytes)) + 1))
+    kw = dict(version=case.version, img_hw=(case.height, case.width), anchors=case.anchors, boxes_per_cell=case.a)
+    gt = targets.records_to_tensor(case.rec, dev)
+    off = torch.from_numpy(case.gt_off).to(dev)
+    sets = []
+    for _ in range(nsets):
+        y = case.y.to(dev).clone()
+        sets.append(dict(y=y, gt=gt.clone(), off=off.clone(),
+                         out=dict(dy=torch.empty_like(y), loss=torch.empty((), device=dev), terms=torch.empty(5, device=dev))))
+
+    def train(s):
+        ops.train_head(s["y"], s["gt"], s["off"], lambdas=lam, out=s["out"], **kw)
+
+    def post(s):
+        s["post"] = ops.postprocess(s["y"], conf_thre=conf_thre, iou_thre=iou_thre, max_out=128, want_cls_spec=False,
+                                    out=s.get("post"), **kw)
+
+    t_train = time_graph(train, sets)
+    t_post = time_graph(post, sets)
+    kept = int(sets[0]["post"]["keep_cnt"].clamp(max=128).sum().item())
+    p = case.image_bytes
+    b_train = 2 * p * case.n + 48 * case.m
+    b_post = p * case.n + 28 * kept
+    print(json.dumps(dict(config=name, n=case.n, grid=[case.s_h, case.s_w], boxes=case.m, sets=nsets,
+                          train_us=round(t_train, 2), train_MB=round(b_train / 1e6, 2),
+                          train_frac=round(b_train / t_train / 1e3 / PEAK, 3),
+                          post_us=round(t_post, 2), post_MB=round(b_post / 1e6, 2),
+                          post_frac=round(b_post / t_post / 1e3 / PEAK, 3), kept_per_image=round(kept / case.n, 1))), flush=True)
+
+
+run("cfg1 v1 7x7 B=2 N=8", synthetic.cfg1(), 0.5)
+run("cfg2 v2 13x13 N=64", synthetic.cfg2(), 0.5)
+run("cfg3 v2 13x13 N=256 (inference, conf 0.5)", synthetic.cfg3(), 0.5)
+run("headline v2 13x13 N=256", synthetic.headline(), 0.5)
+run("cfg5 v2 19x19 N=512 50-100 boxes", synthetic.cfg5(), 0.5)

@@ -256,6 +256,31 @@ def test_build_targets_full_size_and_bad_input(cuda_device):
     assert st[0] >= 1 and st[1] >= 1
 
 
+def test_get_loss_from_boxes_equals_the_dense_signature(cuda_device):
+    """The three entry forms of the drop-in model (dense reference grids, compact records, raw boxes)
+    give the same loss and the same gradient."""
+    from odcp_b200.models.yolov2 import YOLOv2Head
+    z = dict(np.load(os.path.join(GOLDEN, "v2_collate.npz")))
+    n, h, w = int(z["n"]), int(z["height"]), int(z["width"])
+    rec = np.ascontiguousarray(z["rec"]).reshape(-1).view(targets.GT_DTYPE)
+    y0 = torch.randn(n, 13, 13, 5, 25, generator=torch.Generator().manual_seed(5)).to(cuda_device)
+    x = torch.zeros(n, h, w, 3, device=cuda_device)
+    m = YOLOv2Head(num_cls=20).to(cuda_device)
+    res = []
+    for form in ("dense", "boxes"):
+        y = y0.clone().requires_grad_(True)
+        m.set_head_output(y)
+        if form == "dense":
+            dense = [t.to(cuda_device) for t in targets.records_to_dense(rec, n, 13, 13, 20, 2)]
+            loss = m.get_loss(x, *dense, **synthetic.DEFAULT_LAMBDAS)
+        else:
+            loss = m.get_loss_from_boxes(x, z["boxes"], z["labels"], z["img"], **synthetic.DEFAULT_LAMBDAS)
+        loss.backward()
+        res.append((float(loss.item()), y.grad.cpu().numpy()))
+    assert res[0][0] == res[1][0]
+    assert np.array_equal(res[0][1], res[1][1])
+
+
 # ------------------------------------------------------------------------------------------
 # predict / decode
 # ------------------------------------------------------------------------------------------
