@@ -35,11 +35,17 @@
 
 namespace {
 
-constexpr int kDense = 256;               // streaming threads per CTA
+#ifndef YH_X_DENSE
+#define YH_X_DENSE 256
+#endif
+constexpr int kDense = YH_X_DENSE;        // streaming threads per CTA
 constexpr int kDenseWarps = kDense / 32;
 constexpr int kThreads = kDense + 32;     // + one record warp
 constexpr int kWarps = kThreads / 32;
-constexpr int kCtasPerSm = 4;
+#ifndef YH_X_CTAS
+#define YH_X_CTAS 3
+#endif
+constexpr int kCtasPerSm = YH_X_CTAS;
 #ifndef YH_X_CHUNKS
 #define YH_X_CHUNKS 4
 #endif
@@ -48,7 +54,7 @@ constexpr int kCtasPerSm = 4;
 #endif
 constexpr int kChunks = YH_X_CHUNKS;      // TMA chunks (mbarriers) per tile
 constexpr int kAhead = YH_X_AHEAD;        // chunks in flight per CTA
-constexpr int kTileBytesMax = 40 * 1024;  // shared-memory stage of one tile
+constexpr int kTileBytesMax = (kCtasPerSm >= 4 ? 40 : (kCtasPerSm == 3 ? 52 : 80)) * 1024;  // shared-memory stage of one tile
 constexpr int kMaxGrid = 2048;
 constexpr int kClsRegs = 4;               // class logits per lane kept in registers (C <= 128)
 constexpr int kWindow = 128;              // speculative record window (records) per tile
