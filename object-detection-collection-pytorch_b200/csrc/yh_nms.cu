@@ -39,7 +39,10 @@
 
 namespace {
 
-constexpr int kThreads = 512;
+#ifndef YH_X_NMS_THREADS
+#define YH_X_NMS_THREADS 512
+#endif
+constexpr int kThreads = YH_X_NMS_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kTile = 256;             // ranked candidates per suppression tile
 constexpr int kTileWords = kTile / 32;
@@ -215,7 +218,7 @@ __device__ __forceinline__ bool suppresses(const float4& bi, float ai, const flo
 // TV/TA/TC != 0 fix version / boxes per cell / classes at compile time (index arithmetic folds,
 // divisions become multiplies); 0 keeps them as run-time values from the geometry.
 template <int TV, int TA, int TC>
-__global__ void __launch_bounds__(kThreads, 2) yh_nms_kernel(const NmsParams p) {
+__global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const NmsParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];  // [staged rows | candidate arrays]
     __shared__ unsigned int mask[kTile * kTileWords];
     __shared__ unsigned int rem0[kTileWords];
@@ -431,12 +434,12 @@ __global__ void __launch_bounds__(kThreads, 2) yh_nms_kernel(const NmsParams p) 
         const int tn = min(kTile, K - base);
         const int W = (tn + 31) >> 5;
         // (1) against the boxes kept in earlier tiles
-        if (warp < kTileWords) {
+        for (int jp = tid; jp < kTile; jp += kThreads) {  // (whole warps: kTile and kThreads are multiples of 32)
             bool dead = false;
-            if (tid < tn && base > 0) {
-                const float4 bj = ca.s_box[base + tid];
+            if (jp < tn && base > 0) {
+                const float4 bj = ca.s_box[base + jp];
                 const YhBox qj{bj.x, bj.y, bj.z, bj.w};
-                const int lj = use_lab ? ca.s_lab[base + tid] : 0;
+                const int lj = use_lab ? ca.s_lab[base + jp] : 0;
                 const int kept = s_kept;
                 for (int q = 0; q < kept; ++q) {
                     const int i = ca.keep[q];
@@ -446,7 +449,7 @@ __global__ void __launch_bounds__(kThreads, 2) yh_nms_kernel(const NmsParams p) 
                 }
             }
             const unsigned bal = __ballot_sync(0xffffffffu, dead);
-            if (lane == 0) rem0[warp] = bal;  // warp w < kTileWords covers word w of the tile
+            if (lane == 0) rem0[jp >> 5] = bal;
         }
         __syncthreads();
         // (2) intra-tile mask, by column: word (j, w) = candidates i in [32w, 32w+32), ranked before j,
