@@ -154,3 +154,38 @@ def test_host_records_match_the_reference_collate_fn(name):
                                    int(z["s_h"]), int(z["s_w"]), int(z["version"]))
     assert got.tobytes() == want.tobytes()
     assert str(z["obj_dtype"]) == "float64"  # SURVEY B-7: the reference's obj_mask is fp64
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="needs the reference tree (build container only)")
+def test_mixin_composes_with_the_unmodified_reference_model():
+    """`class YOLOv2(YOLOv2HeadOps, ref.YOLOv2)` takes predict / get_loss /
+    detect from the CUDA path and everything else (forward, backbone, collate_fn, train loop) from the
+    reference, without new parameters.  Import only: nothing runs without a GPU."""
+    import types
+    sys.path.insert(0, "/root/reference")
+
+    class _Stub(types.ModuleType):
+        def __getattr__(self, name):
+            return lambda *a, **k: None
+    for name in ("albumentations", "albumentations.pytorch"):
+        sys.modules.setdefault(name, _Stub(name))
+    try:
+        import models.yolov2 as ref_v2
+        from odcp_b200.models._head import HeadOps
+        from odcp_b200.models.yolov2 import YOLOv2HeadOps
+
+        class YOLOv2(YOLOv2HeadOps, ref_v2.YOLOv2):
+            pass
+
+        for name in ("predict", "get_loss", "detect"):
+            assert getattr(YOLOv2, name) is getattr(HeadOps, name)
+        for name in ("forward", "collate_fn", "train_model", "run_one_epoch"):
+            assert getattr(YOLOv2, name) is getattr(ref_v2.YOLOv2, name)
+        import inspect
+        ours = list(inspect.signature(HeadOps.get_loss).parameters)
+        theirs = list(inspect.signature(ref_v2.YOLOv2.get_loss).parameters)
+        assert len(ours) == len(theirs) == 14 and ours[-5:] == theirs[-5:]  # self + 13 arguments, same lambda names
+    finally:
+        sys.path.remove("/root/reference")
+        for k in [k for k in sys.modules if k == "models" or k.startswith("models.") or k == "config"]:
+            del sys.modules[k]
