@@ -173,4 +173,34 @@ __device__ __forceinline__ void yh_fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// --- programmatic dependent launch (PDL): a kernel launched with yh_launch_pdl may have its CTAs
+// scheduled while the previous kernel of the stream is still draining; it must not touch global
+// memory before yh_grid_dependency_wait().  Both are no-ops for an ordinary launch.
+__device__ __forceinline__ void yh_grid_dependency_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void yh_grid_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 #endif  // __CUDACC__
+
+#ifdef __CUDACC__
+// Launch with the programmatic-stream-serialization attribute (CUDA-graph capturable): the launch
+// latency and the prologue of this kernel overlap the tail of the previous one.
+template <typename... KArgs, typename... Args>
+inline cudaError_t yh_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+#endif

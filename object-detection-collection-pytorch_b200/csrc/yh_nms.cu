@@ -249,6 +249,10 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
         yh_mbar_init(&bar_list, kThreads);
         yh_mbar_fence_init();
     }
+    // (programmatic dependent launch: the prologue above overlaps the previous kernel's tail; global
+    // memory is only touched once that kernel has completed)
+    yh_grid_dependency_wait();
+    yh_grid_launch_dependents();
     __syncthreads();
 
     // float offsets (inside the whole head tensor) of a predictor's 5 box logits and C class logits
@@ -588,8 +592,9 @@ int launch_variant(const NmsParams& p, size_t smem, void* stream) {
         if (rc) return rc;
         configured[dev] = smem;
     }
-    yh_nms_kernel<TV, TA, TC><<<(unsigned)p.n, kThreads, smem, (cudaStream_t)stream>>>(p);
-    return yh_check_cuda(cudaGetLastError(), "yh_nms launch");
+    return yh_check_cuda(yh_launch_pdl(yh_nms_kernel<TV, TA, TC>, dim3((unsigned)p.n), dim3(kThreads), smem,
+                                       (cudaStream_t)stream, p),
+                         "yh_nms launch");
 }
 
 int launch(NmsParams& p, void* ws, size_t ws_bytes, void* stream) {

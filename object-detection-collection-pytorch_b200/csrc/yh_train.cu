@@ -362,6 +362,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
         yh_mbar_fence_init();
         s_ready = 0;
     }
+    // everything above overlaps the tail of the previous kernel of the stream (programmatic dependent
+    // launch); nothing below may run before that kernel has completed: it may have produced y, and it
+    // may be the previous launch of this kernel, which shares the workspace
+    yh_grid_dependency_wait();
+    yh_grid_launch_dependents();
     __syncthreads();
 
     WarpSums sums = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -807,8 +812,8 @@ int launch_variant(const TrainParams& p, int grid, cudaStream_t stream) {
         if (rc) return rc;
         configured[dev] = smem;
     }
-    yh_train_kernel<WDY, VEC, TV, TA, TC><<<grid, kThreads, smem, stream>>>(p);
-    return yh_check_cuda(cudaGetLastError(), "yh_train launch");
+    return yh_check_cuda(yh_launch_pdl(yh_train_kernel<WDY, VEC, TV, TA, TC>, dim3(grid), dim3(kThreads), smem, stream, p),
+                         "yh_train launch");
 }
 
 template <bool WDY, bool VEC>
