@@ -67,6 +67,11 @@ extern "C" YH_API int yh_x_ntrace_copy(unsigned long long* host, int n) {
 #define NT(slot) do { } while (0)
 #endif
 
+template <bool B>
+struct FastTag {
+    static constexpr bool value = B;
+};
+
 struct NmsParams {
     YhGeom g;                // head source only
     int src;
@@ -349,235 +354,261 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
     yh_mbar_wait(&bar_list, 0);
 
     const int K = s_count;
-    if (K > kSmemCand) {  // overflow: continue in the workspace arrays
+    const bool overflow = K > kSmemCand;
+    if (overflow) {  // continue in the workspace arrays
         for (int k = tid; k < kSmemCand; k += kThreads) { cw.u_conf[k] = ca.u_conf[k]; cw.u_idx[k] = ca.u_idx[k]; }
-        ca = cw;
         __syncthreads();
     }
 
-    // ---------------- B: rank + decode, eight lanes per candidate ----------------
-    // A candidate's rank = how many candidates beat it: the eight lanes split the comparisons and
-    // fold with three shuffles.  Then (rows landed) four of them activate one box logit each and the
-    // group's first lane decodes the box into the ranked slot.
-    const int sub8 = tid & 7;
-    bool rows_in = false;
-    for (int k0 = 0; k0 < K; k0 += kThreads / 8) {
-        if (k0 + 4 * warp >= K) break;  // no candidate left for this warp: it stays out of the issue slots
-        const int k = k0 + (tid >> 3);
-        const bool on = k < K;
-        const float ck = on ? ca.u_conf[k] : 0.f;
-        const int ik = on ? ca.u_idx[k] : 0;
-        int rank = 0;
-        if (on) {
-            for (int j = sub8; j < K; j += 8) {
-                const float cj = ca.u_conf[j];
-                rank += (cj > ck || (cj == ck && ca.u_idx[j] < ik)) ? 1 : 0;
+    // Everything after the candidate list exists twice: the common case -- all candidates and all their
+    // rows in shared memory -- is compiled with pointers the compiler can PROVE to be shared (32-bit
+    // addresses, LDS/STS); the general case (workspace arrays, rows beyond the staged slots) goes
+    // through generic pointers.  The kernel is bound by instruction issue, and generic accesses with
+    // their 64-bit address arithmetic were a quarter of it.
+    auto rest = [&](auto fast_tag) {
+        constexpr bool FAST = decltype(fast_tag)::value;
+        Cand ca = carve(smem_raw + (size_t)p.stage_slots * p.slot_floats * 4, kSmemCand);
+        if (!FAST && overflow) ca = cw;
+        auto box_ptr = [&](int slot, int idx) -> const float* {
+            const long long f = box_off(idx);
+            if (FAST || slot < p.stage_slots) return reinterpret_cast<const float*>(smem_raw) + (size_t)slot * p.slot_floats + (int)(f & 3);
+            return p.y + f;
+        };
+        auto cls_ptr = [&](int slot, int idx) -> const float* {
+            if (FAST || slot < p.stage_slots) {
+                const float* st = reinterpret_cast<const float*>(smem_raw) + (size_t)slot * p.slot_floats;
+                if (v2) return st + (int)(box_off(idx) & 3) + 5;
+                return st + 8 + (int)(cls_off(idx) & 3);
             }
-        }
-        rank += __shfl_xor_sync(0xffffffffu, rank, 1);
-        rank += __shfl_xor_sync(0xffffffffu, rank, 2);
-        rank += __shfl_xor_sync(0xffffffffu, rank, 4);
-        if (!rows_in) {
-            NT(3);
-            yh_mbar_wait(&bar, 0);  // the staged rows
-            rows_in = true;
-        }
-        float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
-        int lab = 0;
-        if (head) {
-            float act = 0.f;
-            if (on && sub8 < 4) {
-                const float tq = box_ptr(k, ik)[sub8];
-                act = (sub8 < 2 || !v2) ? yh_sigmoid(tq) : expf(tq);
+            return p.y + cls_off(idx);
+        };
+
+        // ---------------- B: rank + decode, eight lanes per candidate ----------------
+        // A candidate's rank = how many candidates beat it: the eight lanes split the comparisons and
+        // fold with three shuffles.  Then (rows landed) four of them activate one box logit each and the
+        // group's first lane decodes the box into the ranked slot.
+        const int sub8 = tid & 7;
+        bool rows_in = false;
+        for (int k0 = 0; k0 < K; k0 += kThreads / 8) {
+            if (k0 + 4 * warp >= K) break;  // no candidate left for this warp: it stays out of the issue slots
+            const int k = k0 + (tid >> 3);
+            const bool on = k < K;
+            const float ck = on ? ca.u_conf[k] : 0.f;
+            const int ik = on ? ca.u_idx[k] : 0;
+            int rank = 0;
+            if (on) {
+                for (int j = sub8; j < K; j += 8) {
+                    const float cj = ca.u_conf[j];
+                    rank += (cj > ck || (cj == ck && ca.u_idx[j] < ik)) ? 1 : 0;
+                }
             }
-            const int l0 = lane & ~7;
-            const float sx = __shfl_sync(0xffffffffu, act, l0), sy = __shfl_sync(0xffffffffu, act, l0 + 1);
-            const float wa = __shfl_sync(0xffffffffu, act, l0 + 2), ha = __shfl_sync(0xffffffffu, act, l0 + 3);
+            rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+            rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+            rank += __shfl_xor_sync(0xffffffffu, rank, 4);
+            if (!rows_in) {
+                NT(3);
+                yh_mbar_wait(&bar, 0);  // the staged rows
+                rows_in = true;
+            }
+            float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+            int lab = 0;
+            if (head) {
+                float act = 0.f;
+                if (on && sub8 < 4) {
+                    const float tq = box_ptr(k, ik)[sub8];
+                    act = (sub8 < 2 || !v2) ? yh_sigmoid(tq) : expf(tq);
+                }
+                const int l0 = lane & ~7;
+                const float sx = __shfl_sync(0xffffffffu, act, l0), sy = __shfl_sync(0xffffffffu, act, l0 + 1);
+                const float wa = __shfl_sync(0xffffffffu, act, l0 + 2), ha = __shfl_sync(0xffffffffu, act, l0 + 3);
+                if (on && sub8 == 0) {
+                    const int cell = ik / A, a = ik - cell * A;
+                    const int cy = cell / g.s_w, cx = cell - cy * g.s_w;
+                    const YhBox b = yh_decode_box(sx, sy, wa, ha, g.pw[a], g.ph[a], cx, cy, g.gw, g.gh);
+                    bx = make_float4(b.x1, b.y1, b.x2, b.y2);
+                }
+            } else if (on && sub8 == 0) {
+                bx = __ldg(p.bbox + (size_t)img * P + ik);
+                if (p.labels) lab = __ldg(p.labels + (size_t)img * P + ik);
+            }
             if (on && sub8 == 0) {
-                const int cell = ik / A, a = ik - cell * A;
-                const int cy = cell / g.s_w, cx = cell - cy * g.s_w;
-                const YhBox b = yh_decode_box(sx, sy, wa, ha, g.pw[a], g.ph[a], cx, cy, g.gw, g.gh);
-                bx = make_float4(b.x1, b.y1, b.x2, b.y2);
+                ca.s_box[rank] = bx;
+                ca.s_area[rank] = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
+                ca.s_slot[rank] = k;
+                ca.s_idx[rank] = ik;
+                ca.s_conf[rank] = ck;
+                if (!head && p.labels) ca.s_lab[rank] = lab;
             }
-        } else if (on && sub8 == 0) {
-            bx = __ldg(p.bbox + (size_t)img * P + ik);
-            if (p.labels) lab = __ldg(p.labels + (size_t)img * P + ik);
         }
-        if (on && sub8 == 0) {
-            ca.s_box[rank] = bx;
-            ca.s_area[rank] = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
-            ca.s_slot[rank] = k;
-            ca.s_idx[rank] = ik;
-            ca.s_conf[rank] = ck;
-            if (!head && p.labels) ca.s_lab[rank] = lab;
-        }
-    }
-    __syncthreads();
+        __syncthreads();
 
-    NT(4);
-    const bool use_lab = head ? (p.class_aware != 0) : (p.labels != nullptr);
-    constexpr int kPick = 8;  // lanes per class pick
-    const int sub = tid & (kPick - 1);
-    if (use_lab && head) {  // label of every candidate (argmax of cls_spec)
-        for (int k0 = 0; k0 < K; k0 += kThreads / kPick) {
-            if (k0 + (32 / kPick) * warp >= K) break;
-            const int k = k0 + tid / kPick;
-            const bool act = k < K;
-            int lab;
-            float sc;
-            group_class_pick<kPick>(act ? cls_ptr(ca.s_slot[k], ca.s_idx[k]) : nullptr, C, act ? ca.s_conf[k] : 0.f, sub,
-                                    act, nullptr, &lab, &sc);
-            if (act && sub == 0) ca.s_lab[k] = lab;
+        NT(4);
+        const bool use_lab = head ? (p.class_aware != 0) : (p.labels != nullptr);
+        constexpr int kPick = 8;  // lanes per class pick
+        const int sub = tid & (kPick - 1);
+        if (use_lab && head) {  // label of every candidate (argmax of cls_spec)
+            for (int k0 = 0; k0 < K; k0 += kThreads / kPick) {
+                if (k0 + (32 / kPick) * warp >= K) break;
+                const int k = k0 + tid / kPick;
+                const bool act = k < K;
+                int lab;
+                float sc;
+                group_class_pick<kPick>(act ? cls_ptr(ca.s_slot[k], ca.s_idx[k]) : nullptr, C, act ? ca.s_conf[k] : 0.f, sub,
+                                        act, nullptr, &lab, &sc);
+                if (act && sub == 0) ca.s_lab[k] = lab;
+            }
+            __syncthreads();
         }
-        __syncthreads();
-    }
 
-    // ---------------- D: greedy suppression, tile by tile ----------------
-    const float thr = p.iou_thre;
-    for (int base = 0; base < K; base += kTile) {
-        const int tn = min(kTile, K - base);
-        const int W = (tn + 31) >> 5;
-        // (1) against the boxes kept in earlier tiles
-        for (int jp = tid; jp < kTile; jp += kThreads) {  // (whole warps: kTile and kThreads are multiples of 32)
-            bool dead = false;
-            if (jp < tn && base > 0) {
-                const float4 bj = ca.s_box[base + jp];
-                const YhBox qj{bj.x, bj.y, bj.z, bj.w};
-                const int lj = use_lab ? ca.s_lab[base + jp] : 0;
-                const int kept = s_kept;
-                for (int q = 0; q < kept; ++q) {
-                    const int i = ca.keep[q];
-                    const float4 bi = ca.s_box[i];
-                    const YhBox qi{bi.x, bi.y, bi.z, bi.w};
-                    if (yh_iou_xyxy(qi, qj) >= thr && (!use_lab || ca.s_lab[i] == lj)) { dead = true; break; }
-                }
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, dead);
-            if (lane == 0) rem0[jp >> 5] = bal;
-        }
-        __syncthreads();
-        // (2) intra-tile mask, by column: word (j, w) = candidates i in [32w, 32w+32), ranked before j,
-        //     that suppress j if kept; each warp takes columns j = warp, warp + kWarps, ... and walks
-        //     the words up to j's own (two at a time: the tests are independent)
-        if (base == 0) NT(5);
-        for (int j = warp; j < tn; j += kWarps) {
-            const float4 bj = ca.s_box[base + j];
-            const float aj = ca.s_area[base + j];
-            const int lj = use_lab ? ca.s_lab[base + j] : 0;
-#pragma unroll 2
-            for (int w = 0; w <= (j >> 5); ++w) {
-                const int i = w * 32 + lane;
-                bool bit = false;
-                if (i < j) {
-                    bit = suppresses(ca.s_box[base + i], ca.s_area[base + i], bj, aj, thr);
-                    if (use_lab) bit = bit && lj == ca.s_lab[base + i];
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, bit);
-                if (lane == 0) mask[j * kTileWords + w] = m;
-            }
-        }
-        __syncthreads();
-        if (base == 0) NT(7);
-        // (3) one warp resolves the greedy order by fixed-point iteration instead of a serial walk:
-        //     alive[j] = !dead0[j] && no alive i < j suppresses j.  Candidate j's value is final once
-        //     all i < j are final, so after t sweeps the first t candidates are right; in practice the
-        //     suppression chains are 2-3 deep and the sweep converges in as many steps (<= tn + 1).
-        //     The same warp then appends the survivors, in rank order, to the keep list.
-        if (warp == 0) {
-            unsigned alive[kTileWords], dead0[kTileWords];
-#pragma unroll
-            for (int w = 0; w < kTileWords; ++w) {
-                dead0[w] = w < W ? rem0[w] : 0xffffffffu;
-                if (w == W - 1 && (tn & 31)) dead0[w] |= ~0u << (tn & 31);  // bits past the tile end
-                alive[w] = ~dead0[w];
-            }
-            if (W <= 2) {
-                // common case (<= 64 candidates): the lane's two columns live in registers
-                const unsigned c00 = lane < tn ? mask[lane * kTileWords] : 0u;
-                const unsigned c10 = 32 + lane < tn ? mask[(32 + lane) * kTileWords] : 0u;
-                const unsigned c11 = 32 + lane < tn ? mask[(32 + lane) * kTileWords + 1] : 0u;
-                for (int sweep = 0; sweep <= tn; ++sweep) {
-                    const unsigned n0 = __ballot_sync(0xffffffffu, (c00 & alive[0]) == 0u) & ~dead0[0];
-                    const unsigned n1 = __ballot_sync(0xffffffffu, ((c10 & n0) | (c11 & alive[1])) == 0u) & ~dead0[1];
-                    const bool same = n0 == alive[0] && n1 == alive[1];
-                    alive[0] = n0;
-                    alive[1] = n1;
-                    if (same) break;
-                }
-            } else {
-                for (int sweep = 0; sweep <= tn; ++sweep) {
-                    bool changed = false;
-#pragma unroll
-                    for (int m = 0; m < kTileWords; ++m) {
-                        if (m < W) {  // (warp-uniform)
-                            const int j = 32 * m + lane;
-                            bool a = false;
-                            if (j < tn) {
-                                unsigned hit = 0u;
-#pragma unroll
-                                for (int w = 0; w < kTileWords; ++w)
-                                    if (w <= m) hit |= mask[j * kTileWords + w] & alive[w];
-                                a = hit == 0u;
-                            }
-                            const unsigned nw = __ballot_sync(0xffffffffu, a) & ~dead0[m];
-                            changed = changed || nw != alive[m];
-                            alive[m] = nw;  // (later words of this sweep already see it)
-                        }
+        // ---------------- D: greedy suppression, tile by tile ----------------
+        const float thr = p.iou_thre;
+        for (int base = 0; base < K; base += kTile) {
+            const int tn = min(kTile, K - base);
+            const int W = (tn + 31) >> 5;
+            // (1) against the boxes kept in earlier tiles
+            for (int jp = tid; jp < kTile; jp += kThreads) {  // (whole warps: kTile and kThreads are multiples of 32)
+                bool dead = false;
+                if (jp < tn && base > 0) {
+                    const float4 bj = ca.s_box[base + jp];
+                    const YhBox qj{bj.x, bj.y, bj.z, bj.w};
+                    const int lj = use_lab ? ca.s_lab[base + jp] : 0;
+                    const int kept = s_kept;
+                    for (int q = 0; q < kept; ++q) {
+                        const int i = ca.keep[q];
+                        const float4 bi = ca.s_box[i];
+                        const YhBox qi{bi.x, bi.y, bi.z, bi.w};
+                        if (yh_iou_xyxy(qi, qj) >= thr && (!use_lab || ca.s_lab[i] == lj)) { dead = true; break; }
                     }
-                    if (!changed) break;
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, dead);
+                if (lane == 0) rem0[jp >> 5] = bal;
+            }
+            __syncthreads();
+            // (2) intra-tile mask, by column: word (j, w) = candidates i in [32w, 32w+32), ranked before j,
+            //     that suppress j if kept; each warp takes columns j = warp, warp + kWarps, ... and walks
+            //     the words up to j's own (two at a time: the tests are independent)
+            if (base == 0) NT(5);
+            for (int j = warp; j < tn; j += kWarps) {
+                const float4 bj = ca.s_box[base + j];
+                const float aj = ca.s_area[base + j];
+                const int lj = use_lab ? ca.s_lab[base + j] : 0;
+    #pragma unroll 2
+                for (int w = 0; w <= (j >> 5); ++w) {
+                    const int i = w * 32 + lane;
+                    bool bit = false;
+                    if (i < j) {
+                        bit = suppresses(ca.s_box[base + i], ca.s_area[base + i], bj, aj, thr);
+                        if (use_lab) bit = bit && lj == ca.s_lab[base + i];
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, bit);
+                    if (lane == 0) mask[j * kTileWords + w] = m;
                 }
             }
-            int kept_n = s_kept;
-#pragma unroll
-            for (int m = 0; m < kTileWords; ++m) {
-                if (m < W) {
-                    if ((alive[m] >> lane) & 1u) ca.keep[kept_n + __popc(alive[m] & ((1u << lane) - 1u))] = base + 32 * m + lane;
-                    kept_n += __popc(alive[m]);
+            __syncthreads();
+            if (base == 0) NT(7);
+            // (3) one warp resolves the greedy order by fixed-point iteration instead of a serial walk:
+            //     alive[j] = !dead0[j] && no alive i < j suppresses j.  Candidate j's value is final once
+            //     all i < j are final, so after t sweeps the first t candidates are right; in practice the
+            //     suppression chains are 2-3 deep and the sweep converges in as many steps (<= tn + 1).
+            //     The same warp then appends the survivors, in rank order, to the keep list.
+            if (warp == 0) {
+                unsigned alive[kTileWords], dead0[kTileWords];
+    #pragma unroll
+                for (int w = 0; w < kTileWords; ++w) {
+                    dead0[w] = w < W ? rem0[w] : 0xffffffffu;
+                    if (w == W - 1 && (tn & 31)) dead0[w] |= ~0u << (tn & 31);  // bits past the tile end
+                    alive[w] = ~dead0[w];
                 }
+                if (W <= 2) {
+                    // common case (<= 64 candidates): the lane's two columns live in registers
+                    const unsigned c00 = lane < tn ? mask[lane * kTileWords] : 0u;
+                    const unsigned c10 = 32 + lane < tn ? mask[(32 + lane) * kTileWords] : 0u;
+                    const unsigned c11 = 32 + lane < tn ? mask[(32 + lane) * kTileWords + 1] : 0u;
+                    for (int sweep = 0; sweep <= tn; ++sweep) {
+                        const unsigned n0 = __ballot_sync(0xffffffffu, (c00 & alive[0]) == 0u) & ~dead0[0];
+                        const unsigned n1 = __ballot_sync(0xffffffffu, ((c10 & n0) | (c11 & alive[1])) == 0u) & ~dead0[1];
+                        const bool same = n0 == alive[0] && n1 == alive[1];
+                        alive[0] = n0;
+                        alive[1] = n1;
+                        if (same) break;
+                    }
+                } else {
+                    for (int sweep = 0; sweep <= tn; ++sweep) {
+                        bool changed = false;
+    #pragma unroll
+                        for (int m = 0; m < kTileWords; ++m) {
+                            if (m < W) {  // (warp-uniform)
+                                const int j = 32 * m + lane;
+                                bool a = false;
+                                if (j < tn) {
+                                    unsigned hit = 0u;
+    #pragma unroll
+                                    for (int w = 0; w < kTileWords; ++w)
+                                        if (w <= m) hit |= mask[j * kTileWords + w] & alive[w];
+                                    a = hit == 0u;
+                                }
+                                const unsigned nw = __ballot_sync(0xffffffffu, a) & ~dead0[m];
+                                changed = changed || nw != alive[m];
+                                alive[m] = nw;  // (later words of this sweep already see it)
+                            }
+                        }
+                        if (!changed) break;
+                    }
+                }
+                int kept_n = s_kept;
+    #pragma unroll
+                for (int m = 0; m < kTileWords; ++m) {
+                    if (m < W) {
+                        if ((alive[m] >> lane) & 1u) ca.keep[kept_n + __popc(alive[m] & ((1u << lane) - 1u))] = base + 32 * m + lane;
+                        kept_n += __popc(alive[m]);
+                    }
+                }
+                if (lane == 0) s_kept = kept_n;
             }
-            if (lane == 0) s_kept = kept_n;
+            __syncthreads();
+            if (base == 0) NT(8);
         }
-        __syncthreads();
-        if (base == 0) NT(8);
-    }
 
-    NT(12);
-    // ---------------- E: emit ----------------
-    const int kept = s_kept;
-    if (tid == 0) p.keep_cnt[img] = kept;
-    const int nout = min(kept, p.max_out);
-    const bool want_cls = head && (p.out_cls_spec || p.out_label || p.out_score);
-    for (int t0 = 0; t0 < nout; t0 += kThreads / kPick) {
-        if (t0 + (32 / kPick) * warp >= nout) break;
-        const int t = t0 + tid / kPick;
-        const bool act = t < nout;
-        int i = 0, idx = 0;
-        float conf = 0.f;
-        size_t o = 0;
-        if (act) {
-            i = ca.keep[t];
-            idx = ca.s_idx[i];
-            conf = ca.s_conf[i];
-            o = (size_t)img * p.max_out + t;
-            if (sub == 0) {
-                p.keep_idx[o] = idx;
-                if (p.out_conf) p.out_conf[o] = conf;
-            } else if (sub == 1) {
-                if (p.out_bbox) p.out_bbox[o] = ca.s_box[i];
+        NT(12);
+        // ---------------- E: emit ----------------
+        const int kept = s_kept;
+        if (tid == 0) p.keep_cnt[img] = kept;
+        const int nout = min(kept, p.max_out);
+        const bool want_cls = head && (p.out_cls_spec || p.out_label || p.out_score);
+        for (int t0 = 0; t0 < nout; t0 += kThreads / kPick) {
+            if (t0 + (32 / kPick) * warp >= nout) break;
+            const int t = t0 + tid / kPick;
+            const bool act = t < nout;
+            int i = 0, idx = 0;
+            float conf = 0.f;
+            size_t o = 0;
+            if (act) {
+                i = ca.keep[t];
+                idx = ca.s_idx[i];
+                conf = ca.s_conf[i];
+                o = (size_t)img * p.max_out + t;
+                if (sub == 0) {
+                    p.keep_idx[o] = idx;
+                    if (p.out_conf) p.out_conf[o] = conf;
+                } else if (sub == 1) {
+                    if (p.out_bbox) p.out_bbox[o] = ca.s_box[i];
+                }
+            }
+            if (want_cls) {
+                int lab;
+                float sc;
+                group_class_pick<kPick>(act ? cls_ptr(ca.s_slot[i], idx) : nullptr, C, conf, sub, act,
+                                        (act && p.out_cls_spec) ? p.out_cls_spec + o * C : nullptr, &lab, &sc);
+                if (act && sub == 2) {
+                    if (p.out_label) p.out_label[o] = lab;
+                    if (p.out_score) p.out_score[o] = sc;
+                }
             }
         }
-        if (want_cls) {
-            int lab;
-            float sc;
-            group_class_pick<kPick>(act ? cls_ptr(ca.s_slot[i], idx) : nullptr, C, conf, sub, act,
-                                    (act && p.out_cls_spec) ? p.out_cls_spec + o * C : nullptr, &lab, &sc);
-            if (act && sub == 2) {
-                if (p.out_label) p.out_label[o] = lab;
-                if (p.out_score) p.out_score[o] = sc;
-            }
-        }
-    }
-    NT(13);
+        NT(13);
+    };
+    if (!overflow && K <= p.stage_slots) rest(FastTag<true>{});
+    else rest(FastTag<false>{});
 }
 
 template <int TV, int TA, int TC>
