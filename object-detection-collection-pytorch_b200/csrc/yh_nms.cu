@@ -260,39 +260,38 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
     yh_grid_launch_dependents();
     __syncthreads();
 
-    // float offsets (inside the whole head tensor) of a predictor's 5 box logits and C class logits
-    const long long fimg = (long long)img * p.img_floats;
-    auto box_off = [&](int idx) -> long long {
-        return fimg + (v2 ? (long long)idx * bs : (long long)(idx / A) * cf + (idx % A) * 5);
-    };
-    auto cls_off = [&](int idx) -> long long {
-        return fimg + (v2 ? (long long)idx * bs + 5 : (long long)(idx / A) * cf + 5 * A);
-    };
+    // float offsets, inside the image, of a predictor's 5 box logits and C class logits (32-bit: one
+    // image of the head tensor is far below 2^31 floats); `fsh` is the image's own shift inside its
+    // 16-byte window, so (fsh + offset) & 3 is a logit's shift inside ITS window
+    const float* yimg = p.y + (long long)img * p.img_floats;
+    const int fsh = (int)(((long long)img * p.img_floats) & 3);
+    auto box_off = [&](int idx) -> int { return v2 ? idx * bs : (idx / A) * cf + (idx % A) * 5; };
+    auto cls_off = [&](int idx) -> int { return v2 ? idx * bs + 5 : (idx / A) * cf + 5 * A; };
     // where the logits of unsorted candidate `slot` (predictor idx) can be read: its staged row, or
     // global memory for candidates beyond the staged slots
     auto box_ptr = [&](int slot, int idx) -> const float* {
-        const long long f = box_off(idx);
-        if (slot < p.stage_slots) return stage + (size_t)slot * p.slot_floats + (int)(f & 3);
-        return p.y + f;
+        const int f = box_off(idx);
+        if (slot < p.stage_slots) return stage + (size_t)slot * p.slot_floats + ((fsh + f) & 3);
+        return yimg + f;
     };
     auto cls_ptr = [&](int slot, int idx) -> const float* {
         if (slot < p.stage_slots) {
-            if (v2) return stage + (size_t)slot * p.slot_floats + (int)(box_off(idx) & 3) + 5;
-            return stage + (size_t)slot * p.slot_floats + 8 + (int)(cls_off(idx) & 3);
+            if (v2) return stage + (size_t)slot * p.slot_floats + ((fsh + box_off(idx)) & 3) + 5;
+            return stage + (size_t)slot * p.slot_floats + 8 + ((fsh + cls_off(idx)) & 3);
         }
-        return p.y + cls_off(idx);
+        return yimg + cls_off(idx);
     };
-    // stage `len` floats starting at tensor offset f into dst (+ the shift of f inside its 16-byte
+    // stage `len` floats starting at image offset f into dst (+ the shift of f inside its 16-byte
     // window): one bulk copy of the aligned window; returns the bytes the mbarrier has to expect
-    const long long lim4 = p.total_floats & ~3ll;
-    auto stage_span = [&](float* dst, long long f, int len) -> uint32_t {
-        const int shift = (int)(f & 3);
+    const long long lim4 = (p.total_floats & ~3ll) - (long long)img * p.img_floats;  // (relative to the image)
+    auto stage_span = [&](float* dst, int f, int len) -> uint32_t {
+        const int shift = (fsh + f) & 3;
         const int win = (shift + len + 3) & ~3;
-        if (p.use_tma && f - shift + win <= lim4) {
-            yh_bulk_load(dst, p.y + (f - shift), (uint32_t)win * 4u, &bar);
+        if (p.use_tma && (long long)(f - shift + win) <= lim4) {
+            yh_bulk_load(dst, yimg + (f - shift), (uint32_t)win * 4u, &bar);
             return (uint32_t)win * 4u;
         }
-        for (int q = 0; q < len; ++q) dst[shift + q] = __ldg(p.y + f + q);  // unaligned tensor / its very end
+        for (int q = 0; q < len; ++q) dst[shift + q] = __ldg(yimg + f + q);  // unaligned tensor / its very end
         return 0u;
     };
 
@@ -305,7 +304,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
         for (int u = 0; u < kLoadUnroll; ++u) {
             const int i = base + u * kThreads + tid;
             val[u] = 0.f;
-            if (i < P) val[u] = head ? __ldg(p.y + box_off(i) + 4) : __ldg(p.conf + (size_t)img * P + i);
+            if (i < P) val[u] = head ? __ldg(yimg + box_off(i) + 4) : __ldg(p.conf + (size_t)img * P + i);
         }
 #pragma unroll
         for (int u = 0; u < kLoadUnroll; ++u) {
@@ -370,17 +369,17 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
         Cand ca = carve(smem_raw + (size_t)p.stage_slots * p.slot_floats * 4, kSmemCand);
         if (!FAST && overflow) ca = cw;
         auto box_ptr = [&](int slot, int idx) -> const float* {
-            const long long f = box_off(idx);
-            if (FAST || slot < p.stage_slots) return reinterpret_cast<const float*>(smem_raw) + (size_t)slot * p.slot_floats + (int)(f & 3);
-            return p.y + f;
+            const int f = box_off(idx);
+            if (FAST || slot < p.stage_slots) return reinterpret_cast<const float*>(smem_raw) + slot * p.slot_floats + ((fsh + f) & 3);
+            return yimg + f;
         };
         auto cls_ptr = [&](int slot, int idx) -> const float* {
             if (FAST || slot < p.stage_slots) {
-                const float* st = reinterpret_cast<const float*>(smem_raw) + (size_t)slot * p.slot_floats;
-                if (v2) return st + (int)(box_off(idx) & 3) + 5;
-                return st + 8 + (int)(cls_off(idx) & 3);
+                const float* st = reinterpret_cast<const float*>(smem_raw) + slot * p.slot_floats;
+                if (v2) return st + ((fsh + box_off(idx)) & 3) + 5;
+                return st + 8 + ((fsh + cls_off(idx)) & 3);
             }
-            return p.y + cls_off(idx);
+            return yimg + cls_off(idx);
         };
 
         // ---------------- B: rank + decode, eight lanes per candidate ----------------
