@@ -97,6 +97,7 @@ struct NmsParams {
     int use_tma;             // y is 16-byte aligned: candidate rows are staged with bulk copies
     int stage_slots;         // candidate rows staged in shared memory (<= kSmemCand)
     int slot_floats;         // floats per staged row slot (multiple of 4)
+    unsigned magic_sw;       // ceil(2^32 / s_w): cell / s_w == umulhi(cell, magic_sw) for cell < 2^16
 };
 
 struct Cand {
@@ -364,8 +365,9 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
     // addresses, LDS/STS); the general case (workspace arrays, rows beyond the staged slots) goes
     // through generic pointers.  The kernel is bound by instruction issue, and generic accesses with
     // their 64-bit address arithmetic were a quarter of it.
-    auto rest = [&](auto fast_tag) {
+    auto rest = [&](auto fast_tag, auto lab_tag) {
         constexpr bool FAST = decltype(fast_tag)::value;
+        constexpr bool LAB = decltype(lab_tag)::value;  // labels take part in the suppression test
         Cand ca = carve(smem_raw + (size_t)p.stage_slots * p.slot_floats * 4, kSmemCand);
         if (!FAST && overflow) ca = cw;
         auto box_ptr = [&](int slot, int idx) -> const float* {
@@ -422,7 +424,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
                 const float wa = __shfl_sync(0xffffffffu, act, l0 + 2), ha = __shfl_sync(0xffffffffu, act, l0 + 3);
                 if (on && sub8 == 0) {
                     const int cell = ik / A, a = ik - cell * A;
-                    const int cy = cell / g.s_w, cx = cell - cy * g.s_w;
+                    const int cy = (int)__umulhi((unsigned)cell, p.magic_sw), cx = cell - cy * g.s_w;  // cell / s_w
                     const YhBox b = yh_decode_box(sx, sy, wa, ha, g.pw[a], g.ph[a], cx, cy, g.gw, g.gh);
                     bx = make_float4(b.x1, b.y1, b.x2, b.y2);
                 }
@@ -442,7 +444,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
         __syncthreads();
 
         NT(4);
-        const bool use_lab = head ? (p.class_aware != 0) : (p.labels != nullptr);
+        const bool use_lab = LAB && (head ? (p.class_aware != 0) : (p.labels != nullptr));
         constexpr int kPick = 8;  // lanes per class pick
         const int sub = tid & (kPick - 1);
         if (use_lab && head) {  // label of every candidate (argmax of cls_spec)
@@ -606,8 +608,10 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
         }
         NT(13);
     };
-    if (!overflow && K <= p.stage_slots) rest(FastTag<true>{});
-    else rest(FastTag<false>{});
+    const bool with_labels = head ? (p.class_aware != 0) : (p.labels != nullptr);
+    if (!overflow && K <= p.stage_slots && !with_labels) rest(FastTag<true>{}, FastTag<false>{});
+    else if (!overflow && K <= p.stage_slots) rest(FastTag<true>{}, FastTag<true>{});
+    else rest(FastTag<false>{}, FastTag<true>{});
 }
 
 template <int TV, int TA, int TC>
@@ -676,6 +680,8 @@ int postprocess_impl(int version, const float* y, int n, int s_h, int s_w, int a
     p.out_bbox = reinterpret_cast<float4*>(out_bbox);
     p.out_conf = out_conf; p.out_cls_spec = out_cls_spec; p.out_label = out_label; p.out_score = out_score;
 
+    p.magic_sw = (unsigned)(0xFFFFFFFFull / (unsigned)s_w) + 1u;
+    YH_REQUIRE(p.g.cells < 65536, YH_ERR_UNSUPPORTED, "more than 65535 grid cells per image");
     p.img_floats = p.g.cells * p.g.cell_floats;
     p.total_floats = (long long)n * p.img_floats;
     p.use_tma = ((uintptr_t)y & 15) == 0;
