@@ -166,6 +166,20 @@ YH_API int yh_v1_postprocess(const float* y, int n, int s_h, int s_w, int b, int
                       float* out_cls_spec, int32_t* out_label, float* out_score,
                       void* ws, size_t ws_bytes, void* stream);
 
+/* Batched true-positive matching for evaluation: the per-detection loop of evaluate_model
+ * (reference models/utils.py:231-262).  A detection is a true positive at level L iff a ground-truth
+ * box of its class in its image has get_iou(gt, det, numpy=True) >= L (float64, no one-to-one
+ * assignment).
+ *   det_bbox[N,max_out,4], det_label[N,max_out], keep_cnt[N]: the post-process outputs;
+ *   gt_boxes_xyxy[M,4] float64, gt_labels[M], gt_off[N+1]: annotations grouped by image;
+ *   levels_host[num_levels] (HOST, <= 16) IoU levels;
+ *   best_iou[N,max_out] float64 (-1: no ground truth of the class, or unused slot);
+ *   tp[N,max_out,num_levels] uint8. */
+YH_API int yh_match_detections(const float* det_bbox, const int32_t* det_label, const int32_t* keep_cnt,
+                        int n, int max_out, const double* gt_boxes_xyxy, const int32_t* gt_labels,
+                        const int32_t* gt_off, const double* levels_host, int num_levels,
+                        double* best_iou, unsigned char* tp, void* stream);
+
 /* Greedy NMS on already-decoded boxes, per image: models/utils.py:68-164.
  *   bbox[N,P,4], conf[N,P]; labels[N,P] or NULL (NULL = class-agnostic, the reference).
  *   keep_idx[N,max_out], keep_cnt[N] as above.  ws: yh_postprocess_workspace_bytes(n, p). */

@@ -35,6 +35,7 @@ SIGNATURES = {
     "yh_postprocess_workspace_bytes": (_sz, [_i, _i]),
     "yh_v2_postprocess": (_i, [_p, _i, _i, _i, _i, _i, _p, _f, _f, _f, _f, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "yh_v1_postprocess": (_i, [_p, _i, _i, _i, _i, _i, _f, _f, _f, _f, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "yh_match_detections": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p]),
     "yh_nms": (_i, [_p, _p, _p, _i, _i, _f, _f, _i, _p, _p, _p, _sz, _p]),
     "yh_iou": (_i, [_p, _p, _i64, _p, _p]),
     "yh_scale_inplace": (_i, [_p, _i64, _p, _p]),

@@ -42,3 +42,48 @@ def nms(bbox_coord_batch, conf_score_batch, cls_spec_conf_score_batch, conf_scor
     k = int(keep_cnt.item())  # the reference's return shapes depend on the data as well
     sel = keep_idx[0, :k].long()
     return bbox[0].index_select(0, sel), conf[0].index_select(0, sel), spec.index_select(0, sel)
+
+
+DEFAULT_LEVELS = (.50, .55, .60, .65, .70, .75, .80, .85, .90, .95)  # reference models/utils.py:177
+
+
+def average_precision(tp, scores, num_gt, eps=1e-6):
+    """AP per IoU level from true-positive flags `tp` [K,L] and class scores [K] of one class, the
+    reference's way (models/utils.py:294-333): descending score order, cumulative precision/recall,
+    precision envelope from the right, sum of envelope times recall increments."""
+    tp = np.asarray(tp, dtype=np.int64).reshape(len(scores), -1)
+    order = np.argsort(np.asarray(scores))[::-1]
+    tp = tp[order]
+    ctp = np.cumsum(tp, axis=0)
+    cfp = np.cumsum(1 - tp, axis=0)
+    prec = ctp / (ctp + cfp + eps)
+    rec = ctp / (num_gt + eps)
+    envelope = np.maximum.accumulate(prec[::-1], axis=0)[::-1]
+    drec = rec - np.concatenate([np.zeros_like(rec[:1]), rec[:-1]], axis=0)
+    return np.sum(envelope * drec, axis=0)
+
+
+def evaluate_detections(post, gt_boxes_xyxy, gt_labels, gt_off, cls_list, level_list=DEFAULT_LEVELS):
+    """Batched counterpart of evaluate_model's inner loops (reference models/utils.py:171-338): `post`
+    is a batched postprocess()/detect result for N images, the ground truth comes as float64 boxes
+    [M,4], class indices [M] and per-image offsets [N+1].  The true-positive matching runs on the device
+    (yh_match_detections); the AP arithmetic is the reference's numpy, on the host.  Returns the
+    reference's dict: {"level_list": levels, class name: AP per level}.  A class without detections gets
+    zeros (the reference raises on it)."""
+    levels = np.asarray(level_list, dtype=np.float64)
+    _, tp = ops.match_detections(post, gt_boxes_xyxy, gt_labels, gt_off, levels)
+    n, max_out = tp.shape[0], tp.shape[1]
+    cnt = post["keep_cnt"].clamp(max=max_out).cpu().numpy()
+    valid = np.arange(max_out)[None, :] < cnt[:, None]
+    tp = tp.cpu().numpy()[valid]
+    label = post["label"].cpu().numpy()[valid]
+    score = post["score"].cpu().numpy()[valid]
+    gt_labels = np.asarray(torch.as_tensor(gt_labels).cpu())
+    result = {"level_list": levels}
+    for ci, cls in enumerate(cls_list):
+        sel = label == ci
+        if not sel.any():
+            result[cls] = np.zeros(len(levels))
+            continue
+        result[cls] = average_precision(tp[sel], score[sel], int(np.sum(gt_labels == ci)))
+    return result

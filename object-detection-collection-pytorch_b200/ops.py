@@ -244,6 +244,28 @@ def postprocess(y, *, version, img_hw, conf_thre, iou_thre, anchors=None, boxes_
                 label=label, score=score, _ws=ws)
 
 
+def match_detections(post, gt_boxes_xyxy, gt_labels, gt_off, levels):
+    """True-positive flags of the detections in `post` (a postprocess() result) against float64
+    ground-truth boxes grouped by image -- yh_match_detections.  Returns (best_iou [N,max_out] float64,
+    tp [N,max_out,L] uint8)."""
+    bbox, label, cnt = post["bbox"], post["label"], post["keep_cnt"]
+    dev = bbox.device
+    n, max_out = int(bbox.shape[0]), int(bbox.shape[1])
+    gt_boxes = torch.as_tensor(gt_boxes_xyxy, dtype=torch.float64).to(dev).reshape(-1, 4).contiguous()
+    gt_labels = torch.as_tensor(gt_labels).to(device=dev, dtype=torch.int32).contiguous()
+    gt_off = torch.as_tensor(gt_off).to(device=dev, dtype=torch.int32).contiguous()
+    if gt_off.numel() != n + 1:
+        raise ValueError("gt_off must have N+1 entries")
+    lv = [float(v) for v in levels]
+    lv_h = (C.c_double * len(lv))(*lv)
+    with torch.cuda.device(dev):
+        best = torch.empty(n, max_out, dtype=torch.float64, device=dev)
+        tp = torch.empty(n, max_out, len(lv), dtype=torch.uint8, device=dev)
+        _lib.call("yh_match_detections", _ptr(bbox), _ptr(label), _ptr(cnt), n, max_out, _ptr(gt_boxes),
+                  _ptr(gt_labels), _ptr(gt_off), lv_h, len(lv), _ptr(best), _ptr(tp), _stream())
+    return best, tp
+
+
 def nms_indices(bbox, conf, *, conf_thre, iou_thre, labels=None, max_out=None):
     """Per-image greedy NMS on decoded boxes: bbox [N,P,4], conf [N,P] -> (keep_idx, keep_cnt)."""
     bbox = _require_cuda_f32(bbox, "bbox")

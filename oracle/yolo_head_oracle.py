@@ -456,3 +456,26 @@ def postprocess_torch(y, height, width, version, anchors, conf_thre, iou_thre):
                         label=sp.argmax(-1).numpy().astype(np.int32) if len(kc) else np.zeros(0, np.int32),
                         score=sp.max(-1)[0].numpy() if len(kc) else np.zeros(0, F32)))
     return out
+
+
+# --------------------------------------------------------------------------------------
+# evaluation: true-positive matching -- models/utils.py:231-262
+# --------------------------------------------------------------------------------------
+def match_detections_np(det_bbox, det_label, gt_boxes, gt_labels, levels):
+    """One image: tp[K,L] for K detections against the image's ground truth, float64 like
+    get_iou(..., numpy=True): a detection is a true positive at a level iff some ground-truth box of
+    its class reaches that IoU (models/utils.py:241-257)."""
+    levels = np.asarray(levels, dtype=np.float64)
+    det_bbox = np.asarray(det_bbox, dtype=np.float64).reshape(-1, 4)
+    gt_boxes = np.asarray(gt_boxes, dtype=np.float64).reshape(-1, 4)
+    tp = np.zeros((len(det_bbox), len(levels)), dtype=np.int64)
+    for k, (b, c) in enumerate(zip(det_bbox, det_label)):
+        g = gt_boxes[np.asarray(gt_labels) == c]
+        ix1, iy1 = np.maximum(g[:, 0], b[0]), np.maximum(g[:, 1], b[1])
+        ix2, iy2 = np.minimum(g[:, 2], b[2]), np.minimum(g[:, 3], b[3])
+        inter = np.clip(ix2 - ix1, 0, None) * np.clip(iy2 - iy1, 0, None)
+        union = (g[:, 2] - g[:, 0]) * (g[:, 3] - g[:, 1]) + (b[2] - b[0]) * (b[3] - b[1]) - inter
+        iou = inter / (union + 1e-6)
+        fp = ((iou[:, None] < levels).astype(int).prod(0) >= 1).astype(int)
+        tp[k] = 1 - fp
+    return tp

@@ -177,8 +177,57 @@ def run_collate(version, n, height, width, seed, num_cls=20):
                 rec=rec.view(np.int32).reshape(-1, 12), obj_dtype=str(obj.dtype), sig_dtype=str(sig_txty.dtype))
 
 
+def run_evaluate(seed, n=12, num_cls=4, height=416, width=416):
+    """The reference's own evaluate_model (models/utils.py:171-338) driven by a stand-in model whose
+    detect() returns canned detections (jittered copies of the ground truth plus clutter): its per-class
+    APs pin the batched evaluation."""
+    rng = np.random.default_rng(seed)
+    boxes, labels, img = synthetic.make_boxes(rng, n, height, width, 2, 5, num_cls)
+    dets = []
+    for i in range(n):
+        g = boxes[img == i]
+        gl = labels[img == i]
+        jit = g + rng.normal(0, 12.0, size=g.shape)
+        clutter = synthetic.make_boxes(rng, 1, height, width, 3, 3, num_cls)
+        db = np.concatenate([jit, clutter[0]], 0).astype(np.float32)
+        dl = np.concatenate([np.where(rng.random(len(gl)) < 0.8, gl, rng.integers(0, num_cls, len(gl))), clutter[1]]).astype(np.int32)
+        ds = rng.random(len(db)).astype(np.float32)
+        order = np.argsort(-ds)
+        dets.append((db[order], dl[order], ds[order]))
+    cls_list = [str(c) for c in range(num_cls)]
+
+    class FakeModel:
+        def __init__(self):
+            self.cls_list = cls_list
+            self.calls = 0
+
+        def detect(self, image, conf, iou):
+            b, l, s_ = dets[self.calls]
+            self.calls += 1
+            return {"bbox_list": b.tolist(), "lbl_list": [cls_list[i] for i in l], "conf_score_list": s_.tolist(),
+                    "cls_spec_conf_score_list": s_.tolist()}
+
+    dataset = [(i, None, {"bbox_list": boxes[img == i].tolist(), "lbl_list": [cls_list[c] for c in labels[img == i]]})
+               for i in range(n)]
+    res = ref_utils.evaluate_model(FakeModel(), dataset, None)
+    max_out = max(len(d[0]) for d in dets)
+    det_bbox = np.zeros((n, max_out, 4), np.float32)
+    det_label = np.zeros((n, max_out), np.int32)
+    det_score = np.zeros((n, max_out), np.float32)
+    cnt = np.zeros(n, np.int32)
+    for i, (b, l, s_) in enumerate(dets):
+        cnt[i] = len(b)
+        det_bbox[i, :len(b)], det_label[i, :len(b)], det_score[i, :len(b)] = b, l, s_
+    off = np.zeros(n + 1, np.int32)
+    np.cumsum(np.bincount(img, minlength=n), out=off[1:])
+    return dict(n=n, num_cls=num_cls, gt_boxes=boxes, gt_labels=labels.astype(np.int32), gt_off=off, det_bbox=det_bbox,
+                det_label=det_label, det_score=det_score, keep_cnt=cnt, levels=np.asarray(res["level_list"], np.float64),
+                ap=np.stack([res[c] for c in cls_list]))
+
+
 def main():
     lam = synthetic.DEFAULT_LAMBDAS
+    np.savez_compressed(os.path.join(HERE, "evaluate.npz"), **run_evaluate(301))
     np.savez_compressed(os.path.join(HERE, "v2_collate.npz"), **run_collate(2, 6, 416, 416, 201))
     np.savez_compressed(os.path.join(HERE, "v2_collate_nonsquare.npz"), **run_collate(2, 3, 352, 480, 202))
     np.savez_compressed(os.path.join(HERE, "v1_collate.npz"), **run_collate(1, 5, 224, 224, 203))

@@ -282,6 +282,33 @@ def test_get_loss_from_boxes_equals_the_dense_signature(cuda_device):
 
 
 # ------------------------------------------------------------------------------------------
+# batched evaluation
+# ------------------------------------------------------------------------------------------
+def test_evaluate_detections_matches_reference_evaluate_model(cuda_device):
+    """yh_match_detections + the host AP arithmetic vs the per-class APs of the reference's own
+    evaluate_model run on the same detections and annotations: bit-exact."""
+    from odcp_b200.models.utils import evaluate_detections
+    z = dict(np.load(os.path.join(GOLDEN, "evaluate.npz")))
+    post = dict(bbox=torch.from_numpy(z["det_bbox"]).to(cuda_device), label=torch.from_numpy(z["det_label"]).to(cuda_device),
+                score=torch.from_numpy(z["det_score"]).to(cuda_device), keep_cnt=torch.from_numpy(z["keep_cnt"]).to(cuda_device))
+    cls_list = [str(c) for c in range(int(z["num_cls"]))]
+    res = evaluate_detections(post, z["gt_boxes"], z["gt_labels"], z["gt_off"], cls_list, z["levels"])
+    assert np.array_equal(res["level_list"], z["levels"])
+    for c, name in enumerate(cls_list):
+        assert np.array_equal(res[name], z["ap"][c]), name
+    # matching against the oracle, slot by slot, including unused slots and classes without ground truth
+    best, tp = ops.match_detections(post, z["gt_boxes"], z["gt_labels"], z["gt_off"], z["levels"])
+    tp = tp.cpu().numpy()
+    for i in range(int(z["n"])):
+        k = int(z["keep_cnt"][i])
+        lo, hi = int(z["gt_off"][i]), int(z["gt_off"][i + 1])
+        want = O.match_detections_np(z["det_bbox"][i, :k], z["det_label"][i, :k], z["gt_boxes"][lo:hi],
+                                     z["gt_labels"][lo:hi], z["levels"])
+        assert np.array_equal(tp[i, :k], want)
+        assert not tp[i, k:].any()
+
+
+# ------------------------------------------------------------------------------------------
 # predict / decode
 # ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name,version", [("v2_predict.npz", 2), ("v1_predict.npz", 1)])

@@ -105,3 +105,25 @@ def test_iou_known_answers():
     assert np.array_equal(O.iou_torch(torch.as_tensor(z["b1"]), torch.as_tensor(z["b2"])).numpy(), z["iou"])
     assert z["iou"][1] == 0 and z["iou"][2] == 0 and z["iou"][3] == 0 and z["iou"][4] == 0
     assert abs(z["iou"][0] - 1.0) < 1e-5
+
+
+def test_evaluation_matching_and_ap_match_the_reference():
+    """Oracle TP matching (models/utils.py:231-262) + the package's average_precision reproduce the
+    per-class APs of the reference's own evaluate_model (tests/golden/evaluate.npz)."""
+    import os
+    from conftest import GOLDEN
+    from odcp_b200.models.utils import average_precision
+    z = dict(np.load(os.path.join(GOLDEN, "evaluate.npz")))
+    n, ncls = int(z["n"]), int(z["num_cls"])
+    tps, labs, scs = [], [], []
+    for i in range(n):
+        k = int(z["keep_cnt"][i])
+        lo, hi = int(z["gt_off"][i]), int(z["gt_off"][i + 1])
+        tps.append(O.match_detections_np(z["det_bbox"][i, :k], z["det_label"][i, :k], z["gt_boxes"][lo:hi],
+                                         z["gt_labels"][lo:hi], z["levels"]))
+        labs.append(z["det_label"][i, :k])
+        scs.append(z["det_score"][i, :k])
+    tp, lab, sc = np.concatenate(tps), np.concatenate(labs), np.concatenate(scs)
+    for c in range(ncls):
+        ap = average_precision(tp[lab == c], sc[lab == c], int(np.sum(z["gt_labels"] == c)))
+        assert np.array_equal(ap, z["ap"][c]), c
