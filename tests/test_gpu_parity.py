@@ -282,6 +282,54 @@ def test_get_loss_from_boxes_equals_the_dense_signature(cuda_device):
 
 
 # ------------------------------------------------------------------------------------------
+# head-tensor layout (channels_last head conv: permute + reshape become a view)
+# ------------------------------------------------------------------------------------------
+def test_channels_last_head_feeds_the_kernel_without_a_copy(cuda_device):
+    from odcp_b200.models import layout
+    from odcp_b200.models.yolov2 import YOLOv2HeadOps
+
+    class TinyV2(YOLOv2HeadOps, torch.nn.Module):
+        def __init__(self):
+            torch.nn.Module.__init__(self)
+            self.conv = torch.nn.Conv2d(16, 5 * 25, 1)
+            self.cls_list = [str(i) for i in range(20)]
+            self.num_cls = 20
+            self.anchor_box_size_list = list(synthetic.YOLOV2_ANCHORS)
+            self.num_anchor_box = 5
+            self.last = None
+
+        def forward(self, x):  # x: [N,H,W,3] like the reference; features are faked from it
+            feat = self.feat
+            out = self.conv(feat)
+            self.last = out
+            return layout.head_tensor(out, self.num_anchor_box)
+
+    case = synthetic.cfg2(n=4)
+    gt = targets.records_to_tensor(case.rec, cuda_device)
+    off = torch.from_numpy(case.gt_off).to(cuda_device)
+    x = torch.zeros(case.n, case.height, case.width, 3, device=cuda_device)
+    feat = torch.randn(case.n, 16, 13, 13, generator=torch.Generator().manual_seed(9)).to(cuda_device)
+    grads = []
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False  # compare the two layouts in full fp32
+    for fmt in ("contiguous", "channels_last"):
+        torch.manual_seed(3)
+        m = TinyV2().to(cuda_device)
+        m.feat = feat
+        if fmt == "channels_last":
+            layout.use_channels_last_head(m)
+            m.feat = feat.contiguous(memory_format=torch.channels_last)
+        loss = m.get_loss_compact(x, gt, off)
+        y = layout.head_tensor(m.last, 5)
+        assert layout.is_free_view(m.last, y) == (fmt == "channels_last")
+        loss.backward()
+        grads.append((float(loss.item()), m.conv.weight.grad.detach().float().cpu().numpy().copy()))
+    torch.backends.cudnn.allow_tf32 = tf32
+    assert abs(grads[0][0] - grads[1][0]) <= 1e-5 * abs(grads[0][0])
+    assert rel_err(grads[1][1], grads[0][1]) <= 1e-4  # (cuDNN picks different algorithms per layout)
+
+
+# ------------------------------------------------------------------------------------------
 # batched evaluation
 # ------------------------------------------------------------------------------------------
 def test_evaluate_detections_matches_reference_evaluate_model(cuda_device):
