@@ -124,7 +124,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -193,8 +193,30 @@ def nvml_index(local_rank):
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL's version banner, for one) print to stdout; the contract is ONE JSON line there.
+    Everything else goes to stderr: fd 1 is pointed at fd 2 until emit() writes the line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+    else:
+        print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
         return
@@ -426,7 +448,7 @@ def main():
             "clocks": sampler.summary(window), "e2e": e2e, "gpu_launches": 2 * K,
             "roofline": roofline, "cpu_baseline": cpu, "loss": loss_value,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
