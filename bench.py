@@ -180,6 +180,25 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples), "window": window}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank to the CPUs NVML reports as local to its GPU (before any pinned host memory is
+    allocated), so the host side of the e2e path does not cross sockets.  Best effort: silently keeps
+    the current affinity if NVML, the topology or the container's CPU set do not allow it."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(nvml_index(local_rank))
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64 + 8)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        pick = cpus & allowed
+        if pick and pick != allowed:
+            os.sched_setaffinity(0, pick)
+        return sorted(pick) if pick else None
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def nvml_index(local_rank):
     vis = os.environ.get("CUDA_VISIBLE_DEVICES")
     if vis:
@@ -229,6 +248,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    if world > 1:
+        bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
