@@ -10,8 +10,9 @@
 // the kernel is organised around ONE round trip for everything the sparse part needs:
 //   * the flattened batch of grid cells is cut into tiles of a few dozen cells (a multiple of 4
 //     cells, so every tile starts 16-byte aligned; one tile per CTA at the headline size, a
-//     grid-stride loop over tiles for larger tensors; 4 CTAs of 8 streaming warps + 1 record warp
-//     per SM);
+//     grid-stride loop over tiles for larger tensors; 3 CTAs of 8 streaming warps + 1 record warp
+//     per SM: 72 registers, no spills -- a local-memory reload after the dense pass queues behind the
+//     draining gradient stores like any other memory access);
 //   * the record warp's first lane is the TMA producer: one bulk copy brings a speculative window
 //     of ground-truth records (placed where the tile's records sit if boxes are spread evenly over
 //     the images) and goes out FIRST, then the tile itself follows in chunks, each on its own
@@ -21,14 +22,20 @@
 //     stores.  dL/dy is zero everywhere except the objectness channel, whose no-object gradient
 //     depends only on the thread's own float4 (at most one objectness logit falls into any 4
 //     consecutive floats): every byte of y is read once and every byte of dy written once;
-//   * sparse pass (record warp, concurrently): the tile's records are picked from the window in
-//     CSR order; one record at a time, lanes decode the A boxes of the record's cell from shared
+//   * sparse pass (concurrently): the record warp picks the tile's records from the window in CSR
+//     order, asks for a private early copy of their cells (so a record of the tile's last chunk
+//     does not wait for the end of the stream), and publishes the list; the records are dealt to
+//     the warps, one warp per record: lanes decode the A boxes of the record's cell from shared
 //     memory, IoU against the record, redux-argmax picks the responsible predictor, the five
 //     lanes of that predictor finish one channel each, lanes then cover the C classes for the
 //     softmax/class term; the 5+C gradient values wait in a shared-memory patch;
-//   * after a CTA barrier the patches overwrite their rows (dense value + record gradient; in
-//     CSR order, so collisions on one predictor accumulate deterministically);
-//   * the six partial sums go through a last-block-done reduction in a fixed order.
+//   * after a CTA barrier the patches overwrite their rows (dense value + record gradient; if two
+//     records share a cell, in CSR order with read-modify-write, so collisions on one predictor
+//     accumulate deterministically);
+//   * the six sums of a CTA are added onto 64-bit fixed-point accumulators with integer atomics
+//     (exact, order-independent: deterministic) behind one acq_rel ticket; the last ticket holder
+//     writes terms and loss;
+//   * launched as a programmatic dependent: the prologue overlaps the previous kernel's tail.
 #include <limits.h>
 
 #include "yh_common.cuh"
@@ -889,7 +896,7 @@ int train_impl(int version, const float* y, int n, int s_h, int s_w, int a, int 
     p.num_tiles = (int)tiles;
     const int grid = (int)(tiles < slots ? tiles : slots);
 
-    // private cell copies: as many as fit next to 4 CTAs' tiles in the SM's shared memory
+    // private cell copies: as many as fit next to kCtasPerSm CTAs' tiles in the SM's shared memory
     p.total_floats = total_cells * cf;
     p.cell_slot_floats = (cf + 6 + 3) & ~3;
     {
