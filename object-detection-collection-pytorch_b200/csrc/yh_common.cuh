@@ -151,6 +151,10 @@ __device__ __forceinline__ void yh_bulk_load(void* smem_dst, const void* gsrc, u
         "l"(gsrc), "r"(bytes), "r"(yh_smem_u32(bar))
         : "memory");
 }
+// global -> L2 only (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void yh_bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
 // shared -> global, tracked by the thread's bulk async-group
 __device__ __forceinline__ void yh_bulk_store(void* gdst, const void* smem_src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),

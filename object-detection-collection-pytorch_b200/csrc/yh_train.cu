@@ -65,8 +65,10 @@ constexpr int kTileBytesMax = (kCtasPerSm >= 4 ? 40 : (kCtasPerSm == 3 ? 52 : 80
 constexpr int kMaxGrid = 2048;
 constexpr int kClsRegs = 4;               // class logits per lane kept in registers (C <= 128)
 constexpr int kWindow = 128;              // speculative record window (records) per tile
-constexpr int kSlots = 24;                // patches (records processed during the dense pass) per tile
+constexpr int kWindowMax = 256;           // record window buffer: an exact window after a miss may be this long
+constexpr int kSlots = 24;                // patches (records processed during the dense pass) per tile, <= 32
 constexpr int kPatchFloats = 32;          // floats per patch row: 5 + C must fit (else the record waits for the end)
+constexpr int kShadowMax = 12;             // records per tile up to which they are processed during the dense pass
 constexpr int kCellSlots = 12;            // records whose cell gets a private early copy (the others wait for their chunk)
 
 #ifdef YH_X_TRACE
@@ -337,17 +339,19 @@ __device__ __forceinline__ int process_record(const TrainParams& p, const int ve
 template <bool WRITE_DY, bool VEC, int TV, int TA, int TC>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const TrainParams p) {
     extern __shared__ __align__(128) float s_tile[];  // the tile's slice of y
-    __shared__ __align__(16) int4 s_win[3 * kWindow];  // speculative window of ground-truth records
-    __shared__ __align__(8) uint64_t s_bar[kChunks + 2];  // one mbarrier per chunk, + the window's, + the private cell copies'
+    __shared__ __align__(16) int4 s_win[3 * kWindowMax];  // window of ground-truth records (speculative, or exact after a miss)
+    __shared__ __align__(8) uint64_t s_bar[kChunks + 3];  // one mbarrier per chunk, + the window's, + the private cell copies', + the exact window's
     __shared__ float red[kWarps * 6];
-    __shared__ int s_rjj[kWindow];   // the tile's records in CSR order: index into gt ...
-    __shared__ int s_rlc[kWindow];   // ... and tile-local cell
+    __shared__ int s_rjj[kWindowMax];   // the tile's records in CSR order: index into gt ...
+    __shared__ int s_rlc[kWindowMax];   // ... and tile-local cell
+    __shared__ int s_w0;                // first record of the window in s_win
+    __shared__ int s_covered;           // the window holds all records of the tile's images
     __shared__ __align__(16) float s_patch[kSlots * kPatchFloats];  // record gradients waiting for the dense pass
     __shared__ float s_pdense[kSlots];                            // dense objectness value of a patched row
     __shared__ int s_pr[kSlots];                                  // responsible anchor of a patch
     __shared__ int s_nrec, s_npatch;  // records listed (-1: list incomplete, scan gt instead) / patched
     __shared__ int s_ncell;           // records of the list with a private cell copy
-    __shared__ int s_collide;         // two patched records share a cell: patches must be applied in order
+    __shared__ int s_collide;         // bit i: patch i shares its cell with another patch (applied in order)
     __shared__ int s_ready;           // tile index + 1 once the record list of that tile is published
 
     const YhGeom& g = p.g;
@@ -365,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
     XT(0);
     if (tid == kDense) {
 #pragma unroll
-        for (int c = 0; c <= kChunks + 1; ++c) yh_mbar_init(&s_bar[c], 1);
+        for (int c = 0; c <= kChunks + 2; ++c) yh_mbar_init(&s_bar[c], 1);
         yh_mbar_fence_init();
         s_ready = 0;
     }
@@ -383,6 +387,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
     // records can be processed during the dense pass when their 5+C gradients fit a patch row
     const bool patchable = WRITE_DY && 5 + C <= kPatchFloats;
     uint32_t phase = 0;  // parity of the mbarriers: every barrier completes once per tile
+    int pre0 = -1, pre1 = -1;  // record warp: exact record range of this CTA's next tile, once known
 
     // ---- the six partial sums of the CTA -> global totals -> (last CTA) terms and loss.
     // Every lane carries partial sums (dense rows; record channels by lane role): the warps fold
@@ -454,10 +459,22 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
         const int n_hi = (c0 + nc - 1) / cells;
         const int ch4 = (nf4 + kChunks - 1) / kChunks;     // float4s per chunk
 
-        // speculative record window of this tile
+        // record window of this tile: speculative for a CTA's first tile; for its later tiles the exact
+        // record range was read while the previous tile was being processed (multi-tile launches)
         int w0 = (int)(p.rec_per_cell * (float)(c0 + (nc >> 1))) - (kWindow >> 1);
         w0 = max(0, min(w0, p.m_local - kWindow));
-        const int wn = min(kWindow, p.m_local - w0);
+        int wn = min(kWindow, p.m_local - w0);
+        if (pre0 >= 0 && pre1 - pre0 <= kWindowMax) {
+            w0 = pre0;
+            wn = pre1 - pre0;
+        }
+        pre0 = -1;
+        if (record_warp && t + (int)gridDim.x < p.num_tiles) {  // (loads that nobody waits for during this tile)
+            const int c0n = (t + (int)gridDim.x) * R;
+            const int ncn = min(R, p.total_cells - c0n);
+            pre0 = __ldg(p.gt_off + c0n / cells);
+            pre1 = min(__ldg(p.gt_off + (c0n + ncn - 1) / cells + 1), p.m_local);
+        }
 
         auto issue_chunk = [&](int c) {  // one thread: chunk c of the tile -> shared memory
             const int lo = c * ch4, n4 = min(ch4, nf4 - lo);
@@ -480,6 +497,15 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
             }
 #pragma unroll
             for (int c = 0; c < kChunks && c < kAhead; ++c) issue_chunk(c);
+            // multi-tile launches: the stage is single-buffered, so the next tile's loads can only
+            // start once this tile is done; pulling the next tile into L2 now keeps DRAM busy through
+            // this tile's tail and turns that later round trip into an L2 hit
+            const int tn_ = t + (int)gridDim.x;
+            if (VEC && tn_ < p.num_tiles) {
+                const int c0n = tn_ * R;
+                const int nfn = (min(R, p.total_cells - c0n) * cf) & ~3;
+                if (nfn > 0) yh_bulk_prefetch_l2(p.y + (size_t)c0n * cf, (uint32_t)nfn * 4u);
+            }
         }
 
         // CSR offsets of the tile's images (every warp: the dense pass needs the box counts)
@@ -523,16 +549,18 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
         // lies in chunks <= c.  Returns false if the record warp has not published the list yet.
         float* s_cell = s_tile + (((size_t)R * cf + 3) & ~(size_t)3) + 4;  // private cell copies, after the tile
         unsigned rec_done = 0u;
-        int my_npatch = -1, my_ncell = 0;
+        int my_npatch = -1, my_ncell = 0, my_w0 = 0;
         bool cells_in = false;
         auto try_records = [&](int upto_chunk, bool block) -> bool {
             if (warp == 0) return true;
             if (my_npatch < 0) {
                 if (*reinterpret_cast<volatile int*>(&s_ready) != t + 1) return false;
                 __threadfence_block();
-                yh_mbar_wait(&s_bar[kChunks], phase);  // (complete by now: makes the window visible to this warp)
+                yh_mbar_wait(&s_bar[kChunks], phase);      // (both complete by now: they make the window,
+                yh_mbar_wait(&s_bar[kChunks + 2], phase);  //  speculative or exact, visible to this warp)
                 my_npatch = s_npatch;
                 my_ncell = s_ncell;
+                my_w0 = s_w0;
             }
             if (!cells_in && my_ncell > 0) {
                 if (block) { yh_mbar_wait(&s_bar[kChunks + 1], phase); cells_in = true; }
@@ -551,7 +579,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
                     ycell = s_tile + lcell * cf;
                 }
                 rec_done |= 1u << k;
-                const int4* rp = s_win + 3 * (jj - w0);
+                const int4* rp = s_win + 3 * (jj - my_w0);
                 RecordRegs rr;
                 rr.hd = rp[0];
                 rr.tt = *reinterpret_cast<const float4*>(rp + 1);
@@ -646,16 +674,33 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
                 const unsigned bal = __ballot_sync(0xffffffffu, lc >= 0);
                 if (lc >= 0) {
                     const int idx = n + __popc(bal & ((1u << lane) - 1u));
-                    if (idx < kWindow) { s_rjj[idx] = jj; s_rlc[idx] = lc; }
+                    if (idx < kWindowMax) { s_rjj[idx] = jj; s_rlc[idx] = lc; }
                 }
                 n += __popc(bal);
             };
-            const bool covered = rec0 >= w0 && rec1 <= w0 + wn;  // the window has them all
+            bool covered = rec0 >= w0 && rec1 <= w0 + wn;  // the window has them all
             yh_mbar_wait(&s_bar[kChunks], phase);  // (always: the barrier's phase must be consumed)
+            int wbase = w0;
+            // The guess missed (box counts far from uniform): one more round trip fetches the exact
+            // window -- the offsets are known now -- instead of sending the tile's records down the
+            // slow path after the dense pass.  (The barrier flips once per tile either way.)
+            if (!covered && rec1 - rec0 <= kWindowMax && rec1 > rec0) {
+                if (lane == 0) {
+                    yh_fence_proxy_async();
+                    yh_mbar_expect_tx(&s_bar[kChunks + 2], (uint32_t)(rec1 - rec0) * 48u);
+                    yh_bulk_load(s_win, p.gt + rec0, (uint32_t)(rec1 - rec0) * 48u, &s_bar[kChunks + 2]);
+                }
+                yh_mbar_wait(&s_bar[kChunks + 2], phase);
+                wbase = rec0;
+                covered = true;
+            } else if (lane == 0) {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(yh_smem_u32(&s_bar[kChunks + 2])) : "memory");
+            }
+            if (lane == 0) { s_w0 = wbase; s_covered = covered ? 1 : 0; }
             if (covered) {
                 for (int base = rec0; base < rec1; base += 32) {
                     const int jj = base + lane;
-                    append(jj, jj < rec1 ? local_cell(s_win[3 * (jj - w0)]) : -1);
+                    append(jj, jj < rec1 ? local_cell(s_win[3 * (jj - wbase)]) : -1);
                 }
             } else {
                 for (int base = rec0; base < rec1; base += 32) {
@@ -665,8 +710,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
             }
             __syncwarp();
             XT(5);  // record warp: list built
-            const bool complete = n <= kWindow;
-            const int n_patch = (patchable && complete && covered) ? min(n, kSlots) : 0;
+            const bool complete = n <= kWindowMax;
+            // Tiles dense with records (BASELINE config 5: ~17 per tile) gain nothing from hiding them behind
+            // the stream -- the streaming warps would spend more time on records than on the stream -- so
+            // beyond kShadowMax records they are all processed after the dense pass, by all warps at once.
+            const int n_patch = (patchable && complete && covered && n <= kShadowMax) ? min(n, kSlots) : 0;
             // Private early copies of the first records' cells: the tile's last chunk lands when the
             // stream ends, and a record found in it would add its ~1.4 us to the CTA's critical path;
             // a 16-byte aligned bulk copy of just the cell, asked for now, is back long before that.
@@ -695,12 +743,13 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
             __threadfence_block();
             if (lane == 0) *reinterpret_cast<volatile int*>(&s_ready) = t + 1;  // publish the list
             __syncwarp();
-            {   // do two patched records share a cell?  (then the patches are applied one by one, in order)
-                bool dup = false;
+            {   // which patched records share their cell with another one?  Those patches are applied one by
+                // one, in order, by this warp; all others by the warps that produced them
+                bool shared_cell = false;
                 if (lane < n_patch)
-                    for (int j = 0; j < lane; ++j) dup = dup || s_rlc[j] == s_rlc[lane];
-                const bool any = __any_sync(0xffffffffu, dup);
-                if (lane == 0) s_collide = any ? 1 : 0;
+                    for (int j = 0; j < n_patch; ++j) shared_cell = shared_cell || (j != lane && s_rlc[j] == s_rlc[lane]);
+                const unsigned bal = __ballot_sync(0xffffffffu, shared_cell);
+                if (lane == 0) s_collide = (int)bal;  // bit i: patch i shares its cell  (kSlots <= 32)
             }
             for (int c = 0; c < kChunks; ++c) {  // this warp's share, as copies and chunks land
                 try_records(c - 1, false);
@@ -720,10 +769,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
         // (no records left over: the sums folded before the barrier are final and get published
         //  right after the patch stores, without another CTA barrier)
         if (last_tile && !(nrec < 0 || nrec > npatch)) sums_final = true;
-        if (!s_collide) {
+        {
+            const unsigned shared_mask = (unsigned)s_collide;
             // every warp applies the patches it produced: a plain overwrite of the 5+C floats of the row
             // (the dense pass' values there are zero but the objectness channel, kept in s_pdense)
             for (int i = warp - 1; i < npatch && warp > 0; i += kWarps - 1) {
+                if ((shared_mask >> i) & 1u) continue;
                 const int lcell = s_rlc[i], r = s_pr[i];
                 if (lane < 5 + C) {
                     float* addr = dt + lcell * cf + (version == 2 ? r * bs + lane : (lane < 5 ? r * 5 + lane : 5 * A + lane - 5));
@@ -732,21 +783,22 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
                     *addr = val;
                 }
             }
-        } else if (record_warp) {
-            for (int i = 0; i < npatch; ++i) {
-                const int lcell = s_rlc[i], r = s_pr[i];
-                // an earlier record of this cell already updated it: read the row back.  Otherwise the
-                // row holds the dense pass' values, known without a load (zero but the objectness channel)
-                bool again = false;
-                for (int j0 = 0; j0 < i; j0 += 32) again = again || __any_sync(0xffffffffu, j0 + lane < i && s_rlc[j0 + lane] == lcell);
-                if (lane < 5 + C) {
-                    float* addr = dt + lcell * cf + (version == 2 ? r * bs + lane : (lane < 5 ? r * 5 + lane : 5 * A + lane - 5));
-                    float val = s_patch[i * kPatchFloats + lane];
-                    if (again) val = __fadd_rn(*addr, val);
-                    else if (lane == 4) val = __fadd_rn(s_pdense[i], val);
-                    *addr = val;
+            // patches of cells that carry several records: in CSR order by one warp; the first one of a
+            // cell overwrites, the later ones read the row back
+            if (record_warp) {
+                for (unsigned todo = shared_mask; todo; todo &= todo - 1u) {
+                    const int i = __ffs(todo) - 1;
+                    const int lcell = s_rlc[i], r = s_pr[i];
+                    const bool again = __any_sync(0xffffffffu, lane < i && s_rlc[lane] == lcell);
+                    if (lane < 5 + C) {
+                        float* addr = dt + lcell * cf + (version == 2 ? r * bs + lane : (lane < 5 ? r * 5 + lane : 5 * A + lane - 5));
+                        float val = s_patch[i * kPatchFloats + lane];
+                        if (again) val = __fadd_rn(*addr, val);
+                        else if (lane == 4) val = __fadd_rn(s_pdense[i], val);
+                        *addr = val;
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
         if (nrec < 0 || nrec > npatch) {
@@ -755,6 +807,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
             // records of one cell stay on one warp in CSR order; read-modify-write on top of dense
             // values and patches.  The tile is still in shared memory.
             if (npatch > 0) __syncthreads();
+            const bool in_window = s_covered != 0;  // the listed records sit in s_win, from s_w0 on
+            const int win0 = s_w0;
+            if (in_window) {
+                yh_mbar_wait(&s_bar[kChunks], phase);      // (both complete: make the window visible
+                yh_mbar_wait(&s_bar[kChunks + 2], phase);  //  to every warp)
+            }
             const int rec0 = o0;
             const int lim = nrec >= 0 ? nrec : min(__ldg(p.gt_off + n_hi + 1), p.m_local);
             for (int base = nrec >= 0 ? npatch : rec0; base < lim; base += 32) {
@@ -770,11 +828,18 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
                     bal &= bal - 1;
                     const int j = __shfl_sync(0xffffffffu, jj, b);
                     const int lcell = __shfl_sync(0xffffffffu, lc, b);
-                    const int4* rp = reinterpret_cast<const int4*>(p.gt + j);
                     RecordRegs rr;
-                    rr.hd = __ldg(rp);
-                    rr.tt = __ldg(reinterpret_cast<const float4*>(rp + 1));
-                    rr.bb = __ldg(reinterpret_cast<const float4*>(rp + 2));
+                    if (nrec >= 0 && in_window) {  // the record window in shared memory has it
+                        const int4* rp = s_win + 3 * (j - win0);
+                        rr.hd = rp[0];
+                        rr.tt = *reinterpret_cast<const float4*>(rp + 1);
+                        rr.bb = *reinterpret_cast<const float4*>(rp + 2);
+                    } else {
+                        const int4* rp = reinterpret_cast<const int4*>(p.gt + j);
+                        rr.hd = __ldg(rp);
+                        rr.tt = __ldg(reinterpret_cast<const float4*>(rp + 1));
+                        rr.bb = __ldg(reinterpret_cast<const float4*>(rp + 2));
+                    }
                     process_record<WRITE_DY ? 1 : 0>(p, version, A, C, rr, j, s_tile + lcell * cf, dt + lcell * cf, nullptr,
                                                      nullptr, kn_of(lcell * cf), lane, my_pw, my_ph, sums);
                 }
@@ -900,7 +965,7 @@ int train_impl(int version, const float* y, int n, int s_h, int s_w, int a, int 
     p.total_floats = total_cells * cf;
     p.cell_slot_floats = (cf + 6 + 3) & ~3;
     {
-        const long long per_cta = (224ll * 1024) / kCtasPerSm - 1024 - 12 * 1024;  // minus reserve and static arrays
+        const long long per_cta = (227ll * 1024) / kCtasPerSm - 1024 - 18 * 1024;  // minus reserve and static arrays
         const long long left = per_cta - ((long long)p.tile_cells * cf * 4 + 32);
         long long slots = left > 0 ? left / (p.cell_slot_floats * 4ll) : 0;
         p.cell_slots = (int)(slots < kCellSlots ? slots : kCellSlots);
