@@ -190,13 +190,15 @@ struct RecordRegs {
 // floats of dy (global memory; holds the dense pass' values, visible after the CTA barrier);
 // `kn` is the box count of the cell's image; `my_pw/my_ph` are the anchor multipliers of this
 // lane's anchor (lane / 5).  Requires 5A <= 32.
-// MODE 0: loss only; 1: add the gradient onto dy in global memory (read-modify-write of the row
-// the dense pass wrote); 2: leave the gradient in the shared-memory patch row `patch` (+ the dense
-// objectness value of the row in *pdense), to be applied after the dense pass.
+// MODE 0: loss only; 1: add the gradient onto dy in global memory (`again`: an earlier record
+// already updated this cell, so the row is read back; otherwise it holds the dense pass' values,
+// which are known without a load: zero but the objectness channel); 2: leave the gradient in the
+// shared-memory patch row `patch` (+ the dense objectness value of the row in *pdense), to be
+// applied after the dense pass.
 template <int MODE>
 __device__ __forceinline__ int process_record(const TrainParams& p, const int version, const int A, const int C,
                                               const RecordRegs& rr, int jj, const float* ycell,
-                                              float* dcell, float* patch, float* pdense, float kn,
+                                              float* dcell, bool again, float* patch, float* pdense, float kn,
                                               int lane, float my_pw, float my_ph, WarpSums& s) {
     const YhGeom& g = p.g;
     const int bs = version == 2 ? 5 + C : 5;
@@ -236,13 +238,21 @@ __device__ __forceinline__ int process_record(const TrainParams& p, const int ve
     float* dcl = dcell + coff;
     const bool resp_lane = mine && a == r;
     float old_ch = 0.f;
-    if (MODE == 1 && resp_lane) old_ch = dcell[r * bs + q];
+    if (MODE == 1 && resp_lane) {
+        if (again) {
+            old_ch = dcell[r * bs + q];
+        } else if (q == 4) {  // what the dense pass wrote for this logit (same helper, same bits)
+            float cf_;
+            const float w = noobj_term(t_raw, kn, &cf_);
+            old_ch = noobj_grad(w, cf_, p.cno);
+        }
+    }
     float lg[kClsRegs], oldc[kClsRegs];
 #pragma unroll
     for (int k = 0; k < kClsRegs; ++k) {
         const int c = lane + 32 * k;
         lg[k] = c < C ? cl[c] : -INFINITY;
-        oldc[k] = (MODE == 1 && c < C) ? dcl[c] : 0.f;
+        oldc[k] = (MODE == 1 && again && c < C) ? dcl[c] : 0.f;
     }
     const float iou_r = __shfl_sync(0xffffffffu, iou, 5 * r);
 
@@ -322,7 +332,7 @@ __device__ __forceinline__ int process_record(const TrainParams& p, const int ve
         }
         for (int c = lane + 32 * kClsRegs; c < C; c += 32) {
             const float pc = expf(cl[c] - mx) * inv;
-            dcl[c] = __fadd_rn(dcl[c], p.ccls * pc * (pc - (c == hd.w ? 1.f : 0.f) - dot));
+            dcl[c] = __fadd_rn(again ? dcl[c] : 0.f, p.ccls * pc * (pc - (c == hd.w ? 1.f : 0.f) - dot));
         }
     }
     if (MODE == 2 && lane < C) {  // 5 + C <= kPatchFloats: one class per lane
@@ -587,7 +597,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
 #ifdef YH_X_TRACE
                 const long long rc0 = clock64();
 #endif
-                const int r = process_record<2>(p, version, A, C, rr, jj, ycell, nullptr,
+                const int r = process_record<2>(p, version, A, C, rr, jj, ycell, nullptr, false,
                                                 s_patch + i * kPatchFloats, s_pdense + i, kn_of(lcell * cf), lane,
                                                 my_pw, my_ph, sums);
                 if (lane == 0) s_pr[i] = r;
@@ -807,6 +817,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
             // records of one cell stay on one warp in CSR order; read-modify-write on top of dense
             // values and patches.  The tile is still in shared memory.
             if (npatch > 0) __syncthreads();
+            const bool track = npatch == 0 && R <= 32 * kWarps;  // cells this warp has updated fit one mask
+            unsigned seen = 0u;
             const bool in_window = s_covered != 0;  // the listed records sit in s_win, from s_w0 on
             const int win0 = s_w0;
             if (in_window) {
@@ -840,8 +852,13 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
                         rr.tt = __ldg(reinterpret_cast<const float4*>(rp + 1));
                         rr.bb = __ldg(reinterpret_cast<const float4*>(rp + 2));
                     }
-                    process_record<WRITE_DY ? 1 : 0>(p, version, A, C, rr, j, s_tile + lcell * cf, dt + lcell * cf, nullptr,
-                                                     nullptr, kn_of(lcell * cf), lane, my_pw, my_ph, sums);
+                    // first record of this cell on this warp (records are dealt by cell): its row still
+                    // holds the dense pass' values -- unless patches were applied before
+                    const unsigned bit = 1u << ((lcell / kWarps) & 31);
+                    const bool again = !track || (seen & bit);
+                    seen |= bit;
+                    process_record<WRITE_DY ? 1 : 0>(p, version, A, C, rr, j, s_tile + lcell * cf, dt + lcell * cf, again,
+                                                     nullptr, nullptr, kn_of(lcell * cf), lane, my_pw, my_ph, sums);
                 }
             }
         }
