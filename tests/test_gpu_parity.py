@@ -624,3 +624,42 @@ def test_postprocess_tail_and_unaligned_sources(cuda_device):
         k = base["keep_cnt"][n]
         assert np.array_equal(r["keep_idx"][n, :k].cpu().numpy(), base["keep_idx"][n, :k])
         assert np.array_equal(r["score"][n, :k].cpu().numpy(), base["score"][n, :k])
+
+
+# ------------------------------------------------------------------------------------------
+# host-buffer pipeline
+# ------------------------------------------------------------------------------------------
+def test_host_pipeline_returns_what_the_direct_calls_return(cuda_device):
+    """HostHeadPipeline (pinned host buffers in, host buffers out, four streams, packed transfers)
+    against the same two calls made directly on device tensors, over more submits than slots."""
+    from odcp_b200.host import HostHeadPipeline
+    lam = synthetic.DEFAULT_LAMBDAS
+    cases = [synthetic.make_case("p%d" % i, 2, 16, 13, 13, 5, 20, 416, 416, seed=900 + i, to_shift=-1.5) for i in range(5)]
+    max_boxes = max(c.m for c in cases)
+    pipe = HostHeadPipeline(16, 13, 13, 5, 20, img_hw=(416, 416), anchors=cases[0].anchors, lambdas=lam, conf_thre=0.5,
+                            iou_thre=0.45, max_out=64, max_boxes=max_boxes, depth=3, device=cuda_device)
+    tickets = []
+    results = []
+    for i, case in enumerate(cases):
+        if i >= pipe.depth:
+            r = pipe.result(tickets[i - pipe.depth])
+            results.append({k: (v.clone() if v is not None else None) for k, v in r.items()})
+        tickets.append(pipe.submit(case.y, targets.records_to_tensor(case.rec), torch.from_numpy(case.gt_off)))
+    for tk in tickets[len(results):]:
+        r = pipe.result(tk)
+        results.append({k: (v.clone() if v is not None else None) for k, v in r.items()})
+    for case, got in zip(cases, results):
+        kw = dict(version=2, img_hw=(416, 416), anchors=case.anchors)
+        y = case.y.to(cuda_device)
+        want = ops.train_head(y, targets.records_to_tensor(case.rec, cuda_device), torch.from_numpy(case.gt_off).to(cuda_device),
+                              lambdas=lam, **kw)
+        post = ops.postprocess(y, conf_thre=0.5, iou_thre=0.45, max_out=64, want_cls_spec=False, **kw)
+        torch.cuda.synchronize()
+        assert float(got["loss"]) == float(want["loss"].item())
+        assert torch.equal(got["dy"], want["dy"].cpu())
+        assert torch.equal(got["terms"], want["terms"].cpu())
+        cnt = post["keep_cnt"].cpu()
+        assert torch.equal(got["keep_cnt"], cnt)
+        mask = torch.arange(64)[None, :] < cnt.clamp(max=64)[:, None]
+        for k in ("keep_idx", "bbox", "conf", "label", "score"):
+            assert torch.equal(got[k][mask], post[k].cpu()[mask]), k
