@@ -50,9 +50,10 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=32, help="images in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--serial", action="store_true",
-                    help="launch post-process after the train head on one stream (default: two streams, "
-                         "the two calls of a step are independent and become parallel graph branches)")
+    ap.add_argument("--two-streams", action="store_true",
+                    help="issue the post-process of a step on a second stream (fork/join inside the step). "
+                         "Default: one stream; the post-process is launched as a programmatic dependent with "
+                         "YH_POST_INPUT_READY, so it already overlaps the train head's tail")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 200)")
     return ap.parse_args()
 
@@ -67,7 +68,8 @@ def workload_config(batch, sets=None, serial=False):
     if sets is not None:
         cfg["l2"] = "%d rotating input/output buffer sets per GPU (inputs+outputs %.0f MB > 126 MB L2)" % (
             sets, sets * 2 * batch * 84500 / 1e6)
-        cfg["streams"] = "train head and post-process of a step on one stream" if serial else \
+        cfg["streams"] = "train head and post-process of a step on one stream, programmatic dependent launches " \
+            "(post-process with YH_POST_INPUT_READY: it overlaps the train head's tail)" if serial else \
             "train head and post-process of a step on two streams (parallel graph branches), steps in order"
     return cfg
 
@@ -281,14 +283,16 @@ def main():
     fork_ev = [torch.cuda.Event() for _ in range(2)]
 
     def run_post(s):
+        # input_ready: the kernel in front of this one on its stream (the train head, or the previous
+        # step's post-process) only READS the head tensors, so this call may start on y while that
+        # kernel is still draining (YH_POST_INPUT_READY); it still completes after it
         s["post"] = ops.postprocess(s["y"], conf_thre=CONF_THRE, iou_thre=IOU_THRE, max_out=MAX_OUT,
-                                    want_cls_spec=False, out=s.get("post"), **kw)
+                                    want_cls_spec=False, out=s.get("post"), input_ready=True, **kw)
 
     def step(s, post=True, train=True):
-        """One step = one train-head call + one post-process call on the same head tensor.  The two
-        calls are independent, so unless --serial they go to two streams (fork/join inside the step:
-        parallel branches of the captured graph); consecutive steps stay ordered."""
-        both = post and train and not args.serial
+        """One step = one train-head call + one post-process call on the same head tensor, in stream
+        order (with --two-streams: fork/join inside the step, parallel branches of the captured graph)."""
+        both = post and train and args.two_streams
         if both:
             fork_ev[0].record(stream)
             side.wait_event(fork_ev[0])
@@ -465,7 +469,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(B, R, args.serial),
+            "dtype": "f32", "data": "synthetic", "config": workload_config(B, R, not args.two_streams),
             "clocks": sampler.summary(window), "e2e": e2e, "gpu_launches": 2 * K,
             "roofline": roofline, "cpu_baseline": cpu, "loss": loss_value,
         }

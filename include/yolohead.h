@@ -52,6 +52,9 @@ extern "C" {
 #define YH_ERR_CUDA (-4)      /* a CUDA runtime call or the launch failed                   */
 #define YH_ERR_UNSUPPORTED (-5)
 
+#define YH_POST_CLASS_AWARE 1
+#define YH_POST_INPUT_READY 2
+
 /* One ground-truth box.  The 12 scalars `collate_fn` scatters into its dense per-box grids
  * (reference models/yolov2.py:1466-1499, models/yolov1.py:1264-1299).  tw/th hold `bwbh`
  * (box size in grid units) for v2 and `sig_twth` (box size / S) for v1. */
@@ -144,8 +147,12 @@ YH_API int yh_build_targets(const double* boxes_xyxy, const int32_t* labels, con
  * descending-confidence greedy NMS per image + class pick.
  * Replaces the predict -> nms -> argmax chain of detect() (reference models/yolov2.py:694-731,
  * models/yolov1.py:491-534) with models/utils.py:68-164 nms applied PER IMAGE.
- *   class_aware = 0 reproduces the reference (class-agnostic); 1 only lets boxes with the same
- *   argmax class suppress each other.
+ *   flags: bit 0 (YH_POST_CLASS_AWARE) 0 reproduces the reference (class-agnostic), 1 only lets
+ *   boxes with the same argmax class suppress each other; bit 1 (YH_POST_INPUT_READY) is a promise
+ *   by the caller that y was NOT written by the kernel launched immediately before this call on
+ *   `stream` (typically that kernel is the train head, which only reads y): the kernel then starts
+ *   on y while that kernel is still draining and only waits for it before it exits, so stream order
+ *   is kept for everything launched afterwards.
  *   Outputs per image, first keep_cnt[n] (<= max_out) entries valid, in descending confidence:
  *   keep_idx[N,max_out] predictor index; out_bbox[N,max_out,4]; out_conf[N,max_out];
  *   out_cls_spec[N,max_out,C] (may be NULL); out_label[N,max_out]; out_score[N,max_out].
@@ -155,13 +162,13 @@ YH_API int yh_build_targets(const double* boxes_xyxy, const int32_t* labels, con
 YH_API size_t yh_postprocess_workspace_bytes(int n, int preds_per_image);
 YH_API int yh_v2_postprocess(const float* y, int n, int s_h, int s_w, int a, int c,
                       const float* anchors_wh_host, float img_h, float img_w,
-                      float conf_thre, float iou_thre, int class_aware, int max_out,
+                      float conf_thre, float iou_thre, int flags, int max_out,
                       int32_t* keep_idx, int32_t* keep_cnt, float* out_bbox, float* out_conf,
                       float* out_cls_spec, int32_t* out_label, float* out_score,
                       void* ws, size_t ws_bytes, void* stream);
 YH_API int yh_v1_postprocess(const float* y, int n, int s_h, int s_w, int b, int c,
                       float img_h, float img_w,
-                      float conf_thre, float iou_thre, int class_aware, int max_out,
+                      float conf_thre, float iou_thre, int flags, int max_out,
                       int32_t* keep_idx, int32_t* keep_cnt, float* out_bbox, float* out_conf,
                       float* out_cls_spec, int32_t* out_label, float* out_score,
                       void* ws, size_t ws_bytes, void* stream);

@@ -84,6 +84,7 @@ struct NmsParams {
     float conf_thre, iou_thre;
     float to_reject;         // objectness logits below this can never reach conf_thre
     int class_aware, max_out;
+    int late_wait;           // YH_POST_INPUT_READY: wait for the previous kernel at the end, not at the start
     int32_t* keep_idx;
     int32_t* keep_cnt;
     float4* out_bbox;
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
     }
     // (programmatic dependent launch: the prologue above overlaps the previous kernel's tail; global
     // memory is only touched once that kernel has completed)
-    yh_grid_dependency_wait();
+    if (!p.late_wait) yh_grid_dependency_wait();
     yh_grid_launch_dependents();
     __syncthreads();
 
@@ -612,6 +613,9 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
     if (!overflow && K <= p.stage_slots && !with_labels) rest(FastTag<true>{}, FastTag<false>{});
     else if (!overflow && K <= p.stage_slots) rest(FastTag<true>{}, FastTag<true>{});
     else rest(FastTag<false>{}, FastTag<true>{});
+    // (YH_POST_INPUT_READY) everything above ran next to the tail of the previous kernel of the stream;
+    // this kernel must not complete before that one has, or work launched after it could overtake it
+    if (p.late_wait) yh_grid_dependency_wait();
 }
 
 template <int TV, int TA, int TC>
@@ -675,7 +679,8 @@ int postprocess_impl(int version, const float* y, int n, int s_h, int s_w, int a
         const double t = conf_thre < 0.9999999 ? log((double)conf_thre / (1.0 - (double)conf_thre)) : 16.0;
         p.to_reject = (float)((t < 16.0 ? t : 16.0) - 0.01);
     }
-    p.class_aware = class_aware; p.max_out = max_out;
+    p.class_aware = (class_aware & YH_POST_CLASS_AWARE) != 0; p.max_out = max_out;
+    p.late_wait = (class_aware & YH_POST_INPUT_READY) != 0;
     p.keep_idx = keep_idx; p.keep_cnt = keep_cnt;
     p.out_bbox = reinterpret_cast<float4*>(out_bbox);
     p.out_conf = out_conf; p.out_cls_spec = out_cls_spec; p.out_label = out_label; p.out_score = out_score;

@@ -124,7 +124,7 @@ class HostHeadPipeline:
                                         conf_thre=self.conf_thre, iou_thre=self.iou_thre,
                                         anchors=self.anchors, boxes_per_cell=self.a,
                                         class_aware=self.class_aware, max_out=self.max_out,
-                                        want_cls_spec=False, out=s["post"])
+                                        want_cls_spec=False, out=s["post"], input_ready=True)
             s["ev_post"].record(self.s_post)
         with torch.cuda.stream(self.s_run):
             self.s_run.wait_event(s["ev_in"])

@@ -202,12 +202,14 @@ def build_targets(boxes_xyxy, labels, img_index, *, num_images, version, img_hw,
 
 
 def postprocess(y, *, version, img_hw, conf_thre, iou_thre, anchors=None, boxes_per_cell=None,
-                class_aware=False, max_out=None, want_cls_spec=True, out=None):
+                class_aware=False, max_out=None, want_cls_spec=True, out=None, input_ready=False):
     """Decode + threshold + per-image greedy NMS + class pick -- yh_v{1,2}_postprocess.
 
     Returns dict(keep_idx [N,max_out] int32, keep_cnt [N] int32, bbox, conf, cls_spec, label, score).
     `out` may be a dict returned by an earlier call with the same shapes: its tensors are reused
-    (no allocation, e.g. inside a pipeline or a CUDA graph).
+    (no allocation, e.g. inside a pipeline or a CUDA graph).  `input_ready=True` promises that y was
+    not written by the kernel launched just before this call on the current stream (e.g. it is the
+    train head, which only reads y): the kernel then overlaps that kernel's tail (YH_POST_INPUT_READY).
     """
     y = _require_cuda_f32(y, "y")
     n, s_h, s_w, a, c = head_shape(y, version, boxes_per_cell)
@@ -233,12 +235,12 @@ def postprocess(y, *, version, img_hw, conf_thre, iou_thre, anchors=None, boxes_
         if version == 2:
             _lib.call("yh_v2_postprocess", _ptr(y), n, s_h, s_w, a, c, _anchors_host(anchors),
                       float(img_hw[0]), float(img_hw[1]), float(conf_thre), float(iou_thre),
-                      int(bool(class_aware)), max_out, _ptr(keep_idx), _ptr(keep_cnt), _ptr(bbox),
+                      int(bool(class_aware)) | (2 if input_ready else 0), max_out, _ptr(keep_idx), _ptr(keep_cnt), _ptr(bbox),
                       _ptr(conf), _ptr(spec), _ptr(label), _ptr(score), _ptr(ws), ws.numel(), _stream())
         else:
             _lib.call("yh_v1_postprocess", _ptr(y), n, s_h, s_w, a, c,
                       float(img_hw[0]), float(img_hw[1]), float(conf_thre), float(iou_thre),
-                      int(bool(class_aware)), max_out, _ptr(keep_idx), _ptr(keep_cnt), _ptr(bbox),
+                      int(bool(class_aware)) | (2 if input_ready else 0), max_out, _ptr(keep_idx), _ptr(keep_cnt), _ptr(bbox),
                       _ptr(conf), _ptr(spec), _ptr(label), _ptr(score), _ptr(ws), ws.numel(), _stream())
     return dict(keep_idx=keep_idx, keep_cnt=keep_cnt, bbox=bbox, conf=conf, cls_spec=spec,
                 label=label, score=score, _ws=ws)

@@ -17,7 +17,7 @@ for name, case, reps in (("headline", synthetic.headline(), 300), ("cfg2+collisi
     bad = 0
     for i in range(reps):
         r = ops.train_head(y, gt, off, lambdas=lam, want_resp=True, **kw)
-        p = ops.postprocess(y, conf_thre=0.5, iou_thre=0.45, max_out=128, **kw)
+        p = ops.postprocess(y, conf_thre=0.5, iou_thre=0.45, max_out=128, input_ready=True, **kw)
         cur = [r["loss"].clone(), r["terms"].clone(), r["dy"].clone(), r["resp"].clone(), p["keep_cnt"].clone(), p["keep_idx"].clone(),
                p["label"].clone(), p["score"].clone(), p["bbox"].clone()]
         if ref is None:

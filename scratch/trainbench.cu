@@ -47,6 +47,7 @@ int main(int argc, char** argv) {
     const float anchors[10] = {1.3221f, 1.73145f, 3.19275f, 4.00944f, 5.05587f, 8.09892f, 9.47112f, 4.84053f, 11.2364f, 10.0071f};
     const float lam[5] = {5, 5, 1, .5f, 1};
     const int MAXO = 128;
+    int post_flags = 0;
 
     struct Set { float *y, *dy, *terms, *loss, *obox, *oconf, *oscore; YhGt* gt; int *off, *kidx, *kcnt, *olab; void *ws, *pws; };
     std::vector<Set> sets(R);
@@ -91,13 +92,16 @@ int main(int argc, char** argv) {
                            s.ws, yh_train_workspace_bytes(), st);
     };
     auto post = [&](Set& s) {
-        return yh_v2_postprocess(s.y, N, S, S, A, C, anchors, 416.f, 416.f, 0.5f, 0.45f, 0, MAXO, s.kidx, s.kcnt, s.obox, s.oconf,
+        return yh_v2_postprocess(s.y, N, S, S, A, C, anchors, 416.f, 416.f, 0.5f, 0.45f, post_flags, MAXO, s.kidx, s.kcnt, s.obox, s.oconf,
                                  nullptr, s.olab, s.oscore, s.pws, pws_bytes, st);
     };
     const double tb = 2.0 * floats * 4 + 48.0 * M;
     run("train", tb, train);
     run("post", 1.0 * floats * 4, post);
     run("train+post", tb + floats * 4, [&](Set& s) { int rc = train(s); return rc ? rc : post(s); });
+    post_flags = YH_POST_INPUT_READY;
+    run("train+post (input ready)", tb + floats * 4, [&](Set& s) { int rc = train(s); return rc ? rc : post(s); });
+    post_flags = 0;
 #ifdef YH_X_TRACE
     {
         CK(cudaMemset(sets[0].dy, 0, 16));
