@@ -101,6 +101,23 @@ YH_API int yh_v1_train(const float* y, int n, int s_h, int s_w, int b, int c,
                 const float* lambdas_host, float* dy, float* terms, float* loss,
                 int32_t* resp, float* iou_resp, void* ws, size_t ws_bytes, void* stream);
 
+/* The same two calls for callers that can promise more (HostHeadPipeline and bench.py do): NONE of
+ * this call's buffers (y, gt, gt_off, dy, terms, loss, resp, iou_resp) is read or written by the
+ * two kernels launched immediately before it on `stream`.  The kernel then starts while those
+ * kernels are still draining -- it is launched as a programmatic dependent and only waits for them
+ * before it touches the workspace (shared with the previous launch) and before it completes, so
+ * stream order is kept for everything launched afterwards.  Same results, bit for bit. */
+YH_API int yh_v2_train_overlapped(const float* y, int n, int s_h, int s_w, int a, int c,
+                const float* anchors_wh_host, float img_h, float img_w,
+                const YhGt* gt, const int32_t* gt_off, int m_local, int m_global,
+                const float* lambdas_host, float* dy, float* terms, float* loss,
+                int32_t* resp, float* iou_resp, void* ws, size_t ws_bytes, void* stream);
+YH_API int yh_v1_train_overlapped(const float* y, int n, int s_h, int s_w, int b, int c,
+                float img_h, float img_w,
+                const YhGt* gt, const int32_t* gt_off, int m_local, int m_global,
+                const float* lambdas_host, float* dy, float* terms, float* loss,
+                int32_t* resp, float* iou_resp, void* ws, size_t ws_bytes, void* stream);
+
 /* The six outputs of predict() (reference models/yolov2.py:433-649, models/yolov1.py:207-437).
  * Any output pointer may be NULL.  Shapes, with P = S_h*S_w*A predictors per image:
  *   sig_txty[N,P,2]  wh_act[N,P,2] (v2: exp(twth), v1: sigmoid(twth))  bbox[N,P,4] pixels xyxy

@@ -27,6 +27,8 @@ SIGNATURES = {
     "yh_train_workspace_bytes": (_sz, []),
     "yh_v2_train": (_i, [_p, _i, _i, _i, _i, _i, _p, _f, _f, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "yh_v1_train": (_i, [_p, _i, _i, _i, _i, _i, _f, _f, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "yh_v2_train_overlapped": (_i, [_p, _i, _i, _i, _i, _i, _p, _f, _f, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "yh_v1_train_overlapped": (_i, [_p, _i, _i, _i, _i, _i, _f, _f, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "yh_v2_decode": (_i, [_p, _i, _i, _i, _i, _i, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p]),
     "yh_v1_decode": (_i, [_p, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p, _p, _p, _p, _p]),
     "yh_compact_workspace_bytes": (_sz, [_i, _i]),

@@ -105,6 +105,7 @@ struct TrainParams {
     int tile_cells;       // cells per tile (multiple of 4)
     int num_tiles;
     int m_local;          // records in gt
+    int late_wait;        // *_overlapped entry points: wait for the previous kernels before publishing, not at the start
     int cell_slots;       // private cell copies per tile that fit in shared memory (<= kCellSlots)
     int cell_slot_floats; // floats per private cell copy (cell + alignment slack, multiple of 4)
     long long total_floats;
@@ -386,7 +387,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
     // everything above overlaps the tail of the previous kernel of the stream (programmatic dependent
     // launch); nothing below may run before that kernel has completed: it may have produced y, and it
     // may be the previous launch of this kernel, which shares the workspace
-    yh_grid_dependency_wait();
+    if (!p.late_wait) yh_grid_dependency_wait();
     yh_grid_launch_dependents();
     __syncthreads();
 
@@ -874,7 +875,13 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
         write_warp_sums();
         __syncthreads();
     }
-    if (tid == kPublisher) publish();
+    if (tid == kPublisher) {
+        // (*_overlapped) this kernel ran next to the tails of the kernels in front of it; the workspace
+        // is shared with the previous launch of this kernel, and this launch must not complete before
+        // they have: wait for them now
+        if (p.late_wait) yh_grid_dependency_wait();
+        publish();
+    }
     XT_FLUSH;
 }
 #ifdef YH_X_TRACE
@@ -920,7 +927,7 @@ int train_impl(int version, const float* y, int n, int s_h, int s_w, int a, int 
                const float* anchors_wh_host, float img_h, float img_w, const YhGt* gt,
                const int32_t* gt_off, int m_local, int m_global, const float* lambdas_host,
                float* dy, float* terms, float* loss, int32_t* resp, float* iou_resp, void* ws,
-               size_t ws_bytes, void* stream) {
+               size_t ws_bytes, void* stream, int late_wait = 0) {
     TrainParams p;
     int rc = yh_make_geom(&p.g, version, n, s_h, s_w, a, c, anchors_wh_host, img_h, img_w);
     if (rc) return rc;
@@ -944,6 +951,7 @@ int train_impl(int version, const float* y, int n, int s_h, int s_w, int a, int 
     YH_REQUIRE(total_cells * cf < (1ll << 31), YH_ERR_UNSUPPORTED, "head tensor has 2^31 or more floats");
     p.total_cells = (int)total_cells;
     p.m_local = m_local;
+    p.late_wait = late_wait;
     p.rec_per_cell = (float)((double)m_local / (double)total_cells);
 
     const double M = (double)m_global;
@@ -1013,6 +1021,22 @@ int yh_v1_train(const float* y, int n, int s_h, int s_w, int b, int c, float img
                 float* iou_resp, void* ws, size_t ws_bytes, void* stream) {
     return train_impl(1, y, n, s_h, s_w, b, c, nullptr, img_h, img_w, gt, gt_off, m_local, m_global,
                       lambdas_host, dy, terms, loss, resp, iou_resp, ws, ws_bytes, stream);
+}
+
+int yh_v2_train_overlapped(const float* y, int n, int s_h, int s_w, int a, int c, const float* anchors_wh_host,
+                           float img_h, float img_w, const YhGt* gt, const int32_t* gt_off, int m_local,
+                           int m_global, const float* lambdas_host, float* dy, float* terms, float* loss,
+                           int32_t* resp, float* iou_resp, void* ws, size_t ws_bytes, void* stream) {
+    return train_impl(2, y, n, s_h, s_w, a, c, anchors_wh_host, img_h, img_w, gt, gt_off, m_local,
+                      m_global, lambdas_host, dy, terms, loss, resp, iou_resp, ws, ws_bytes, stream, 1);
+}
+
+int yh_v1_train_overlapped(const float* y, int n, int s_h, int s_w, int b, int c, float img_h, float img_w,
+                           const YhGt* gt, const int32_t* gt_off, int m_local, int m_global,
+                           const float* lambdas_host, float* dy, float* terms, float* loss, int32_t* resp,
+                           float* iou_resp, void* ws, size_t ws_bytes, void* stream) {
+    return train_impl(1, y, n, s_h, s_w, b, c, nullptr, img_h, img_w, gt, gt_off, m_local, m_global,
+                      lambdas_host, dy, terms, loss, resp, iou_resp, ws, ws_bytes, stream, 1);
 }
 
 }  // extern "C"

@@ -69,13 +69,16 @@ def head_shape(y, version, a=None):
 
 
 def train_head(y, gt, gt_off, *, version, img_hw, lambdas, anchors=None, boxes_per_cell=None,
-               m_global=None, want_grad=True, want_resp=False, out=None):
+               m_global=None, want_grad=True, want_resp=False, out=None, input_ready=False):
     """Fused decode + assignment + loss (+ dL/dy) -- yh_v2_train / yh_v1_train.
 
     y       head tensor (CUDA fp32), gt int32 [M,12] records sorted by image (targets.py),
     gt_off  int32 [N+1] CSR offsets, img_hw (H, W) of the network input,
     lambdas dict with the five reference weights or a sequence of five floats.
     Returns dict(loss 0-dim, terms[5], dy or None, resp/iou_resp or None).
+    `input_ready=True` promises that none of this call's tensors is read or written by the two
+    kernels launched just before it on the current stream (yh_v*_train_overlapped): the kernel then
+    overlaps their tails.
     """
     y = _require_cuda_f32(y, "y")
     n, s_h, s_w, a, c = head_shape(y, version, boxes_per_cell)
@@ -113,12 +116,12 @@ def train_head(y, gt, gt_off, *, version, img_hw, lambdas, anchors=None, boxes_p
         if version == 2:
             if anchors is None or len(anchors) != a:
                 raise ValueError("anchors must list %d (w,h) pairs" % a)
-            _lib.call("yh_v2_train", _ptr(y), n, s_h, s_w, a, c, _anchors_host(anchors),
+            _lib.call("yh_v2_train_overlapped" if input_ready else "yh_v2_train", _ptr(y), n, s_h, s_w, a, c, _anchors_host(anchors),
                       float(img_hw[0]), float(img_hw[1]), _ptr(gt), _ptr(gt_off), m_local, m_glob,
                       lam_h, _ptr(dy), _ptr(terms), _ptr(loss), _ptr(resp), _ptr(iou_resp),
                       _ptr(ws), ws.numel(), _stream())
         else:
-            _lib.call("yh_v1_train", _ptr(y), n, s_h, s_w, a, c,
+            _lib.call("yh_v1_train_overlapped" if input_ready else "yh_v1_train", _ptr(y), n, s_h, s_w, a, c,
                       float(img_hw[0]), float(img_hw[1]), _ptr(gt), _ptr(gt_off), m_local, m_glob,
                       lam_h, _ptr(dy), _ptr(terms), _ptr(loss), _ptr(resp), _ptr(iou_resp),
                       _ptr(ws), ws.numel(), _stream())

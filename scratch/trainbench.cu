@@ -48,6 +48,7 @@ int main(int argc, char** argv) {
     const float lam[5] = {5, 5, 1, .5f, 1};
     const int MAXO = 128;
     int post_flags = 0;
+    bool train_ov = false;
 
     struct Set { float *y, *dy, *terms, *loss, *obox, *oconf, *oscore; YhGt* gt; int *off, *kidx, *kcnt, *olab; void *ws, *pws; };
     std::vector<Set> sets(R);
@@ -88,8 +89,8 @@ int main(int argc, char** argv) {
         CK(cudaGraphExecDestroy(ge)); CK(cudaGraphDestroy(g));
     };
     auto train = [&](Set& s) {
-        return yh_v2_train(s.y, N, S, S, A, C, anchors, 416.f, 416.f, s.gt, s.off, M, M, lam, s.dy, s.terms, s.loss, nullptr, nullptr,
-                           s.ws, yh_train_workspace_bytes(), st);
+        return (train_ov ? yh_v2_train_overlapped : yh_v2_train)(s.y, N, S, S, A, C, anchors, 416.f, 416.f, s.gt, s.off, M, M, lam, s.dy, s.terms,
+                                                                 s.loss, nullptr, nullptr, s.ws, yh_train_workspace_bytes(), st);
     };
     auto post = [&](Set& s) {
         return yh_v2_postprocess(s.y, N, S, S, A, C, anchors, 416.f, 416.f, 0.5f, 0.45f, post_flags, MAXO, s.kidx, s.kcnt, s.obox, s.oconf,
@@ -101,6 +102,13 @@ int main(int argc, char** argv) {
     run("train+post", tb + floats * 4, [&](Set& s) { int rc = train(s); return rc ? rc : post(s); });
     post_flags = YH_POST_INPUT_READY;
     run("train+post (input ready)", tb + floats * 4, [&](Set& s) { int rc = train(s); return rc ? rc : post(s); });
+    train_ov = true;
+    run("train+post (both overlapped)", tb + floats * 4, [&](Set& s) { int rc = train(s); return rc ? rc : post(s); });
+    run("train (overlapped, back to back)", tb, train);
+    post_flags = 0;
+    run("train overlapped + post plain", tb + floats * 4, [&](Set& s) { int rc = train(s); return rc ? rc : post(s); });
+    post_flags = YH_POST_INPUT_READY;
+    train_ov = false;
     post_flags = 0;
 #ifdef YH_X_TRACE
     {

@@ -663,3 +663,55 @@ def test_host_pipeline_returns_what_the_direct_calls_return(cuda_device):
         mask = torch.arange(64)[None, :] < cnt.clamp(max=64)[:, None]
         for k in ("keep_idx", "bbox", "conf", "label", "score"):
             assert torch.equal(got[k][mask], post[k].cpu()[mask]), k
+
+
+def test_overlapped_launch_chain_gives_the_same_results(cuda_device):
+    """yh_v2_train_overlapped + YH_POST_INPUT_READY: a captured chain of steps over rotating buffer sets,
+    every kernel but the first overlapping the tails of the ones in front of it, replayed several times,
+    must leave in every set exactly what stream-ordered calls produce."""
+    lam = synthetic.DEFAULT_LAMBDAS
+    cases = [synthetic.make_case("o%d" % i, 2, 96, 13, 13, 5, 20, 416, 416, seed=700 + i, to_shift=-1.5) for i in range(4)]
+    kw = dict(version=2, img_hw=(416, 416), anchors=cases[0].anchors)
+    sets, want = [], []
+    for c in cases:
+        y = c.y.to(cuda_device)
+        gt = targets.records_to_tensor(c.rec, cuda_device)
+        off = torch.from_numpy(c.gt_off).to(cuda_device)
+        r = ops.train_head(y, gt, off, lambdas=lam, **kw)
+        p = ops.postprocess(y, conf_thre=0.5, iou_thre=0.45, max_out=96, want_cls_spec=False, **kw)
+        torch.cuda.synchronize()
+        want.append(dict(loss=r["loss"].clone(), terms=r["terms"].clone(), dy=r["dy"].clone(),
+                         post={k: v.clone() for k, v in p.items() if k in ("keep_cnt", "keep_idx", "bbox", "label", "score", "conf")}))
+        sets.append(dict(y=y, gt=gt, off=off, out=dict(dy=torch.empty_like(y), loss=torch.empty((), device=cuda_device),
+                                                        terms=torch.empty(5, device=cuda_device)), post=None))
+    stream = torch.cuda.Stream(cuda_device)
+
+    def chain():
+        for i, s_ in enumerate(sets):
+            ops.train_head(s_["y"], s_["gt"], s_["off"], lambdas=lam, out=s_["out"], input_ready=(i > 0), **kw)
+            s_["post"] = ops.postprocess(s_["y"], conf_thre=0.5, iou_thre=0.45, max_out=96, want_cls_spec=False,
+                                         out=s_["post"], input_ready=True, **kw)
+
+    with torch.cuda.stream(stream):
+        chain()
+        stream.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            chain()
+        for rep in range(6):
+            for s_ in sets:  # poison the outputs: a kernel that did not run, or ran on stale data, shows
+                s_["out"]["dy"].fill_(float("nan"))
+                s_["out"]["loss"].fill_(float("nan"))
+                s_["post"]["keep_cnt"].fill_(-1)
+            for _ in range(3):
+                g.replay()
+            stream.synchronize()
+            for s_, w in zip(sets, want):
+                assert torch.equal(s_["out"]["loss"], w["loss"])
+                assert torch.equal(s_["out"]["terms"], w["terms"])
+                assert torch.equal(s_["out"]["dy"], w["dy"])
+                cnt = w["post"]["keep_cnt"]
+                assert torch.equal(s_["post"]["keep_cnt"], cnt)
+                mask = torch.arange(96, device=cuda_device)[None, :] < cnt.clamp(max=96)[:, None]
+                for k in ("keep_idx", "bbox", "label", "score", "conf"):
+                    assert torch.equal(s_["post"][k][mask], w["post"][k][mask]), k
