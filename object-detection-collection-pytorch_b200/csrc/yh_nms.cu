@@ -49,6 +49,11 @@ constexpr int kTileWords = kTile / 32;
 constexpr int kSmemCand = 256;         // candidates held in shared memory
 constexpr int kStageBytesMax = 64 * 1024;  // shared memory for staged candidate rows
 constexpr int kLoadUnroll = 2;         // objectness loads in flight per thread (845 predictors = 1.65 per thread)
+constexpr int kGroups = 4;             // whole-image mode: the image arrives in kGroups bulk copies, one warp group each
+#ifndef YH_X_NMS_IMG_BYTES
+#define YH_X_NMS_IMG_BYTES (88 * 1024)
+#endif
+constexpr int kImgBytesMax = YH_X_NMS_IMG_BYTES;  // images up to this size are staged whole (2 CTAs per SM)
 
 enum { SRC_HEAD = 0, SRC_DECODED = 2 };
 
@@ -97,6 +102,7 @@ struct NmsParams {
     int img_floats;          // floats per image
     int use_tma;             // y is 16-byte aligned: candidate rows are staged with bulk copies
     int stage_slots;         // candidate rows staged in shared memory (<= kSmemCand)
+    int stage_bytes;         // shared memory in front of the candidate arrays (staged rows, or the whole image)
     int slot_floats;         // floats per staged row slot (multiple of 4)
     unsigned magic_sw;       // ceil(2^32 / s_w): cell / s_w == umulhi(cell, magic_sw) for cell < 2^16
 };
@@ -203,6 +209,61 @@ __device__ __forceinline__ void group_class_pick(const float* cl, int C, float c
     *score = bv;
 }
 
+// Class pick for outputs that only need label and score, by 4 adjacent lanes, classes in registers (C <= 32):
+// the label is the first maximum of cls_spec = softmax * conf, and only classes whose logit is within 1e-4 of
+// the largest one can reach it (a smaller logit gives a cls_spec smaller by a factor 1 - 1e-4, far beyond
+// the rounding of expf, the division and the product), so only those classes -- almost always one -- take the
+// division.  Same sums, in the same order, as group_class_pick<4>: the score has the same bits.  *ok is false
+// where that argument does not hold (non-finite sum, cls_spec below the normal range): the caller
+// then runs group_class_pick for the warp.
+constexpr int kPickRegs = 8;
+__device__ __forceinline__ void quad_class_pick_fast(const float* cl, int C, float conf, int sub, bool active,
+                                                     int* label, float* score, bool* ok) {
+    float l[kPickRegs];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < kPickRegs; ++k) {
+        const int c = sub + 4 * k;
+        l[k] = (active && c < C) ? cl[c] : -INFINITY;
+        mx = fmaxf(mx, l[k]);
+    }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    float se = 0.f;
+#pragma unroll
+    for (int k = 0; k < kPickRegs; ++k) {
+        const int c = sub + 4 * k;
+        if (c < C) {  // (uniform per k for the lanes of a group up to the last k)
+            const float near_ = l[k];
+            l[k] = expf(l[k] - mx);
+            se += l[k];
+            if (!(near_ >= mx - 1e-4f)) l[k] = -1.f;  // cannot be the maximum: no division
+        } else {
+            l[k] = -1.f;
+        }
+    }
+    se += __shfl_xor_sync(0xffffffffu, se, 1);
+    se += __shfl_xor_sync(0xffffffffu, se, 2);
+    float bv = -INFINITY;
+    int bi = 1 << 30;
+#pragma unroll
+    for (int k = 0; k < kPickRegs; ++k) {
+        if (l[k] >= 0.f) {
+            const float sp = __fmul_rn(__fdiv_rn(l[k], se), conf);
+            if (sp > bv) { bv = sp; bi = sub + 4 * k; }  // first max per lane (c ascending)
+        }
+    }
+#pragma unroll
+    for (int o = 1; o < 4; o <<= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    *label = bi;
+    *score = bv;
+    *ok = !active || (se < INFINITY && bv >= 1e-30f && bv < INFINITY);  // (false for NaN)
+}
+
 // bit = "box i suppresses box j": iou(i, j) >= thr with the reference's arithmetic
 // (models/utils.py:47-63, 133: j survives iff iou < thr).  ai/aj are the boxes' areas as yh_iou_xyxy
 // rounds them.  Boxes that do not overlap have iou == 0 exactly, and away from the threshold the
@@ -224,13 +285,17 @@ __device__ __forceinline__ bool suppresses(const float4& bi, float ai, const flo
 
 // TV/TA/TC != 0 fix version / boxes per cell / classes at compile time (index arithmetic folds,
 // divisions become multiplies); 0 keeps them as run-time values from the geometry.
-template <int TV, int TA, int TC>
+// IMG: the image's whole slice of the head tensor is staged in shared memory by kGroups bulk copies
+// issued at the start (ONE global round trip, no per-candidate copies); otherwise the objectness
+// logits are read with strided loads and only the candidates' rows are staged.
+template <int TV, int TA, int TC, bool IMG>
 __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const NmsParams p) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];  // [staged rows | candidate arrays]
+    extern __shared__ __align__(128) unsigned char smem_raw[];  // [staged rows or image | candidate arrays]
     __shared__ unsigned int mask[kTile * kTileWords];
     __shared__ unsigned int rem0[kTileWords];
     __shared__ __align__(8) uint64_t bar;      // staged rows have landed (transaction bytes)
     __shared__ __align__(8) uint64_t bar_list; // every thread has listed its candidates
+    __shared__ __align__(8) uint64_t bar_img[kGroups];  // IMG: one per bulk copy of the image
     __shared__ int s_count, s_kept;
 
     const YhGeom& g = p.g;
@@ -243,23 +308,51 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
     const int bs = v2 ? 5 + C : 5, cf = v2 ? A * (5 + C) : 5 * A + C;
 
     float* stage = reinterpret_cast<float*>(smem_raw);
-    unsigned char* cand_smem = smem_raw + (size_t)p.stage_slots * p.slot_floats * 4;
+    unsigned char* cand_smem = smem_raw + p.stage_bytes;
     Cand ca = carve(cand_smem, kSmemCand);
     Cand cw = ca;  // workspace copy for images that overflow shared memory
     if (p.ws) cw = carve(p.ws + (size_t)img * p.ws_per_image, P);
 
     NT(0);
+    if (IMG) {  // the single-tile path sets suppression bits with atomicOr
+        for (int q = tid; q < kTile * kTileWords / 4; q += kThreads) reinterpret_cast<uint4*>(mask)[q] = make_uint4(0u, 0u, 0u, 0u);
+    }
     if (tid == 0) {
         s_count = 0;
         s_kept = 0;
         yh_mbar_init(&bar, kThreads);
         yh_mbar_init(&bar_list, kThreads);
+        if (IMG) {
+#pragma unroll
+            for (int q = 0; q < kGroups; ++q) yh_mbar_init(&bar_img[q], 1);
+        }
         yh_mbar_fence_init();
     }
     // (programmatic dependent launch: the prologue above overlaps the previous kernel's tail; global
     // memory is only touched once that kernel has completed)
     if (!p.late_wait) yh_grid_dependency_wait();
     yh_grid_launch_dependents();
+    // IMG: the image's aligned window [image start - fsh, ...) goes to shared memory in kGroups pieces cut at
+    // unit boundaries (v2: predictors, v1: cells) rounded down to 16 bytes; window float w is image float w - fsh
+    const int img_units = (TV ? TV : p.g.version) == 2 ? p.p : p.g.cells;
+    const int img_unit_floats = (TV ? TV : p.g.version) == 2 ? 5 + (TC ? TC : p.c) : p.g.cell_floats;
+    if (IMG && tid == 0) {
+        const int fsh0 = (int)(((long long)img * p.img_floats) & 3);
+        const float* wsrc = p.y + ((long long)img * p.img_floats - fsh0);
+        const long long limw = (p.total_floats & ~3ll) - ((long long)img * p.img_floats - fsh0);  // bulk copies end here
+        const int wend = (int)min((long long)((fsh0 + p.img_floats + 3) & ~3), limw);
+#pragma unroll
+        for (int q = 0; q < kGroups; ++q) {
+            const int lo = q == 0 ? 0 : (fsh0 + ((img_units * q) / kGroups) * img_unit_floats) & ~3;
+            const int hi = q == kGroups - 1 ? wend : min(wend, (fsh0 + ((img_units * (q + 1)) / kGroups) * img_unit_floats) & ~3);
+            if (hi > lo) {
+                yh_mbar_expect_tx(&bar_img[q], (uint32_t)(hi - lo) * 4u);
+                yh_bulk_load(reinterpret_cast<float*>(smem_raw) + lo, wsrc + lo, (uint32_t)(hi - lo) * 4u, &bar_img[q]);
+            } else {
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(yh_smem_u32(&bar_img[q])) : "memory");
+            }
+        }
+    }
     __syncthreads();
 
     // float offsets, inside the image, of a predictor's 5 box logits and C class logits (32-bit: one
@@ -298,8 +391,44 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
     };
 
     NT(1);
-    // ---------------- A: threshold + stage the survivors' rows ----------------
     uint32_t tx = 0;
+    if (IMG) {
+        // ---------------- A (whole image): each warp group thresholds its piece as it lands ----------------
+        const float* win = reinterpret_cast<const float*>(smem_raw);
+        constexpr int kGroupThreads = kThreads / kGroups;
+        const int grp = tid / kGroupThreads, gtid = tid - grp * kGroupThreads;
+        const int upp = v2 ? 1 : A;  // predictors per unit
+        const int i_lo = ((img_units * grp) / kGroups) * upp, i_hi = ((img_units * (grp + 1)) / kGroups) * upp;
+        {   // floats past the last whole 16 bytes of the tensor (last image only): plain loads
+            const int wend = (int)min((long long)(fsh + p.img_floats), lim4 + fsh);
+            if (tid < fsh + p.img_floats - wend) stage[wend + tid] = __ldg(yimg + (wend - fsh) + tid);
+        }
+        yh_mbar_wait(&bar_img[grp], 0);
+        for (int base = i_lo; base < i_hi; base += kGroupThreads) {  // (warp-uniform trip count)
+            const int i = base + gtid;
+            float conf = 0.f;
+            bool pass = false;
+            if (i < i_hi) {
+                const float t = win[fsh + box_off(i) + 4];
+                if (!(t < p.to_reject)) {  // far below the threshold: sigmoid not needed
+                    conf = yh_sigmoid(t);
+                    pass = conf >= p.conf_thre;  // models/utils.py:92
+                }
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, pass);
+            if (bal) {
+                int slot0 = 0;
+                if (lane == 0) slot0 = atomicAdd(&s_count, __popc(bal));
+                slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+                if (pass) {
+                    const int slot = slot0 + __popc(bal & ((1u << lane) - 1u));
+                    if (slot < kSmemCand) { ca.u_conf[slot] = conf; ca.u_idx[slot] = i; }
+                    else { cw.u_conf[slot] = conf; cw.u_idx[slot] = i; }
+                }
+            }
+        }
+    } else
+    // ---------------- A: threshold + stage the survivors' rows ----------------
     for (int base = 0; base < P; base += kThreads * kLoadUnroll) {
         float val[kLoadUnroll];
 #pragma unroll
@@ -349,10 +478,16 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
     // will deliver, "my rows are on their way".  Ranking only needs the list, so it runs while the
     // rows are still in flight.
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(yh_smem_u32(&bar_list)) : "memory");
-    if (tx) yh_mbar_expect_tx(&bar, tx);
-    else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(yh_smem_u32(&bar)) : "memory");
+    if (!IMG) {
+        if (tx) yh_mbar_expect_tx(&bar, tx);
+        else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(yh_smem_u32(&bar)) : "memory");
+    }
     NT(2);
     yh_mbar_wait(&bar_list, 0);
+    if (IMG) {  // (all pieces have landed by now: every group has gone through its own; this makes them visible)
+#pragma unroll
+        for (int q = 0; q < kGroups; ++q) yh_mbar_wait(&bar_img[q], 0);
+    }
 
     const int K = s_count;
     const bool overflow = K > kSmemCand;
@@ -369,14 +504,16 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
     auto rest = [&](auto fast_tag, auto lab_tag) {
         constexpr bool FAST = decltype(fast_tag)::value;
         constexpr bool LAB = decltype(lab_tag)::value;  // labels take part in the suppression test
-        Cand ca = carve(smem_raw + (size_t)p.stage_slots * p.slot_floats * 4, kSmemCand);
+        Cand ca = carve(smem_raw + p.stage_bytes, kSmemCand);
         if (!FAST && overflow) ca = cw;
         auto box_ptr = [&](int slot, int idx) -> const float* {
             const int f = box_off(idx);
+            if (IMG) return reinterpret_cast<const float*>(smem_raw) + (fsh + f);
             if (FAST || slot < p.stage_slots) return reinterpret_cast<const float*>(smem_raw) + slot * p.slot_floats + ((fsh + f) & 3);
             return yimg + f;
         };
         auto cls_ptr = [&](int slot, int idx) -> const float* {
+            if (IMG) return reinterpret_cast<const float*>(smem_raw) + (fsh + cls_off(idx));
             if (FAST || slot < p.stage_slots) {
                 const float* st = reinterpret_cast<const float*>(smem_raw) + slot * p.slot_floats;
                 if (v2) return st + ((fsh + box_off(idx)) & 3) + 5;
@@ -409,7 +546,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
             rank += __shfl_xor_sync(0xffffffffu, rank, 4);
             if (!rows_in) {
                 NT(3);
-                yh_mbar_wait(&bar, 0);  // the staged rows
+                if (!IMG) yh_mbar_wait(&bar, 0);  // the staged rows
                 rows_in = true;
             }
             float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -446,7 +583,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
 
         NT(4);
         const bool use_lab = LAB && (head ? (p.class_aware != 0) : (p.labels != nullptr));
-        constexpr int kPick = 8;  // lanes per class pick
+        constexpr int kPick = 4;  // lanes per class pick (as in the whole-image path: same sums, same bits)
         const int sub = tid & (kPick - 1);
         if (use_lab && head) {  // label of every candidate (argmax of cls_spec)
             for (int k0 = 0; k0 < K; k0 += kThreads / kPick) {
@@ -609,28 +746,239 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
         }
         NT(13);
     };
+
+    // Whole-image mode with at most one tile of candidates, all in shared memory: the lean path.  The
+    // kernel's tail is bound by instruction issue (two CTAs per SM, and the next kernel of the stream
+    // streaming next to them), so every phase is laid out for few warp instructions:
+    //   B  two lanes per candidate: each counts half of the candidates that beat it (16-byte loads of
+    //      the unsorted lists), then decodes one axis of the box (x: tx, tw; y: ty, th);
+    //   D  the i < j pairs are enumerated densely over all threads (the triangle folded into a
+    //      K/2 x (K-1) rectangle), set bits go to the mask with atomicOr (rare), then the fixed-point
+    //      resolution of the greedy order by one warp, as in the general path;
+    //   E  four lanes per kept box, class pick without the divisions that cannot matter.
+    auto rest_img = [&](auto lab_tag) {
+        constexpr bool LAB = decltype(lab_tag)::value;
+        const float* win = reinterpret_cast<const float*>(smem_raw);
+        Cand ca = carve(smem_raw + p.stage_bytes, kSmemCand);
+        const bool use_lab = LAB && p.class_aware != 0;
+
+        // ---------------- B: rank + decode ----------------
+        {
+            const int k = tid >> 1, ax = tid & 1;  // candidate, axis
+            if ((tid & ~31) < 2 * K) {  // (whole warps)
+                const bool on = k < K;
+                const float ck = on ? ca.u_conf[k] : 0.f;
+                const int ik = on ? ca.u_idx[k] : 0;
+                int rank = 0;
+                const float4* c4 = reinterpret_cast<const float4*>(ca.u_conf);
+                const int4* i4 = reinterpret_cast<const int4*>(ca.u_idx);
+                const int K4 = K >> 2;
+                for (int q = ax; q < K4; q += 2) {
+                    const float4 cj = c4[q];
+                    const int4 ij = i4[q];
+                    rank += (cj.x > ck || (cj.x == ck && ij.x < ik)) ? 1 : 0;
+                    rank += (cj.y > ck || (cj.y == ck && ij.y < ik)) ? 1 : 0;
+                    rank += (cj.z > ck || (cj.z == ck && ij.z < ik)) ? 1 : 0;
+                    rank += (cj.w > ck || (cj.w == ck && ij.w < ik)) ? 1 : 0;
+                }
+                if (ax == 0) {
+                    for (int j = 4 * K4; j < K; ++j) {
+                        const float cj = ca.u_conf[j];
+                        rank += (cj > ck || (cj == ck && ca.u_idx[j] < ik)) ? 1 : 0;
+                    }
+                }
+                rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+                // this lane's axis of the box: lo/hi corner coordinate (same roundings as yh_decode_box)
+                float lo = 0.f, hi = 0.f;
+                if (on) {
+                    const float* row = win + (fsh + box_off(ik));
+                    const float tc = row[ax], ts = row[2 + ax];
+                    const float sc = yh_sigmoid(tc);
+                    const float sa = v2 ? expf(ts) : yh_sigmoid(ts);
+                    const int cell = ik / A, a = ik - cell * A;
+                    const int cy = (int)__umulhi((unsigned)cell, p.magic_sw), cx = cell - cy * g.s_w;  // cell / s_w
+                    const float bsz = __fmul_rn(ax ? g.ph[a] : g.pw[a], sa);
+                    const float bc = __fadd_rn(sc, (float)(ax ? cy : cx));
+                    const float hs = __fmul_rn(bsz, 0.5f);
+                    const float gsz = ax ? g.gh : g.gw;
+                    lo = __fmul_rn(__fsub_rn(bc, hs), gsz);
+                    hi = __fmul_rn(__fadd_rn(bc, hs), gsz);
+                }
+                const float olo = __shfl_xor_sync(0xffffffffu, lo, 1), ohi = __shfl_xor_sync(0xffffffffu, hi, 1);
+                if (on && ax == 0) {
+                    ca.s_box[rank] = make_float4(lo, olo, hi, ohi);
+                    ca.s_area[rank] = __fmul_rn(__fsub_rn(hi, lo), __fsub_rn(ohi, olo));
+                    ca.s_idx[rank] = ik;
+                    ca.s_conf[rank] = ck;
+                }
+            }
+        }
+        __syncthreads();
+        NT(4);
+
+        constexpr int kPick = 4;  // lanes per class pick
+        const int sub = tid & (kPick - 1);
+        // label and score of ranked candidate / kept box: fast pick, the full one where it does not apply
+        // (`with_spec` is uniform over the warp: both functions shuffle across all 32 lanes)
+        auto pick = [&](const float* cl, float conf, bool act, bool with_spec, float* spec_out, int* lab, float* sc) {
+            bool ok = false;
+            if (C <= 4 * kPickRegs && !with_spec) quad_class_pick_fast(cl, C, conf, sub, act, lab, sc, &ok);
+            if (!__all_sync(0xffffffffu, ok)) group_class_pick<kPick>(cl, C, conf, sub, act, spec_out, lab, sc);
+        };
+        if (use_lab) {  // label of every candidate (argmax of cls_spec)
+            for (int k0 = 0; k0 < K; k0 += kThreads / kPick) {
+                if (k0 + (32 / kPick) * warp >= K) break;
+                const int k = k0 + tid / kPick;
+                const bool act = k < K;
+                int lab;
+                float sc;
+                pick(act ? win + (fsh + cls_off(ca.s_idx[k])) : nullptr, act ? ca.s_conf[k] : 0.f, act, false, nullptr, &lab, &sc);
+                if (act && sub == 0) ca.s_lab[k] = lab;
+            }
+            __syncthreads();
+        }
+
+        // ---------------- D: greedy suppression (one tile) ----------------
+        const float thr = p.iou_thre;
+        const int tn = K;
+        const int W = (tn + 31) >> 5;
+        {
+            const int Ke = K + (K & 1), cols = Ke - 1, total = (Ke >> 1) * cols;
+            const unsigned magic = cols > 1 ? (unsigned)(0xFFFFFFFFu / (unsigned)cols) + 1u : 0u;  // pair / cols, pair < 2^16
+            for (int pr = tid; pr < total; pr += kThreads) {
+                const int r = cols > 1 ? (int)__umulhi((unsigned)pr, magic) : pr;
+                const int c = pr - r * cols;
+                const int i = c >= r ? r : Ke - 1 - r;
+                const int j = c >= r ? c + 1 : Ke - 1 - c;
+                if (j < K) {
+                    bool bit = suppresses(ca.s_box[i], ca.s_area[i], ca.s_box[j], ca.s_area[j], thr);
+                    if (use_lab) bit = bit && ca.s_lab[i] == ca.s_lab[j];
+                    if (bit) atomicOr(&mask[j * kTileWords + (i >> 5)], 1u << (i & 31));
+                }
+            }
+        }
+        __syncthreads();
+        NT(7);
+        if (warp == 0) {
+            unsigned alive[kTileWords], dead0[kTileWords];
+#pragma unroll
+            for (int w = 0; w < kTileWords; ++w) {
+                dead0[w] = w < W ? 0u : 0xffffffffu;
+                if (w == W - 1 && (tn & 31)) dead0[w] |= ~0u << (tn & 31);  // bits past the tile end
+                alive[w] = ~dead0[w];
+            }
+            if (W <= 2) {
+                // common case (<= 64 candidates): the lane's two columns live in registers
+                const unsigned c00 = lane < tn ? mask[lane * kTileWords] : 0u;
+                const unsigned c10 = 32 + lane < tn ? mask[(32 + lane) * kTileWords] : 0u;
+                const unsigned c11 = 32 + lane < tn ? mask[(32 + lane) * kTileWords + 1] : 0u;
+                for (int sweep = 0; sweep <= tn; ++sweep) {
+                    const unsigned n0 = __ballot_sync(0xffffffffu, (c00 & alive[0]) == 0u) & ~dead0[0];
+                    const unsigned n1 = __ballot_sync(0xffffffffu, ((c10 & n0) | (c11 & alive[1])) == 0u) & ~dead0[1];
+                    const bool same = n0 == alive[0] && n1 == alive[1];
+                    alive[0] = n0;
+                    alive[1] = n1;
+                    if (same) break;
+                }
+            } else {
+                for (int sweep = 0; sweep <= tn; ++sweep) {
+                    bool changed = false;
+#pragma unroll
+                    for (int m = 0; m < kTileWords; ++m) {
+                        if (m < W) {  // (warp-uniform)
+                            const int j = 32 * m + lane;
+                            bool a = false;
+                            if (j < tn) {
+                                unsigned hit = 0u;
+#pragma unroll
+                                for (int w = 0; w < kTileWords; ++w)
+                                    if (w <= m) hit |= mask[j * kTileWords + w] & alive[w];
+                                a = hit == 0u;
+                            }
+                            const unsigned nw = __ballot_sync(0xffffffffu, a) & ~dead0[m];
+                            changed = changed || nw != alive[m];
+                            alive[m] = nw;  // (later words of this sweep already see it)
+                        }
+                    }
+                    if (!changed) break;
+                }
+            }
+            int kept_n = 0;
+#pragma unroll
+            for (int m = 0; m < kTileWords; ++m) {
+                if (m < W) {
+                    if ((alive[m] >> lane) & 1u) ca.keep[kept_n + __popc(alive[m] & ((1u << lane) - 1u))] = 32 * m + lane;
+                    kept_n += __popc(alive[m]);
+                }
+            }
+            if (lane == 0) s_kept = kept_n;
+        }
+        __syncthreads();
+        NT(8);
+
+        NT(12);
+        // ---------------- E: emit ----------------
+        const int kept = s_kept;
+        if (tid == 0) p.keep_cnt[img] = kept;
+        const int nout = min(kept, p.max_out);
+        const bool want_cls = p.out_cls_spec || p.out_label || p.out_score;
+        for (int t0 = 0; t0 < nout; t0 += kThreads / kPick) {
+            if (t0 + (32 / kPick) * warp >= nout) break;
+            const int t = t0 + tid / kPick;
+            const bool act = t < nout;
+            int i = 0, idx = 0;
+            float conf = 0.f;
+            size_t o = 0;
+            if (act) {
+                i = ca.keep[t];
+                idx = ca.s_idx[i];
+                conf = ca.s_conf[i];
+                o = (size_t)img * p.max_out + t;
+                if (sub == 0) {
+                    p.keep_idx[o] = idx;
+                    if (p.out_conf) p.out_conf[o] = conf;
+                } else if (sub == 1) {
+                    if (p.out_bbox) p.out_bbox[o] = ca.s_box[i];
+                }
+            }
+            if (want_cls) {
+                int lab;
+                float sc;
+                pick(act ? win + (fsh + cls_off(idx)) : nullptr, conf, act, p.out_cls_spec != nullptr,
+                     (act && p.out_cls_spec) ? p.out_cls_spec + o * C : nullptr, &lab, &sc);
+                if (act && sub == 2) {
+                    if (p.out_label) p.out_label[o] = lab;
+                    if (p.out_score) p.out_score[o] = sc;
+                }
+            }
+        }
+        NT(13);
+    };
     const bool with_labels = head ? (p.class_aware != 0) : (p.labels != nullptr);
-    if (!overflow && K <= p.stage_slots && !with_labels) rest(FastTag<true>{}, FastTag<false>{});
-    else if (!overflow && K <= p.stage_slots) rest(FastTag<true>{}, FastTag<true>{});
+    const bool fast = !overflow && (IMG || K <= p.stage_slots);
+    if (IMG && fast && !with_labels) rest_img(FastTag<false>{});
+    else if (IMG && fast) rest_img(FastTag<true>{});
+    else if (fast && !with_labels) rest(FastTag<true>{}, FastTag<false>{});
+    else if (fast) rest(FastTag<true>{}, FastTag<true>{});
     else rest(FastTag<false>{}, FastTag<true>{});
     // (YH_POST_INPUT_READY) everything above ran next to the tail of the previous kernel of the stream;
     // this kernel must not complete before that one has, or work launched after it could overtake it
     if (p.late_wait) yh_grid_dependency_wait();
 }
 
-template <int TV, int TA, int TC>
+template <int TV, int TA, int TC, bool IMG>
 int launch_variant(const NmsParams& p, size_t smem, void* stream) {
     static size_t configured[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) dev = 0;
     if (smem > 32 * 1024 && smem > configured[dev]) {
-        int rc = yh_check_cuda(cudaFuncSetAttribute(yh_nms_kernel<TV, TA, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+        int rc = yh_check_cuda(cudaFuncSetAttribute(yh_nms_kernel<TV, TA, TC, IMG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                                "cudaFuncSetAttribute(nms)");
         if (rc) return rc;
         configured[dev] = smem;
     }
-    return yh_check_cuda(yh_launch_pdl(yh_nms_kernel<TV, TA, TC>, dim3((unsigned)p.n), dim3(kThreads), smem,
+    return yh_check_cuda(yh_launch_pdl(yh_nms_kernel<TV, TA, TC, IMG>, dim3((unsigned)p.n), dim3(kThreads), smem,
                                        (cudaStream_t)stream, p),
                          "yh_nms launch");
 }
@@ -649,12 +997,23 @@ int launch(NmsParams& p, void* ws, size_t ws_bytes, void* stream) {
         p.ws = reinterpret_cast<unsigned char*>(ws);
         p.ws_per_image = cand_bytes(p.p);
     }
-    const size_t smem = (size_t)p.stage_slots * p.slot_floats * 4 + cand_bytes(kSmemCand);
+    // whole-image staging: the image's aligned window (<= 3 floats of shift in front, padded to 16 bytes)
+    // fits next to a second CTA's; needs bulk copies (aligned y) and C >= 3 (then the floats past the last
+    // whole 16 bytes of the tensor, which arrive by plain loads, are never an objectness logit)
+    const int win_bytes = ((p.img_floats + 3 + 3) & ~3) * 4;
+    const bool img_mode = p.src == SRC_HEAD && p.use_tma && p.c >= 3 && win_bytes <= kImgBytesMax;
+    p.stage_bytes = img_mode ? win_bytes : p.stage_slots * p.slot_floats * 4;
+    const size_t smem = (size_t)p.stage_bytes + cand_bytes(kSmemCand);
     // compile-time geometries for the shapes the reference uses (VOC: YOLOv2 5 anchors x 20 classes,
     // YOLOv1 B=2, C=20); anything else, and decoded-box input, runs the run-time-geometry variant
-    if (p.src == SRC_HEAD && p.g.version == 2 && p.g.a == 5 && p.c == 20) return launch_variant<2, 5, 20>(p, smem, stream);
-    if (p.src == SRC_HEAD && p.g.version == 1 && p.g.a == 2 && p.c == 20) return launch_variant<1, 2, 20>(p, smem, stream);
-    return launch_variant<0, 0, 0>(p, smem, stream);
+    if (img_mode) {
+        if (p.g.version == 2 && p.g.a == 5 && p.c == 20) return launch_variant<2, 5, 20, true>(p, smem, stream);
+        if (p.g.version == 1 && p.g.a == 2 && p.c == 20) return launch_variant<1, 2, 20, true>(p, smem, stream);
+        return launch_variant<0, 0, 0, true>(p, smem, stream);
+    }
+    if (p.src == SRC_HEAD && p.g.version == 2 && p.g.a == 5 && p.c == 20) return launch_variant<2, 5, 20, false>(p, smem, stream);
+    if (p.src == SRC_HEAD && p.g.version == 1 && p.g.a == 2 && p.c == 20) return launch_variant<1, 2, 20, false>(p, smem, stream);
+    return launch_variant<0, 0, 0, false>(p, smem, stream);
 }
 
 int postprocess_impl(int version, const float* y, int n, int s_h, int s_w, int a, int c,
