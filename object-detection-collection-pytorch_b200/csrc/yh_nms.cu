@@ -88,6 +88,7 @@ struct NmsParams {
     int n, p, c;
     float conf_thre, iou_thre;
     float to_reject;         // objectness logits below this can never reach conf_thre
+    float to_accept;         // objectness logits from this on always reach conf_thre (+inf: no such shortcut)
     int class_aware, max_out;
     int late_wait;           // YH_POST_INPUT_READY: wait for the previous kernel at the end, not at the start
     int32_t* keep_idx;
@@ -283,6 +284,18 @@ __device__ __forceinline__ bool suppresses(const float4& bi, float ai, const flo
     return __fdiv_rn(inter, den) >= thr;
 }
 
+// The same decision for the dense pair enumeration, where nearly every pair is far below the threshold:
+// with thr > 0 (`thr_pos`, uniform) a pair whose intersection is below 0.999999 * thr * (union + 1e-6) cannot
+// reach thr (a union that is not positive, or NaNs anywhere, fail this test and take the full one).
+__device__ __forceinline__ bool suppresses_dense(const float4& bi, float ai, const float4& bj, float aj, float thr, bool thr_pos) {
+    const float iw = __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x));
+    const float ih = __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y));
+    const float inter = __fmul_rn(fmaxf(iw, 0.0f), fmaxf(ih, 0.0f));
+    const float den = __fadd_rn(__fsub_rn(__fadd_rn(ai, aj), inter), 1e-6f);
+    if (thr_pos && inter < __fmul_rn(__fmul_rn(thr, den), 0.999999f)) return false;
+    return suppresses(bi, ai, bj, aj, thr);
+}
+
 // TV/TA/TC != 0 fix version / boxes per cell / classes at compile time (index arithmetic folds,
 // divisions become multiplies); 0 keeps them as run-time values from the geometry.
 // IMG: the image's whole slice of the head tensor is staged in shared memory by kGroups bulk copies
@@ -310,8 +323,8 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
     float* stage = reinterpret_cast<float*>(smem_raw);
     unsigned char* cand_smem = smem_raw + p.stage_bytes;
     Cand ca = carve(cand_smem, kSmemCand);
-    Cand cw = ca;  // workspace copy for images that overflow shared memory
-    if (p.ws) cw = carve(p.ws + (size_t)img * p.ws_per_image, P);
+    // workspace copy for images that overflow shared memory (carved where it is needed: the common case never is)
+    auto carve_ws = [&]() -> Cand { return p.ws ? carve(p.ws + (size_t)img * p.ws_per_image, P) : ca; };
 
     NT(0);
     if (IMG) {  // the single-tile path sets suppression bits with atomicOr
@@ -403,27 +416,40 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
             const int wend = (int)min((long long)(fsh + p.img_floats), lim4 + fsh);
             if (tid < fsh + p.img_floats - wend) stage[wend + tid] = __ldg(yimg + (wend - fsh) + tid);
         }
+        // one warp of the group polls the mbarrier, the others sleep on a hardware barrier (a polling warp
+        // takes issue slots from the CTA next door); their own test afterwards succeeds at once and makes
+        // the bulk copy's bytes visible to them
+        if (gtid < 32) yh_mbar_wait(&bar_img[grp], 0);
+        asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kGroupThreads) : "memory");
         yh_mbar_wait(&bar_img[grp], 0);
-        for (int base = i_lo; base < i_hi; base += kGroupThreads) {  // (warp-uniform trip count)
-            const int i = base + gtid;
-            float conf = 0.f;
-            bool pass = false;
-            if (i < i_hi) {
-                const float t = win[fsh + box_off(i) + 4];
-                if (!(t < p.to_reject)) {  // far below the threshold: sigmoid not needed
-                    conf = yh_sigmoid(t);
-                    pass = conf >= p.conf_thre;  // models/utils.py:92
-                }
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, pass);
-            if (bal) {
+        // conf >= conf_thre is decided on the logit wherever that is safe (to_reject / to_accept leave a
+        // band around logit(conf_thre) in which the sigmoid is evaluated); survivors are listed with
+        // their LOGIT -- the sigmoid of the ~50 survivors is taken later by as many threads, instead
+        // of here by every warp that holds one
+        for (int base = i_lo; base < i_hi; base += 2 * kGroupThreads) {  // (warp-uniform trip count)
+            const int i0 = base + gtid, i1 = i0 + kGroupThreads;
+            float t0 = __int_as_float(0x7fc00000), t1 = t0;  // (idle lanes: NaN fails every test below)
+            if (i0 < i_hi) t0 = win[fsh + box_off(i0) + 4];
+            if (i1 < i_hi) t1 = win[fsh + box_off(i1) + 4];
+            bool pass0 = t0 >= p.to_accept, pass1 = t1 >= p.to_accept;
+            if (!pass0 && t0 >= p.to_reject) pass0 = yh_sigmoid(t0) >= p.conf_thre;  // models/utils.py:92
+            if (!pass1 && t1 >= p.to_reject) pass1 = yh_sigmoid(t1) >= p.conf_thre;
+            const unsigned bal0 = __ballot_sync(0xffffffffu, pass0), bal1 = __ballot_sync(0xffffffffu, pass1);
+            if (bal0 | bal1) {
                 int slot0 = 0;
-                if (lane == 0) slot0 = atomicAdd(&s_count, __popc(bal));
+                if (lane == 0)
+                    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(slot0) : "r"(yh_smem_u32(&s_count)), "r"(__popc(bal0) + __popc(bal1)) : "memory");
                 slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-                if (pass) {
-                    const int slot = slot0 + __popc(bal & ((1u << lane) - 1u));
-                    if (slot < kSmemCand) { ca.u_conf[slot] = conf; ca.u_idx[slot] = i; }
-                    else { cw.u_conf[slot] = conf; cw.u_idx[slot] = i; }
+                const unsigned below = (1u << lane) - 1u;
+                if (pass0) {
+                    const int slot = slot0 + __popc(bal0 & below);
+                    if (slot < kSmemCand) reinterpret_cast<int2*>(ca.u_conf)[slot] = make_int2(__float_as_int(t0), i0);
+                    else { const Cand cw = carve_ws(); cw.u_conf[slot] = t0; cw.u_idx[slot] = i0; }
+                }
+                if (pass1) {
+                    const int slot = slot0 + __popc(bal0) + __popc(bal1 & below);
+                    if (slot < kSmemCand) reinterpret_cast<int2*>(ca.u_conf)[slot] = make_int2(__float_as_int(t1), i1);
+                    else { const Cand cw = carve_ws(); cw.u_conf[slot] = t1; cw.u_idx[slot] = i1; }
                 }
             }
         }
@@ -460,7 +486,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
                 if (pass) {
                     const int slot = slot0 + __popc(bal & ((1u << lane) - 1u));
                     if (slot < kSmemCand) { ca.u_conf[slot] = conf; ca.u_idx[slot] = i; }
-                    else { cw.u_conf[slot] = conf; cw.u_idx[slot] = i; }
+                    else { const Cand cw = carve_ws(); cw.u_conf[slot] = conf; cw.u_idx[slot] = i; }
                     if (head && slot < p.stage_slots) {
                         float* dst = stage + (size_t)slot * p.slot_floats;
                         if (v2) {
@@ -491,8 +517,31 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
 
     const int K = s_count;
     const bool overflow = K > kSmemCand;
+    Cand cw = ca;
+    int2* const pairs = reinterpret_cast<int2*>(ca.u_conf);  // IMG: (u_conf | u_idx) hold 64-bit entries instead
     if (overflow) {  // continue in the workspace arrays
-        for (int k = tid; k < kSmemCand; k += kThreads) { cw.u_conf[k] = ca.u_conf[k]; cw.u_idx[k] = ca.u_idx[k]; }
+        cw = carve_ws();
+        if (IMG) {
+            // phase A left (logit, predictor) pairs: confidence = sigmoid(logit), into the separate arrays
+            for (int k = tid; k < K; k += kThreads) {
+                float t;
+                int i;
+                if (k < kSmemCand) { t = __int_as_float(pairs[k].x); i = pairs[k].y; }
+                else { t = cw.u_conf[k]; i = cw.u_idx[k]; }
+                cw.u_conf[k] = yh_sigmoid(t);
+                cw.u_idx[k] = i;
+            }
+        } else {
+            for (int k = tid; k < kSmemCand; k += kThreads) { cw.u_conf[k] = ca.u_conf[k]; cw.u_idx[k] = ca.u_idx[k]; }
+        }
+        __syncthreads();
+    } else if (IMG) {
+        // (logit, predictor) -> sort key: confidence bits in the high word (positive floats order like
+        // integers), complement of the predictor index in the low word (ties: lower index first)
+        for (int k = tid; k < K; k += kThreads) {
+            const int2 e = pairs[k];
+            pairs[k] = make_int2(~e.y, __float_as_int(yh_sigmoid(__int_as_float(e.x))));
+        }
         __syncthreads();
     }
 
@@ -767,26 +816,19 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
             const int k = tid >> 1, ax = tid & 1;  // candidate, axis
             if ((tid & ~31) < 2 * K) {  // (whole warps)
                 const bool on = k < K;
-                const float ck = on ? ca.u_conf[k] : 0.f;
-                const int ik = on ? ca.u_idx[k] : 0;
+                const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(ca.u_conf);
+                const unsigned long long kk = on ? keys[k] : 0ull;
+                const float ck = __int_as_float((int)(kk >> 32));
+                const int ik = (int)~(unsigned)kk;
                 int rank = 0;
-                const float4* c4 = reinterpret_cast<const float4*>(ca.u_conf);
-                const int4* i4 = reinterpret_cast<const int4*>(ca.u_idx);
-                const int K4 = K >> 2;
-                for (int q = ax; q < K4; q += 2) {
-                    const float4 cj = c4[q];
-                    const int4 ij = i4[q];
-                    rank += (cj.x > ck || (cj.x == ck && ij.x < ik)) ? 1 : 0;
-                    rank += (cj.y > ck || (cj.y == ck && ij.y < ik)) ? 1 : 0;
-                    rank += (cj.z > ck || (cj.z == ck && ij.z < ik)) ? 1 : 0;
-                    rank += (cj.w > ck || (cj.w == ck && ij.w < ik)) ? 1 : 0;
+                const ulonglong2* k2 = reinterpret_cast<const ulonglong2*>(ca.u_conf);
+                const int K2 = K >> 1;
+                for (int q = ax; q < K2; q += 2) {  // (keys are unique: the predictor index is part of them)
+                    const ulonglong2 kj = k2[q];
+                    rank += kj.x > kk ? 1 : 0;
+                    rank += kj.y > kk ? 1 : 0;
                 }
-                if (ax == 0) {
-                    for (int j = 4 * K4; j < K; ++j) {
-                        const float cj = ca.u_conf[j];
-                        rank += (cj > ck || (cj == ck && ca.u_idx[j] < ik)) ? 1 : 0;
-                    }
-                }
+                if (ax == 0 && (K & 1)) rank += keys[K - 1] > kk ? 1 : 0;
                 rank += __shfl_xor_sync(0xffffffffu, rank, 1);
                 // this lane's axis of the box: lo/hi corner coordinate (same roundings as yh_decode_box)
                 float lo = 0.f, hi = 0.f;
@@ -840,6 +882,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
 
         // ---------------- D: greedy suppression (one tile) ----------------
         const float thr = p.iou_thre;
+        const bool thr_pos = thr > 0.f;
         const int tn = K;
         const int W = (tn + 31) >> 5;
         {
@@ -851,7 +894,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
                 const int i = c >= r ? r : Ke - 1 - r;
                 const int j = c >= r ? c + 1 : Ke - 1 - c;
                 if (j < K) {
-                    bool bit = suppresses(ca.s_box[i], ca.s_area[i], ca.s_box[j], ca.s_area[j], thr);
+                    bool bit = suppresses_dense(ca.s_box[i], ca.s_area[i], ca.s_box[j], ca.s_area[j], thr, thr_pos);
                     if (use_lab) bit = bit && ca.s_lab[i] == ca.s_lab[j];
                     if (bit) atomicOr(&mask[j * kTileWords + (i >> 5)], 1u << (i & 31));
                 }
@@ -1032,9 +1075,17 @@ int postprocess_impl(int version, const float* y, int n, int s_h, int s_w, int a
     p.n = n; p.p = p.g.preds; p.c = c;
     p.conf_thre = conf_thre; p.iou_thre = iou_thre;
     // sigmoid(t) >= thr needs t >= logit(thr) up to a few ulp; reject only with a wide margin
+    // (the margins are in logit units: 1e-3 there moves the sigmoid by 1e-3 * conf * (1 - conf), >= 1e-5 for
+    // thresholds in [0.01, 0.99] -- far beyond the few ulp of expf and the division; outside that range only a
+    // wide reject margin is used and every other logit takes the sigmoid)
+    p.to_accept = INFINITY;
     if (!(conf_thre > 0.f)) p.to_reject = -INFINITY;          // everything passes (or thr is NaN)
     else if (conf_thre > 1.f) p.to_reject = INFINITY;         // nothing can pass
-    else {
+    else if (conf_thre >= 0.01f && conf_thre <= 0.99f) {
+        const double t = log((double)conf_thre / (1.0 - (double)conf_thre));
+        p.to_reject = (float)(t - 1e-3);
+        p.to_accept = (float)(t + 1e-3);
+    } else {
         const double t = conf_thre < 0.9999999 ? log((double)conf_thre / (1.0 - (double)conf_thre)) : 16.0;
         p.to_reject = (float)((t < 16.0 ? t : 16.0) - 0.01);
     }
