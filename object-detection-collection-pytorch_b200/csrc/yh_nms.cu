@@ -140,6 +140,14 @@ __device__ __forceinline__ Cand carve(unsigned char* base, int cap) {
     return a;
 }
 
+// Candidate beyond the shared-memory lists -> the image's workspace arrays (rare: kept out of line so that
+// its 64-bit address arithmetic is not hoisted into the common path).
+__device__ __noinline__ void overflow_put(unsigned char* ws_img, int cap, int slot, float conf, int idx) {
+    const Cand cw = carve(ws_img, cap);
+    cw.u_conf[slot] = conf;
+    cw.u_idx[slot] = idx;
+}
+
 // Class pick of one predictor by a group of G adjacent lanes (32 / G predictors per warp at a time):
 // softmax over its C logits, cls_spec = p * conf (reference models/yolov2.py:625-640),
 // label = first argmax of cls_spec, score = its max (models/yolov2.py:726-731).  Optionally stores
@@ -230,30 +238,23 @@ __device__ __forceinline__ void quad_class_pick_fast(const float* cl, int C, flo
     }
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-    float se = 0.f;
+    // this lane's class that can be the maximum (more than one: the caller takes the full pick)
+    const float near_ = mx - 1e-4f;
+    float se = 0.f, eb = -1.f;
+    int cb = 1 << 30, ncand = 0;
 #pragma unroll
     for (int k = 0; k < kPickRegs; ++k) {
         const int c = sub + 4 * k;
         if (c < C) {  // (uniform per k for the lanes of a group up to the last k)
-            const float near_ = l[k];
-            l[k] = expf(l[k] - mx);
-            se += l[k];
-            if (!(near_ >= mx - 1e-4f)) l[k] = -1.f;  // cannot be the maximum: no division
-        } else {
-            l[k] = -1.f;
+            const float e = expf(l[k] - mx);
+            se += e;
+            if (l[k] >= near_) { eb = e; cb = c; ++ncand; }
         }
     }
     se += __shfl_xor_sync(0xffffffffu, se, 1);
     se += __shfl_xor_sync(0xffffffffu, se, 2);
-    float bv = -INFINITY;
-    int bi = 1 << 30;
-#pragma unroll
-    for (int k = 0; k < kPickRegs; ++k) {
-        if (l[k] >= 0.f) {
-            const float sp = __fmul_rn(__fdiv_rn(l[k], se), conf);
-            if (sp > bv) { bv = sp; bi = sub + 4 * k; }  // first max per lane (c ascending)
-        }
-    }
+    float bv = ncand ? __fmul_rn(__fdiv_rn(eb, se), conf) : -INFINITY;
+    int bi = cb;
 #pragma unroll
     for (int o = 1; o < 4; o <<= 1) {
         const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
@@ -262,7 +263,7 @@ __device__ __forceinline__ void quad_class_pick_fast(const float* cl, int C, flo
     }
     *label = bi;
     *score = bv;
-    *ok = !active || (se < INFINITY && bv >= 1e-30f && bv < INFINITY);  // (false for NaN)
+    *ok = !active || (ncand <= 1 && se < INFINITY && bv >= 1e-30f && bv < INFINITY);  // (false for NaN)
 }
 
 // bit = "box i suppresses box j": iou(i, j) >= thr with the reference's arithmetic
@@ -412,7 +413,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
         const int grp = tid / kGroupThreads, gtid = tid - grp * kGroupThreads;
         const int upp = v2 ? 1 : A;  // predictors per unit
         const int i_lo = ((img_units * grp) / kGroups) * upp, i_hi = ((img_units * (grp + 1)) / kGroups) * upp;
-        {   // floats past the last whole 16 bytes of the tensor (last image only): plain loads
+        if (img == p.n - 1) {  // floats past the last whole 16 bytes of the tensor: plain loads
             const int wend = (int)min((long long)(fsh + p.img_floats), lim4 + fsh);
             if (tid < fsh + p.img_floats - wend) stage[wend + tid] = __ldg(yimg + (wend - fsh) + tid);
         }
@@ -444,12 +445,12 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
                 if (pass0) {
                     const int slot = slot0 + __popc(bal0 & below);
                     if (slot < kSmemCand) reinterpret_cast<int2*>(ca.u_conf)[slot] = make_int2(__float_as_int(t0), i0);
-                    else { const Cand cw = carve_ws(); cw.u_conf[slot] = t0; cw.u_idx[slot] = i0; }
+                    else overflow_put(p.ws + (size_t)img * p.ws_per_image, P, slot, t0, i0);
                 }
                 if (pass1) {
                     const int slot = slot0 + __popc(bal0) + __popc(bal1 & below);
                     if (slot < kSmemCand) reinterpret_cast<int2*>(ca.u_conf)[slot] = make_int2(__float_as_int(t1), i1);
-                    else { const Cand cw = carve_ws(); cw.u_conf[slot] = t1; cw.u_idx[slot] = i1; }
+                    else overflow_put(p.ws + (size_t)img * p.ws_per_image, P, slot, t1, i1);
                 }
             }
         }
@@ -486,7 +487,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
                 if (pass) {
                     const int slot = slot0 + __popc(bal & ((1u << lane) - 1u));
                     if (slot < kSmemCand) { ca.u_conf[slot] = conf; ca.u_idx[slot] = i; }
-                    else { const Cand cw = carve_ws(); cw.u_conf[slot] = conf; cw.u_idx[slot] = i; }
+                    else overflow_put(p.ws + (size_t)img * p.ws_per_image, P, slot, conf, i);
                     if (head && slot < p.stage_slots) {
                         float* dst = stage + (size_t)slot * p.slot_floats;
                         if (v2) {
@@ -517,8 +518,227 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
 
     const int K = s_count;
     const bool overflow = K > kSmemCand;
-    Cand cw = ca;
+    const bool with_labels = head ? (p.class_aware != 0) : (p.labels != nullptr);
     int2* const pairs = reinterpret_cast<int2*>(ca.u_conf);  // IMG: (u_conf | u_idx) hold 64-bit entries instead
+
+    // Whole-image mode with at most one tile of candidates, all in shared memory: the lean path.  The
+    // kernel's tail is bound by instruction issue (two CTAs per SM, and the next kernel of the stream
+    // streaming next to them), so every phase is laid out for few warp instructions:
+    //   B  two lanes per candidate: each counts half of the candidates that beat it (16-byte loads of
+    //      the unsorted lists), then decodes one axis of the box (x: tx, tw; y: ty, th);
+    //   D  the i < j pairs are enumerated densely over all threads (the triangle folded into a
+    //      K/2 x (K-1) rectangle), set bits go to the mask with atomicOr (rare), then the fixed-point
+    //      resolution of the greedy order by one warp, as in the general path;
+    //   E  four lanes per kept box, class pick without the divisions that cannot matter.
+    auto rest_img = [&](auto lab_tag) {
+        constexpr bool LAB = decltype(lab_tag)::value;
+        const float* win = reinterpret_cast<const float*>(smem_raw);
+        Cand ca = carve(smem_raw + p.stage_bytes, kSmemCand);
+        const bool use_lab = LAB && p.class_aware != 0;
+
+        // ---------------- B: rank + decode ----------------
+        {
+            const int k = tid >> 1, ax = tid & 1;  // candidate, axis
+            if ((tid & ~31) < 2 * K) {  // (whole warps)
+                const bool on = k < K;
+                const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(ca.u_conf);
+                const unsigned long long kk = on ? keys[k] : 0ull;
+                const float ck = __int_as_float((int)(kk >> 32));
+                const int ik = (int)~(unsigned)kk;
+                int rank = 0;
+                const ulonglong2* k2 = reinterpret_cast<const ulonglong2*>(ca.u_conf);
+                const int K2 = K >> 1;
+                for (int q = ax; q < K2; q += 2) {  // (keys are unique: the predictor index is part of them)
+                    const ulonglong2 kj = k2[q];
+                    rank += kj.x > kk ? 1 : 0;
+                    rank += kj.y > kk ? 1 : 0;
+                }
+                if (ax == 0 && (K & 1)) rank += keys[K - 1] > kk ? 1 : 0;
+                rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+                // this lane's axis of the box: lo/hi corner coordinate (same roundings as yh_decode_box)
+                float lo = 0.f, hi = 0.f;
+                if (on) {
+                    const float* row = win + (fsh + box_off(ik));
+                    const float tc = row[ax], ts = row[2 + ax];
+                    const float sc = yh_sigmoid(tc);
+                    const float sa = v2 ? expf(ts) : yh_sigmoid(ts);
+                    const int cell = ik / A, a = ik - cell * A;
+                    const int cy = (int)__umulhi((unsigned)cell, p.magic_sw), cx = cell - cy * g.s_w;  // cell / s_w
+                    const float bsz = __fmul_rn(ax ? g.ph[a] : g.pw[a], sa);
+                    const float bc = __fadd_rn(sc, (float)(ax ? cy : cx));
+                    const float hs = __fmul_rn(bsz, 0.5f);
+                    const float gsz = ax ? g.gh : g.gw;
+                    lo = __fmul_rn(__fsub_rn(bc, hs), gsz);
+                    hi = __fmul_rn(__fadd_rn(bc, hs), gsz);
+                }
+                const float olo = __shfl_xor_sync(0xffffffffu, lo, 1), ohi = __shfl_xor_sync(0xffffffffu, hi, 1);
+                if (on && ax == 0) {
+                    ca.s_box[rank] = make_float4(lo, olo, hi, ohi);
+                    ca.s_area[rank] = __fmul_rn(__fsub_rn(hi, lo), __fsub_rn(ohi, olo));
+                    ca.s_idx[rank] = ik;
+                    ca.s_conf[rank] = ck;
+                }
+            }
+        }
+        __syncthreads();
+        NT(4);
+
+        constexpr int kPick = 4;  // lanes per class pick
+        const int sub = tid & (kPick - 1);
+        // label and score of ranked candidate / kept box: fast pick, the full one where it does not apply
+        // (`with_spec` is uniform over the warp: both functions shuffle across all 32 lanes)
+        auto pick = [&](const float* cl, float conf, bool act, bool with_spec, float* spec_out, int* lab, float* sc) {
+            bool ok = false;
+            if (C <= 4 * kPickRegs && !with_spec) quad_class_pick_fast(cl, C, conf, sub, act, lab, sc, &ok);
+            if (!__all_sync(0xffffffffu, ok)) group_class_pick<kPick>(cl, C, conf, sub, act, spec_out, lab, sc);
+        };
+        if (use_lab) {  // label of every candidate (argmax of cls_spec)
+            for (int k0 = 0; k0 < K; k0 += kThreads / kPick) {
+                if (k0 + (32 / kPick) * warp >= K) break;
+                const int k = k0 + tid / kPick;
+                const bool act = k < K;
+                int lab;
+                float sc;
+                pick(act ? win + (fsh + cls_off(ca.s_idx[k])) : nullptr, act ? ca.s_conf[k] : 0.f, act, false, nullptr, &lab, &sc);
+                if (act && sub == 0) ca.s_lab[k] = lab;
+            }
+            __syncthreads();
+        }
+
+        // ---------------- D: greedy suppression (one tile) ----------------
+        const float thr = p.iou_thre;
+        const bool thr_pos = thr > 0.f;
+        const int tn = K;
+        const int W = (tn + 31) >> 5;
+        {
+            const int Ke = K + (K & 1), cols = Ke - 1, total = (Ke >> 1) * cols;
+            const unsigned magic = cols > 1 ? (unsigned)(0xFFFFFFFFu / (unsigned)cols) + 1u : 0u;  // pair / cols, pair < 2^16
+            for (int pr = tid; pr < total; pr += kThreads) {
+                const int r = cols > 1 ? (int)__umulhi((unsigned)pr, magic) : pr;
+                const int c = pr - r * cols;
+                const int i = c >= r ? r : Ke - 1 - r;
+                const int j = c >= r ? c + 1 : Ke - 1 - c;
+                if (j < K) {
+                    bool bit = suppresses_dense(ca.s_box[i], ca.s_area[i], ca.s_box[j], ca.s_area[j], thr, thr_pos);
+                    if (use_lab) bit = bit && ca.s_lab[i] == ca.s_lab[j];
+                    if (bit) atomicOr(&mask[j * kTileWords + (i >> 5)], 1u << (i & 31));
+                }
+            }
+        }
+        __syncthreads();
+        NT(7);
+        if (warp == 0) {
+            unsigned alive[kTileWords], dead0[kTileWords];
+#pragma unroll
+            for (int w = 0; w < kTileWords; ++w) {
+                dead0[w] = w < W ? 0u : 0xffffffffu;
+                if (w == W - 1 && (tn & 31)) dead0[w] |= ~0u << (tn & 31);  // bits past the tile end
+                alive[w] = ~dead0[w];
+            }
+            if (W <= 2) {
+                // common case (<= 64 candidates): the lane's two columns live in registers
+                const unsigned c00 = lane < tn ? mask[lane * kTileWords] : 0u;
+                const unsigned c10 = 32 + lane < tn ? mask[(32 + lane) * kTileWords] : 0u;
+                const unsigned c11 = 32 + lane < tn ? mask[(32 + lane) * kTileWords + 1] : 0u;
+                for (int sweep = 0; sweep <= tn; ++sweep) {
+                    const unsigned n0 = __ballot_sync(0xffffffffu, (c00 & alive[0]) == 0u) & ~dead0[0];
+                    const unsigned n1 = __ballot_sync(0xffffffffu, ((c10 & n0) | (c11 & alive[1])) == 0u) & ~dead0[1];
+                    const bool same = n0 == alive[0] && n1 == alive[1];
+                    alive[0] = n0;
+                    alive[1] = n1;
+                    if (same) break;
+                }
+            } else {
+                for (int sweep = 0; sweep <= tn; ++sweep) {
+                    bool changed = false;
+#pragma unroll
+                    for (int m = 0; m < kTileWords; ++m) {
+                        if (m < W) {  // (warp-uniform)
+                            const int j = 32 * m + lane;
+                            bool a = false;
+                            if (j < tn) {
+                                unsigned hit = 0u;
+#pragma unroll
+                                for (int w = 0; w < kTileWords; ++w)
+                                    if (w <= m) hit |= mask[j * kTileWords + w] & alive[w];
+                                a = hit == 0u;
+                            }
+                            const unsigned nw = __ballot_sync(0xffffffffu, a) & ~dead0[m];
+                            changed = changed || nw != alive[m];
+                            alive[m] = nw;  // (later words of this sweep already see it)
+                        }
+                    }
+                    if (!changed) break;
+                }
+            }
+            int kept_n = 0;
+#pragma unroll
+            for (int m = 0; m < kTileWords; ++m) {
+                if (m < W) {
+                    if ((alive[m] >> lane) & 1u) ca.keep[kept_n + __popc(alive[m] & ((1u << lane) - 1u))] = 32 * m + lane;
+                    kept_n += __popc(alive[m]);
+                }
+            }
+            if (lane == 0) s_kept = kept_n;
+        }
+        __syncthreads();
+        NT(8);
+
+        NT(12);
+        // ---------------- E: emit ----------------
+        const int kept = s_kept;
+        if (tid == 0) p.keep_cnt[img] = kept;
+        const int nout = min(kept, p.max_out);
+        const bool want_cls = p.out_cls_spec || p.out_label || p.out_score;
+        for (int t0 = 0; t0 < nout; t0 += kThreads / kPick) {
+            if (t0 + (32 / kPick) * warp >= nout) break;
+            const int t = t0 + tid / kPick;
+            const bool act = t < nout;
+            int i = 0, idx = 0;
+            float conf = 0.f;
+            size_t o = 0;
+            if (act) {
+                i = ca.keep[t];
+                idx = ca.s_idx[i];
+                conf = ca.s_conf[i];
+                o = (size_t)img * p.max_out + t;
+                if (sub == 0) {
+                    p.keep_idx[o] = idx;
+                    if (p.out_conf) p.out_conf[o] = conf;
+                } else if (sub == 1) {
+                    if (p.out_bbox) p.out_bbox[o] = ca.s_box[i];
+                }
+            }
+            if (want_cls) {
+                int lab;
+                float sc;
+                pick(act ? win + (fsh + cls_off(idx)) : nullptr, conf, act, p.out_cls_spec != nullptr,
+                     (act && p.out_cls_spec) ? p.out_cls_spec + o * C : nullptr, &lab, &sc);
+                if (act && sub == 2) {
+                    if (p.out_label) p.out_label[o] = lab;
+                    if (p.out_score) p.out_score[o] = sc;
+                }
+            }
+        }
+        NT(13);
+    };
+
+    if (IMG && !overflow) {
+        // the common case first, and out of the way of everything below
+        // (logit, predictor) -> sort key: confidence bits in the high word (positive floats order like
+        // integers), complement of the predictor index in the low word (ties: lower index first)
+        for (int k = tid; k < K; k += kThreads) {
+            const int2 e = pairs[k];
+            pairs[k] = make_int2(~e.y, __float_as_int(yh_sigmoid(__int_as_float(e.x))));
+        }
+        __syncthreads();
+        if (!with_labels) rest_img(FastTag<false>{});
+        else rest_img(FastTag<true>{});
+        if (p.late_wait) yh_grid_dependency_wait();  // (see the end of the kernel)
+        return;
+    }
+
+    Cand cw = ca;
     if (overflow) {  // continue in the workspace arrays
         cw = carve_ws();
         if (IMG) {
@@ -533,14 +753,6 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
             }
         } else {
             for (int k = tid; k < kSmemCand; k += kThreads) { cw.u_conf[k] = ca.u_conf[k]; cw.u_idx[k] = ca.u_idx[k]; }
-        }
-        __syncthreads();
-    } else if (IMG) {
-        // (logit, predictor) -> sort key: confidence bits in the high word (positive floats order like
-        // integers), complement of the predictor index in the low word (ties: lower index first)
-        for (int k = tid; k < K; k += kThreads) {
-            const int2 e = pairs[k];
-            pairs[k] = make_int2(~e.y, __float_as_int(yh_sigmoid(__int_as_float(e.x))));
         }
         __syncthreads();
     }
@@ -796,212 +1008,8 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
         NT(13);
     };
 
-    // Whole-image mode with at most one tile of candidates, all in shared memory: the lean path.  The
-    // kernel's tail is bound by instruction issue (two CTAs per SM, and the next kernel of the stream
-    // streaming next to them), so every phase is laid out for few warp instructions:
-    //   B  two lanes per candidate: each counts half of the candidates that beat it (16-byte loads of
-    //      the unsorted lists), then decodes one axis of the box (x: tx, tw; y: ty, th);
-    //   D  the i < j pairs are enumerated densely over all threads (the triangle folded into a
-    //      K/2 x (K-1) rectangle), set bits go to the mask with atomicOr (rare), then the fixed-point
-    //      resolution of the greedy order by one warp, as in the general path;
-    //   E  four lanes per kept box, class pick without the divisions that cannot matter.
-    auto rest_img = [&](auto lab_tag) {
-        constexpr bool LAB = decltype(lab_tag)::value;
-        const float* win = reinterpret_cast<const float*>(smem_raw);
-        Cand ca = carve(smem_raw + p.stage_bytes, kSmemCand);
-        const bool use_lab = LAB && p.class_aware != 0;
-
-        // ---------------- B: rank + decode ----------------
-        {
-            const int k = tid >> 1, ax = tid & 1;  // candidate, axis
-            if ((tid & ~31) < 2 * K) {  // (whole warps)
-                const bool on = k < K;
-                const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(ca.u_conf);
-                const unsigned long long kk = on ? keys[k] : 0ull;
-                const float ck = __int_as_float((int)(kk >> 32));
-                const int ik = (int)~(unsigned)kk;
-                int rank = 0;
-                const ulonglong2* k2 = reinterpret_cast<const ulonglong2*>(ca.u_conf);
-                const int K2 = K >> 1;
-                for (int q = ax; q < K2; q += 2) {  // (keys are unique: the predictor index is part of them)
-                    const ulonglong2 kj = k2[q];
-                    rank += kj.x > kk ? 1 : 0;
-                    rank += kj.y > kk ? 1 : 0;
-                }
-                if (ax == 0 && (K & 1)) rank += keys[K - 1] > kk ? 1 : 0;
-                rank += __shfl_xor_sync(0xffffffffu, rank, 1);
-                // this lane's axis of the box: lo/hi corner coordinate (same roundings as yh_decode_box)
-                float lo = 0.f, hi = 0.f;
-                if (on) {
-                    const float* row = win + (fsh + box_off(ik));
-                    const float tc = row[ax], ts = row[2 + ax];
-                    const float sc = yh_sigmoid(tc);
-                    const float sa = v2 ? expf(ts) : yh_sigmoid(ts);
-                    const int cell = ik / A, a = ik - cell * A;
-                    const int cy = (int)__umulhi((unsigned)cell, p.magic_sw), cx = cell - cy * g.s_w;  // cell / s_w
-                    const float bsz = __fmul_rn(ax ? g.ph[a] : g.pw[a], sa);
-                    const float bc = __fadd_rn(sc, (float)(ax ? cy : cx));
-                    const float hs = __fmul_rn(bsz, 0.5f);
-                    const float gsz = ax ? g.gh : g.gw;
-                    lo = __fmul_rn(__fsub_rn(bc, hs), gsz);
-                    hi = __fmul_rn(__fadd_rn(bc, hs), gsz);
-                }
-                const float olo = __shfl_xor_sync(0xffffffffu, lo, 1), ohi = __shfl_xor_sync(0xffffffffu, hi, 1);
-                if (on && ax == 0) {
-                    ca.s_box[rank] = make_float4(lo, olo, hi, ohi);
-                    ca.s_area[rank] = __fmul_rn(__fsub_rn(hi, lo), __fsub_rn(ohi, olo));
-                    ca.s_idx[rank] = ik;
-                    ca.s_conf[rank] = ck;
-                }
-            }
-        }
-        __syncthreads();
-        NT(4);
-
-        constexpr int kPick = 4;  // lanes per class pick
-        const int sub = tid & (kPick - 1);
-        // label and score of ranked candidate / kept box: fast pick, the full one where it does not apply
-        // (`with_spec` is uniform over the warp: both functions shuffle across all 32 lanes)
-        auto pick = [&](const float* cl, float conf, bool act, bool with_spec, float* spec_out, int* lab, float* sc) {
-            bool ok = false;
-            if (C <= 4 * kPickRegs && !with_spec) quad_class_pick_fast(cl, C, conf, sub, act, lab, sc, &ok);
-            if (!__all_sync(0xffffffffu, ok)) group_class_pick<kPick>(cl, C, conf, sub, act, spec_out, lab, sc);
-        };
-        if (use_lab) {  // label of every candidate (argmax of cls_spec)
-            for (int k0 = 0; k0 < K; k0 += kThreads / kPick) {
-                if (k0 + (32 / kPick) * warp >= K) break;
-                const int k = k0 + tid / kPick;
-                const bool act = k < K;
-                int lab;
-                float sc;
-                pick(act ? win + (fsh + cls_off(ca.s_idx[k])) : nullptr, act ? ca.s_conf[k] : 0.f, act, false, nullptr, &lab, &sc);
-                if (act && sub == 0) ca.s_lab[k] = lab;
-            }
-            __syncthreads();
-        }
-
-        // ---------------- D: greedy suppression (one tile) ----------------
-        const float thr = p.iou_thre;
-        const bool thr_pos = thr > 0.f;
-        const int tn = K;
-        const int W = (tn + 31) >> 5;
-        {
-            const int Ke = K + (K & 1), cols = Ke - 1, total = (Ke >> 1) * cols;
-            const unsigned magic = cols > 1 ? (unsigned)(0xFFFFFFFFu / (unsigned)cols) + 1u : 0u;  // pair / cols, pair < 2^16
-            for (int pr = tid; pr < total; pr += kThreads) {
-                const int r = cols > 1 ? (int)__umulhi((unsigned)pr, magic) : pr;
-                const int c = pr - r * cols;
-                const int i = c >= r ? r : Ke - 1 - r;
-                const int j = c >= r ? c + 1 : Ke - 1 - c;
-                if (j < K) {
-                    bool bit = suppresses_dense(ca.s_box[i], ca.s_area[i], ca.s_box[j], ca.s_area[j], thr, thr_pos);
-                    if (use_lab) bit = bit && ca.s_lab[i] == ca.s_lab[j];
-                    if (bit) atomicOr(&mask[j * kTileWords + (i >> 5)], 1u << (i & 31));
-                }
-            }
-        }
-        __syncthreads();
-        NT(7);
-        if (warp == 0) {
-            unsigned alive[kTileWords], dead0[kTileWords];
-#pragma unroll
-            for (int w = 0; w < kTileWords; ++w) {
-                dead0[w] = w < W ? 0u : 0xffffffffu;
-                if (w == W - 1 && (tn & 31)) dead0[w] |= ~0u << (tn & 31);  // bits past the tile end
-                alive[w] = ~dead0[w];
-            }
-            if (W <= 2) {
-                // common case (<= 64 candidates): the lane's two columns live in registers
-                const unsigned c00 = lane < tn ? mask[lane * kTileWords] : 0u;
-                const unsigned c10 = 32 + lane < tn ? mask[(32 + lane) * kTileWords] : 0u;
-                const unsigned c11 = 32 + lane < tn ? mask[(32 + lane) * kTileWords + 1] : 0u;
-                for (int sweep = 0; sweep <= tn; ++sweep) {
-                    const unsigned n0 = __ballot_sync(0xffffffffu, (c00 & alive[0]) == 0u) & ~dead0[0];
-                    const unsigned n1 = __ballot_sync(0xffffffffu, ((c10 & n0) | (c11 & alive[1])) == 0u) & ~dead0[1];
-                    const bool same = n0 == alive[0] && n1 == alive[1];
-                    alive[0] = n0;
-                    alive[1] = n1;
-                    if (same) break;
-                }
-            } else {
-                for (int sweep = 0; sweep <= tn; ++sweep) {
-                    bool changed = false;
-#pragma unroll
-                    for (int m = 0; m < kTileWords; ++m) {
-                        if (m < W) {  // (warp-uniform)
-                            const int j = 32 * m + lane;
-                            bool a = false;
-                            if (j < tn) {
-                                unsigned hit = 0u;
-#pragma unroll
-                                for (int w = 0; w < kTileWords; ++w)
-                                    if (w <= m) hit |= mask[j * kTileWords + w] & alive[w];
-                                a = hit == 0u;
-                            }
-                            const unsigned nw = __ballot_sync(0xffffffffu, a) & ~dead0[m];
-                            changed = changed || nw != alive[m];
-                            alive[m] = nw;  // (later words of this sweep already see it)
-                        }
-                    }
-                    if (!changed) break;
-                }
-            }
-            int kept_n = 0;
-#pragma unroll
-            for (int m = 0; m < kTileWords; ++m) {
-                if (m < W) {
-                    if ((alive[m] >> lane) & 1u) ca.keep[kept_n + __popc(alive[m] & ((1u << lane) - 1u))] = 32 * m + lane;
-                    kept_n += __popc(alive[m]);
-                }
-            }
-            if (lane == 0) s_kept = kept_n;
-        }
-        __syncthreads();
-        NT(8);
-
-        NT(12);
-        // ---------------- E: emit ----------------
-        const int kept = s_kept;
-        if (tid == 0) p.keep_cnt[img] = kept;
-        const int nout = min(kept, p.max_out);
-        const bool want_cls = p.out_cls_spec || p.out_label || p.out_score;
-        for (int t0 = 0; t0 < nout; t0 += kThreads / kPick) {
-            if (t0 + (32 / kPick) * warp >= nout) break;
-            const int t = t0 + tid / kPick;
-            const bool act = t < nout;
-            int i = 0, idx = 0;
-            float conf = 0.f;
-            size_t o = 0;
-            if (act) {
-                i = ca.keep[t];
-                idx = ca.s_idx[i];
-                conf = ca.s_conf[i];
-                o = (size_t)img * p.max_out + t;
-                if (sub == 0) {
-                    p.keep_idx[o] = idx;
-                    if (p.out_conf) p.out_conf[o] = conf;
-                } else if (sub == 1) {
-                    if (p.out_bbox) p.out_bbox[o] = ca.s_box[i];
-                }
-            }
-            if (want_cls) {
-                int lab;
-                float sc;
-                pick(act ? win + (fsh + cls_off(idx)) : nullptr, conf, act, p.out_cls_spec != nullptr,
-                     (act && p.out_cls_spec) ? p.out_cls_spec + o * C : nullptr, &lab, &sc);
-                if (act && sub == 2) {
-                    if (p.out_label) p.out_label[o] = lab;
-                    if (p.out_score) p.out_score[o] = sc;
-                }
-            }
-        }
-        NT(13);
-    };
-    const bool with_labels = head ? (p.class_aware != 0) : (p.labels != nullptr);
-    const bool fast = !overflow && (IMG || K <= p.stage_slots);
-    if (IMG && fast && !with_labels) rest_img(FastTag<false>{});
-    else if (IMG && fast) rest_img(FastTag<true>{});
-    else if (fast && !with_labels) rest(FastTag<true>{}, FastTag<false>{});
+    const bool fast = !IMG && !overflow && K <= p.stage_slots;  // (IMG: only images that overflowed get here)
+    if (fast && !with_labels) rest(FastTag<true>{}, FastTag<false>{});
     else if (fast) rest(FastTag<true>{}, FastTag<true>{});
     else rest(FastTag<false>{}, FastTag<true>{});
     // (YH_POST_INPUT_READY) everything above ran next to the tail of the previous kernel of the stream;
