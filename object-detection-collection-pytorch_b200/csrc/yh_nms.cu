@@ -612,9 +612,12 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
         const int W = (tn + 31) >> 5;
         {
             const int Ke = K + (K & 1), cols = Ke - 1, total = (Ke >> 1) * cols;
-            const unsigned magic = cols > 1 ? (unsigned)(0xFFFFFFFFu / (unsigned)cols) + 1u : 0u;  // pair / cols, pair < 2^16
+            // pair / cols through the float reciprocal: (pair + 0.5) / cols is at least 0.5 / cols >= 2^-9 away from
+            // an integer and the quotient is below 2^7, so the few ulp of the approximate division cannot move
+            // its integer part (pair < 2^15: exact in float)
+            const float inv_cols = __fdividef(1.0f, (float)cols);
             for (int pr = tid; pr < total; pr += kThreads) {
-                const int r = cols > 1 ? (int)__umulhi((unsigned)pr, magic) : pr;
+                const int r = (int)(((float)pr + 0.5f) * inv_cols);
                 const int c = pr - r * cols;
                 const int i = c >= r ? r : Ke - 1 - r;
                 const int j = c >= r ? c + 1 : Ke - 1 - c;
