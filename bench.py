@@ -407,23 +407,33 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
-    achieved = train_bytes / (train_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "yh_train_kernel (fused decode+assign+loss+dL/dy), stream-ordered launches",
+    # The timed region runs the kernels as an overlapped launch chain, so the dominant kernel's average launch
+    # duration in that regime is the issue interval of back-to-back launches (graph time / launches).  The
+    # isolated figure (every launch waits for the one in front of it to complete) is reported next to it.
+    def gbs(nbytes, ms_):
+        return nbytes / (ms_ * 1e-3) / 1e9
+
+    achieved = gbs(train_bytes, train_ov_ms)
+    roofline = {"bound": "hbm",
+                "kernel": "yh_train_kernel (fused decode+assign+loss+dL/dy) + its one-warp finalize dependent",
+                "regime": "back-to-back launches over the rotating buffer sets, programmatic dependent launches "
+                          "with the overlap promise (yh_v2_train_overlapped) as in the timed region; duration = "
+                          "CUDA-event time of the graph / launches",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": train_bytes,
-                "us_per_launch": train_ms * 1e3,
-                "postprocess_kernel": {"us_per_launch": post_ms * 1e3, "algorithmic_bytes_per_launch": post_bytes,
-                                       "achieved": post_bytes / (post_ms * 1e-3) / 1e9,
-                                       "frac": post_bytes / (post_ms * 1e-3) / 1e9 / peak},
-                "sustained": {"what": "back-to-back launches over the rotating buffer sets with the overlap promise "
-                                      "(yh_v2_train_overlapped / YH_POST_INPUT_READY): consecutive launches run "
-                                      "next to each other's tails; time per launch = graph time / launches",
-                              "train_us_per_launch": train_ov_ms * 1e3,
-                              "train_frac": train_bytes / (train_ov_ms * 1e-3) / 1e9 / peak,
-                              "post_us_per_launch": post_ov_ms * 1e3,
-                              "post_frac": post_bytes / (post_ov_ms * 1e-3) / 1e9 / peak},
-                "step": {"algorithmic_bytes": train_bytes + post_bytes,
-                         "frac": (train_bytes + post_bytes) / (ms / K * 1e-3) / 1e9 / peak}}
+                "us_per_launch": train_ov_ms * 1e3,
+                "isolated": {"what": "stream-ordered launches: each launch starts after the previous one has completed "
+                                     "(only launch latency hidden)",
+                             "train_us_per_launch": train_ms * 1e3, "train_achieved": gbs(train_bytes, train_ms),
+                             "train_frac": gbs(train_bytes, train_ms) / peak,
+                             "post_us_per_launch": post_ms * 1e3, "post_frac": gbs(post_bytes, post_ms) / peak},
+                "postprocess_kernel": {"us_per_launch": post_ov_ms * 1e3, "algorithmic_bytes_per_launch": post_bytes,
+                                       "achieved": gbs(post_bytes, post_ov_ms), "frac": gbs(post_bytes, post_ov_ms) / peak,
+                                       "regime": "back-to-back launches with YH_POST_INPUT_READY"},
+                "step": {"what": "train head + post-process of the timed region (the north-star target: >= 0.60)",
+                         "algorithmic_bytes": train_bytes + post_bytes, "us": ms / K * 1e3,
+                         "achieved": gbs(train_bytes + post_bytes, ms / K),
+                         "frac": gbs(train_bytes + post_bytes, ms / K) / peak}}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
@@ -491,7 +501,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(B, R, not args.two_streams),
-            "clocks": sampler.summary(window), "e2e": e2e, "gpu_launches": 2 * K,
+            "clocks": sampler.summary(window), "e2e": e2e, "gpu_launches": 3 * K,
             "roofline": roofline, "cpu_baseline": cpu, "loss": loss_value,
         }
         emit(line)

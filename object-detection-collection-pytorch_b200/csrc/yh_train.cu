@@ -430,6 +430,13 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
         }
         if (flags) atomicOr(p.acc + 6, (unsigned long long)flags);
         XT(5);
+#ifndef YH_X_ONE_KERNEL
+        // The totals are turned into terms and loss by yh_train_finalize_kernel, a one-warp programmatic
+        // dependent of this kernel: it is resident long before this kernel ends and runs the moment it has
+        // completed.  A ticket here (release, round trip, read-back by the last CTA: three dependent L2
+        // round trips under the draining gradient stores, ~2.3 us) would sit on the kernel's critical path.
+        return;
+#endif
         // release (this thread's atomics above are performed before the ticket is visible) and acquire
         // (the last ticket holder sees every CTA's sums) in ONE acq_rel atomic: no sequentially
         // consistent fence, which costs about a microsecond while the gradient stores drain
@@ -893,6 +900,53 @@ extern "C" YH_API int yh_x_rcycles_copy(unsigned int* host, int n) {
 }
 #endif
 
+struct FinalParams {
+    unsigned long long* acc;
+    float* terms;
+    float* loss;
+    float lam[5];
+    double inv_den[5];
+};
+
+// Totals -> terms and loss (reference models/yolov2.py:1132-1138), and the workspace back to zero for the
+// next launch.  Launched as a programmatic dependent right behind yh_train_kernel.
+__global__ void __launch_bounds__(32) yh_train_finalize_kernel(const FinalParams f) {
+    yh_grid_launch_dependents();
+    yh_grid_dependency_wait();  // the train kernel has completed and its sums are visible
+    if (threadIdx.x == 0) {
+        constexpr double kFix = 4294967296.0;
+        unsigned long long a[7];
+#pragma unroll
+        for (int q = 0; q < 7; ++q) a[q] = __ldcg(f.acc + q);
+        double tot[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) tot[q] = (double)a[q] / kFix;
+        const unsigned bad = (unsigned)a[6];
+        const double nan = __longlong_as_double(0x7ff8000000000000ll);
+        const double t0 = (bad & 1u) ? nan : tot[0] * f.inv_den[0];
+        const double t1 = (bad & 2u) ? nan : tot[1] * f.inv_den[1];
+        const double t2 = (bad & 4u) ? nan : tot[2] * f.inv_den[2];
+        const double t3 = (bad & 24u) ? nan : (tot[3] - tot[4]) * f.inv_den[3];
+        const double t4 = (bad & 32u) ? nan : tot[5] * f.inv_den[4];
+        f.terms[0] = (float)t0; f.terms[1] = (float)t1; f.terms[2] = (float)t2;
+        f.terms[3] = (float)t3; f.terms[4] = (float)t4;
+        f.loss[0] = (float)(f.lam[0] * t0 + f.lam[1] * t1 + f.lam[2] * t2 + f.lam[3] * t3 + f.lam[4] * t4);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) f.acc[q] = 0ull;  // ready for the next launch
+    }
+}
+
+int launch_finalize(const TrainParams& p, cudaStream_t stream) {
+#ifdef YH_X_ONE_KERNEL
+    return 0;
+#else
+    FinalParams f;
+    f.acc = p.acc; f.terms = p.terms; f.loss = p.loss;
+    for (int i = 0; i < 5; ++i) { f.lam[i] = p.lam[i]; f.inv_den[i] = p.inv_den[i]; }
+    return yh_check_cuda(yh_launch_pdl(yh_train_finalize_kernel, dim3(1), dim3(32), 0, stream, f), "yh_train_finalize launch");
+#endif
+}
+
 template <bool WDY, bool VEC, int TV, int TA, int TC>
 int launch_variant(const TrainParams& p, int grid, cudaStream_t stream) {
     const size_t smem = (((size_t)p.tile_cells * p.g.cell_floats + 3) & ~(size_t)3) * 4 + 16 +
@@ -997,8 +1051,10 @@ int train_impl(int version, const float* y, int n, int s_h, int s_w, int a, int 
     }
     const bool vec = ((uintptr_t)y & 15) == 0 && ((uintptr_t)dy & 15) == 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (dy) return vec ? launch_geometry<true, true>(p, grid, st) : launch_geometry<true, false>(p, grid, st);
-    return vec ? launch_geometry<false, true>(p, grid, st) : launch_geometry<false, false>(p, grid, st);
+    if (dy) rc = vec ? launch_geometry<true, true>(p, grid, st) : launch_geometry<true, false>(p, grid, st);
+    else rc = vec ? launch_geometry<false, true>(p, grid, st) : launch_geometry<false, false>(p, grid, st);
+    if (rc) return rc;
+    return launch_finalize(p, st);
 }
 
 }  // namespace
