@@ -412,10 +412,17 @@ def test_compact_targets_recovers_records(key, cuda_device):
 # ------------------------------------------------------------------------------------------
 # post-process / NMS
 # ------------------------------------------------------------------------------------------
-def run_post(case, conf_thre, iou_thre, dev, class_aware=False, max_out=None):
-    r = ops.postprocess(case.y.to(dev), version=case.version, img_hw=(case.height, case.width),
+def run_post(case, conf_thre, iou_thre, dev, class_aware=False, max_out=None, want_cls_spec=True, unaligned=False):
+    y = case.y.to(dev)
+    if unaligned:  # a 4-byte aligned view: no bulk copies, the general path of the kernel
+        buf = torch.zeros(case.y.numel() + 1, device=dev)
+        y = buf[1:].view(case.y.shape)
+        y.copy_(case.y)
+        assert y.data_ptr() % 16 == 4
+    r = ops.postprocess(y, version=case.version, img_hw=(case.height, case.width),
                         conf_thre=conf_thre, iou_thre=iou_thre, anchors=case.anchors,
-                        boxes_per_cell=case.a, class_aware=class_aware, max_out=max_out)
+                        boxes_per_cell=case.a, class_aware=class_aware, max_out=max_out,
+                        want_cls_spec=want_cls_spec)
     torch.cuda.synchronize()
     return {k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in r.items()}
 
@@ -439,11 +446,11 @@ def test_postprocess_matches_reference_golden(name, cuda_device):
     assert np.allclose(flat_kept(r, "score"), z["nms_cls_spec"].max(-1), rtol=1e-5, atol=1e-7)
 
 
-def check_post_vs_oracle(case, conf_thre, iou_thre, dev, class_aware=False):
+def check_post_vs_oracle(case, conf_thre, iou_thre, dev, class_aware=False, want_cls_spec=True):
     anchors = case.anchors if case.version == 2 else case.a
     want = O.postprocess_np(case.y, case.height, case.width, case.version, anchors, conf_thre, iou_thre,
                             class_aware=class_aware)
-    r = run_post(case, conf_thre, iou_thre, dev, class_aware=class_aware)
+    r = run_post(case, conf_thre, iou_thre, dev, class_aware=class_aware, want_cls_spec=want_cls_spec)
     cnt = np.array([len(w["idx"]) for w in want], dtype=np.int32)
     assert np.array_equal(r["keep_cnt"], cnt)
     for n, w in enumerate(want):
@@ -464,6 +471,177 @@ def test_postprocess_class_aware_vs_oracle(cuda_device):
     check_post_vs_oracle(synthetic.cfg3(n=32), 0.5, 0.45, cuda_device, class_aware=True)
     check_post_vs_oracle(synthetic.make_case("v1n", 1, 6, 7, 7, 2, 20, 448, 448, seed=41, to_shift=0.5),
                          0.4, 0.3, cuda_device, class_aware=True)
+
+
+class _Objectness:
+    """The objectness logits of a case's head tensor as [N, P] (predictor order of the kernels), writable."""
+
+    def __init__(self, case):
+        self.case = case
+        a = case.a
+        if case.version == 2:
+            self.v = case.y.view(case.n, -1, 5 + case.c)[:, :, 4]                          # [N, P]
+        else:
+            self.v = case.y.view(case.n, case.s_h * case.s_w, -1)[:, :, 4:5 * a:5]          # [N, cells, A]
+        self.shape = (case.n, case.s_h * case.s_w * a)
+
+    def fill(self, n, value):
+        if n is None:
+            self.v[...] = value
+        else:
+            self.v[n] = value
+
+    def put(self, n, idx, values):
+        idx = torch.as_tensor(np.asarray(idx), dtype=torch.long)
+        values = torch.as_tensor(np.asarray(values, dtype=np.float32))
+        if self.case.version == 2:
+            self.v[n, idx] = values
+        else:
+            self.v[n, idx // self.case.a, idx % self.case.a] = values
+
+    def numpy(self):
+        return self.v.reshape(self.shape[0], -1).numpy().copy()
+
+
+def _objectness(case):
+    assert case.y.is_contiguous()
+    return _Objectness(case)
+
+
+def assert_same_post(a, b, keys=("keep_idx", "label", "score", "conf", "bbox")):
+    assert np.array_equal(a["keep_cnt"], b["keep_cnt"])
+    for n, k in enumerate(a["keep_cnt"]):
+        for key in keys:
+            assert np.array_equal(a[key][n, :k], b[key][n, :k]), (key, n)
+
+
+def test_postprocess_without_cls_spec_vs_oracle(cuda_device):
+    """want_cls_spec=False takes the class pick that skips the divisions which cannot matter."""
+    check_post_vs_oracle(synthetic.cfg3(n=32), 0.5, 0.45, cuda_device, want_cls_spec=False)
+    check_post_vs_oracle(synthetic.cfg3(n=8), 0.5, 0.45, cuda_device, class_aware=True, want_cls_spec=False)
+    check_post_vs_oracle(synthetic.make_case("v1p", 1, 6, 7, 7, 2, 20, 448, 448, seed=43, to_shift=0.5),
+                         0.4, 0.3, cuda_device, want_cls_spec=False)
+    check_post_vs_oracle(synthetic.make_case("p19", 2, 3, 19, 19, 5, 20, 608, 608, seed=44, to_shift=-2.0),
+                         0.5, 0.45, cuda_device, want_cls_spec=False)
+
+
+@pytest.mark.parametrize("geom", ["v2_13", "v2_19", "v1_7"])
+def test_postprocess_candidate_count_edges(geom, cuda_device):
+    """Images with exactly K candidates around every boundary of the kernel: none, one, odd/even pair
+    enumeration, warp and ballot-word boundaries, and the shared-memory limit (256: beyond it the image
+    continues in the workspace).  Every image against the oracle, with and without cls_spec."""
+    if geom == "v2_13":
+        case = synthetic.make_case("ke13", 2, 17, 13, 13, 5, 20, 416, 416, seed=61)
+    elif geom == "v2_19":
+        case = synthetic.make_case("ke19", 2, 17, 19, 19, 5, 20, 608, 608, seed=62)
+    else:
+        case = synthetic.make_case("ke7", 1, 17, 7, 7, 2, 20, 448, 448, seed=63)
+    to = _objectness(case)
+    p = to.shape[1]
+    ks = [0, 1, 2, 3, 4, 5, 31, 32, 33, 63, 64, 65, 97, 255, 256, 257, 300]
+    rng = np.random.default_rng(7)
+    to.fill(None, -30.0)
+    for n, k in enumerate(ks):
+        k = min(k, p)
+        to.put(n, rng.choice(p, size=k, replace=False), rng.uniform(0.5, 4.0, size=k))
+    # (spread the boxes so that a good share of them survives: smaller sizes)
+    if case.version == 2:
+        case.y[..., 2:4] -= 1.5
+    for spec in (True, False):
+        cnt = check_post_vs_oracle(case, 0.5, 0.45, cuda_device, want_cls_spec=spec)
+        assert cnt[0] == 0 and cnt[1] == 1 and cnt.max() > 60
+    # the general path (no bulk copies) gives the same bits
+    assert_same_post(run_post(case, 0.5, 0.45, cuda_device, want_cls_spec=False),
+                     run_post(case, 0.5, 0.45, cuda_device, want_cls_spec=False, unaligned=True))
+
+
+@pytest.mark.parametrize("thr", [0.5, 0.3, 0.9, 0.01, 0.99, 0.0099, 0.995, 1e-4, 0.9999])
+def test_postprocess_threshold_band(thr, cuda_device):
+    """conf >= conf_thre is decided on the logit outside a band of +-1e-3 around logit(conf_thre) and by the
+    sigmoid inside it: objectness logits on, next to and far from every edge of that band.  The whole-image
+    path must list exactly the candidates of the general path (which takes the sigmoid of every logit above
+    the reject margin), and both must agree with the oracle wherever sigmoid(t) is not within a few ulp
+    of the threshold."""
+    case = synthetic.make_case("band", 2, 2, 13, 13, 5, 20, 416, 416, seed=71)
+    to = _objectness(case)
+    t0 = np.log(thr / (1.0 - thr))
+    offs = [0.0]
+    for d in (1e-7, 1e-6, 1e-5, 1e-4, 5e-4, 9.9e-4, 1e-3, 1.01e-3, 1.5e-3, 1e-2, 0.1, 1.0, 3.0):
+        offs += [d, -d]
+    vals = []
+    for o in offs:
+        v = np.float32(t0 + o)
+        vals += [v, np.nextafter(v, np.float32(np.inf)), np.nextafter(v, np.float32(-np.inf))]
+    vals = np.array(vals, dtype=np.float32)
+    assert len(vals) <= 200
+    to.fill(None, -60.0)
+    rng = np.random.default_rng(3)
+    for n in range(case.n):
+        to.put(n, rng.choice(to.shape[1], size=len(vals), replace=False), vals)
+    # iou_thre 2: nothing is suppressed, the kept list is the candidate list
+    fast = run_post(case, thr, 2.0, cuda_device, want_cls_spec=False)
+    gen = run_post(case, thr, 2.0, cuda_device, want_cls_spec=False, unaligned=True)
+    assert_same_post(fast, gen)
+    conf = (np.float32(1.0) / (np.float32(1.0) + np.exp(-to.numpy()))).astype(np.float32)
+    thr32 = np.float32(thr)
+    for n in range(case.n):
+        got = np.zeros(to.shape[1], dtype=bool)
+        got[fast["keep_idx"][n, :fast["keep_cnt"][n]]] = True
+        want = conf[n] >= thr32
+        clear = np.abs(conf[n] - thr32) > 8 * np.spacing(thr32)
+        assert np.array_equal(got[clear], want[clear]), (thr, np.nonzero(got != want)[0])
+        assert want[clear].sum() >= 6 and (~want[clear]).sum() >= 20
+
+
+def test_postprocess_class_pick_adversarial(cuda_device):
+    """Class logits built to break a class pick that skips work: exact and near ties for the maximum,
+    saturated softmax, all classes equal, scores in the denormal range.  The fast pick (no cls_spec, whole
+    image path), the full pick (cls_spec requested) and the general path must return the same labels and
+    scores, bit for bit; where the maximum is unique in float arithmetic the label is the oracle's."""
+    case = synthetic.make_case("pick", 2, 8, 13, 13, 5, 20, 416, 416, seed=81, to_shift=-1.4)
+    cls = case.y[..., 5:]                       # [N, S, S, A, C]
+    rng = np.random.default_rng(11)
+    shape = tuple(cls.shape[1:4])
+    cls[1] = 0.25                               # all classes equal: label 0
+    a = torch.from_numpy(rng.integers(0, 20, size=shape))
+    b = torch.from_numpy(rng.integers(0, 20, size=shape))
+    top = cls[2].max(-1).values + 0.5           # two exact maxima
+    cls[2].scatter_(-1, a[..., None], top[..., None])
+    cls[2].scatter_(-1, b[..., None], top[..., None])
+    top = cls[3].max(-1).values + 0.5           # runner-up one ulp below the maximum
+    cls[3].scatter_(-1, a[..., None], top[..., None])
+    cls[3].scatter_(-1, b[..., None], torch.nextafter(top, torch.tensor(-1e30))[..., None])
+    top = cls[4].max(-1).values + 0.5           # runner-up just inside / outside the 1e-4 window
+    d = torch.from_numpy(rng.choice([0.9e-4, 1.1e-4, 1e-4], size=shape).astype(np.float32))
+    cls[4].scatter_(-1, a[..., None], top[..., None])
+    cls[4].scatter_(-1, b[..., None], (top - d)[..., None])
+    cls[5] = -80.0                              # saturated: one class takes everything
+    cls[5].scatter_(-1, a[..., None], torch.full(shape, 80.0)[..., None])
+    cls[6] *= 30.0
+    to = _objectness(case)
+    to.fill(7, -200.0)                          # scores in the denormal range (conf ~ 5e-39)
+    to.put(7, rng.choice(to.shape[1], size=40, replace=False), rng.uniform(-88.4, -87.6, size=40))
+    for thr, imgs in ((0.5, slice(0, 7)), (1e-40, slice(7, 8))):
+        sub = synthetic.HeadCase(case.name, 2, imgs.stop - imgs.start, 13, 13, 5, 20, 416, 416,
+                                 case.y[imgs].contiguous(), case.rec[:0], np.zeros(imgs.stop - imgs.start + 1, np.int32),
+                                 anchors=case.anchors)
+        fast = run_post(sub, thr, 0.45, cuda_device, want_cls_spec=False)
+        full = run_post(sub, thr, 0.45, cuda_device, want_cls_spec=True)
+        gen = run_post(sub, thr, 0.45, cuda_device, want_cls_spec=False, unaligned=True)
+        assert fast["keep_cnt"].min() >= 5
+        assert_same_post(fast, full)
+        assert_same_post(fast, gen)
+        if thr == 0.5:
+            k = fast["keep_cnt"]
+            assert (fast["label"][1, :k[1]] == 0).all()
+            for n in (2, 3):   # ties / one-ulp runner-up: the reference's argmax takes the first maximum
+                idx = fast["keep_idx"][n, :k[n]]
+                rows = sub.y[n].reshape(-1, 25)[idx, 5:].numpy()
+                assert np.array_equal(fast["label"][n, :k[n]], rows.argmax(-1))
+            for n in (0, 5):
+                want = O.postprocess_np(sub.y[n:n + 1], 416, 416, 2, sub.anchors, 0.5, 0.45)[0]
+                assert np.array_equal(fast["keep_idx"][n, :k[n]], want["idx"])
+                assert np.array_equal(fast["label"][n, :k[n]], want["label"])
 
 
 def test_postprocess_dense_candidates_multi_tile(cuda_device):
