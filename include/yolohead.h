@@ -68,7 +68,8 @@ YH_API int yh_abi_version(void);
 YH_API const char* yh_last_error(void);
 
 /* Bytes of scratch the train entry points need.  The buffer must be zero-filled ONCE when it
- * is allocated; the kernels leave it zeroed again on exit (it holds a block ticket).  Do not
+ * is allocated; a call leaves it zeroed again (it holds the batch's six fixed-point loss sums
+ * between the train kernel and its one-warp finalize kernel -- a train call enqueues both).  Do not
  * share one workspace between calls that may run concurrently on different streams. */
 YH_API size_t yh_train_workspace_bytes(void);
 

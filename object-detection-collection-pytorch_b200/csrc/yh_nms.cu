@@ -5,33 +5,36 @@
 // predict -> nms -> argmax chain of detect() (reference models/yolov2.py:694-731,
 // models/yolov1.py:491-534).
 //
-// One CTA (512 threads) per image, one launch for the whole batch, no sort.  The kernel is
-// latency-bound (a few microseconds end to end), so it is organised around TWO overlapped global
-// round trips:
-//   A  threshold : every thread reads the objectness logit of its predictors (strided 4-byte
-//                  loads, all in flight at once) and tests `sigmoid(to) >= conf_thre`.  A survivor
-//                  reserves a candidate slot and immediately stages its row (5 box logits + C class
-//                  logits) in shared memory with a 1-D TMA bulk copy of the 16-byte aligned window
-//                  around it; every thread then arrives ONCE on one mbarrier, carrying the bytes it
-//                  asked for, so a single wait covers "all candidates found" and "all rows landed".
-//                  All later phases read shared memory only;
+// One CTA (512 threads) per image, one launch for the whole batch, no sort.  Measured on B200: the
+// kernel is DRAM-bound while the images arrive (all CTAs are resident) and bound by instruction
+// issue afterwards (two CTAs per SM, each phase a few hundred nanoseconds), so it is organised
+// around ONE global round trip and few warp instructions:
+//   A  threshold : (whole-image mode, `IMG`: the head tensor is 16-byte aligned and an image fits
+//                  in shared memory -- both reference grids) thread 0 issues four TMA bulk copies
+//                  of the image, one mbarrier each; each group of four warps thresholds its piece as
+//                  it lands.  `sigmoid(to) >= conf_thre` is decided on the logit outside a band of
+//                  1e-3 around logit(conf_thre); survivors are listed as (logit, predictor) pairs,
+//                  one shared atomic per 64 predictors; their sigmoids are taken afterwards, by
+//                  as many threads, which leave 64-bit sort keys (confidence | ~predictor).
+//                  (general mode: strided loads of the objectness logits, a bulk copy per
+//                  candidate row; rows beyond the staged slots are read from global memory);
 //   B  rank      : a candidate's position in the descending-confidence order is the number of
 //                  candidates that beat it (ties: lower predictor index first) -> the order is
-//                  unique and deterministic without a sort; one warp per candidate, ballot/popc;
-//                  the same warp decodes the candidate's box into its ranked slot (same rounding
-//                  sequence as the train head / predict kernels);
-//   D  suppress  : tiles of 256 ranked candidates: (1) test the tile against the boxes kept so
-//                  far, (2) build the intra-tile suppression bitmask with one ballot per 32
-//                  pairs, (3) one warp walks the KEPT boxes of the tile (ffs over the live bits),
-//                  OR-ing their mask rows;
-//   E  emit      : four lanes per kept box: class softmax of its staged row, cls_spec = p * conf,
+//                  unique and deterministic without a sort; two lanes per candidate split the
+//                  comparisons and then decode one axis of the box each (same rounding sequence
+//                  as the train head / predict kernels);
+//   D  suppress  : the i < j pairs of the ranked candidates, enumerated densely over all threads;
+//                  "i suppresses j" bits into a bitmask (rare: atomicOr); one warp resolves the
+//                  greedy order by fixed-point iteration over the mask and lists the survivors;
+//   E  emit      : four lanes per kept box: class softmax of its row, cls_spec = p * conf,
 //                  argmax label / max score, and the box record.
 // The reference's greedy rule (models/utils.py:124-158): candidate j is dropped iff an earlier
 // KEPT candidate i has iou(i, j) >= iou_thre.  class_aware additionally requires equal labels.
 //
-// Candidate lists and staged rows live in shared memory up to 256 candidates per image (the
-// common case by a wide margin); images with more spill to the caller's workspace, read their
-// rows from global memory, and take the same code path through generic pointers.
+// Up to 256 candidates per image everything lives in shared memory (the common case by a wide
+// margin: rest_img below); images with more continue in the caller's workspace, in suppression
+// tiles of 256 candidates, through generic pointers (rest below, also the path of yh_nms and of
+// unaligned or oversized head tensors).
 #include <math.h>
 #include <string.h>
 

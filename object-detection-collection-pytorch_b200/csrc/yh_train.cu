@@ -33,8 +33,10 @@
 //     records share a cell, in CSR order with read-modify-write, so collisions on one predictor
 //     accumulate deterministically);
 //   * the six sums of a CTA are added onto 64-bit fixed-point accumulators with integer atomics
-//     (exact, order-independent: deterministic) behind one acq_rel ticket; the last ticket holder
-//     writes terms and loss;
+//     (exact, order-independent: deterministic); yh_train_finalize_kernel, a one-warp programmatic
+//     dependent launched right behind this kernel, turns the totals into terms and loss and
+//     re-zeroes the workspace (a last-CTA ticket inside this kernel costs three dependent L2 round
+//     trips at the very end of its critical path; -DYH_X_ONE_KERNEL keeps that variant);
 //   * launched as a programmatic dependent: the prologue overlaps the previous kernel's tail.
 #include <limits.h>
 
