@@ -14,7 +14,10 @@ _METHODS = ("predict", "get_loss", "get_loss_compact", "detect", "detect_batch",
             "_yh_anchors", "_yh_kwargs", "_yh_image_batch", "_yh_annot")
 
 
-def patch_reference(ref_yolov1=None, ref_yolov2=None, ref_utils=None):
+def patch_reference(ref_yolov1=None, ref_yolov2=None, ref_utils=None, fused_sgd=False):
+    """`fused_sgd=True` also replaces the `SGD` name the reference's run_one_epoch resolves
+    (models/yolov2.py:7, :1253-1268) with odcp_b200.optim.SGD: the same update (a new optimizer per
+    iteration, so every step is a first step) in one kernel launch."""
     from . import utils as u
     from .yolov1 import YOLOv1HeadOps
     from .yolov2 import YOLOv2HeadOps
@@ -32,6 +35,9 @@ def patch_reference(ref_yolov1=None, ref_yolov2=None, ref_utils=None):
         # the module-level names the reference's methods resolve at call time
         mod.nms = u.nms
         mod.get_iou = u.get_iou
+        if fused_sgd:
+            from ..optim import SGD
+            mod.SGD = SGD
         done.append(cls_name)
     if ref_utils is not None:
         ref_utils.nms = u.nms

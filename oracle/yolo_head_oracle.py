@@ -479,3 +479,26 @@ def match_detections_np(det_bbox, det_label, gt_boxes, gt_labels, levels):
         fp = ((iou[:, None] < levels).astype(int).prod(0) >= 1).astype(int)
         tp[k] = 1 - fp
     return tp
+
+
+# --------------------------------------------------------------------------------------
+# optimizer step -- models/yolov2.py:1253-1272 (torch.optim.SGD, re-created every iteration)
+# --------------------------------------------------------------------------------------
+def sgd_step_np(params, grads, lr, momentum=0.9, weight_decay=5e-4, bufs=None):
+    """One torch.optim.SGD step per tensor, float32 with one rounding per torch op:
+    d = g + weight_decay * p; buf = d on an optimizer's first step (bufs is None: what the reference
+    gets by building a new optimizer in every iteration, models/yolov2.py:1254-1268), else
+    momentum * buf + d; p <- p - lr * buf.  Returns (new params, new bufs)."""
+    f32 = np.float32
+    new_p, new_b = [], []
+    for i, (p, g) in enumerate(zip(params, grads)):
+        p = np.asarray(p, dtype=f32)
+        d = np.asarray(g, dtype=f32) + f32(weight_decay) * p if weight_decay != 0 else np.asarray(g, dtype=f32)
+        if momentum != 0:
+            if bufs is not None and bufs[i] is not None:
+                d = f32(momentum) * np.asarray(bufs[i], dtype=f32) + d
+            new_b.append(d.astype(f32))
+        else:
+            new_b.append(None)
+        new_p.append((p - f32(lr) * d).astype(f32))
+    return new_p, new_b

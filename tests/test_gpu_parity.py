@@ -893,3 +893,109 @@ def test_overlapped_launch_chain_gives_the_same_results(cuda_device):
                 mask = torch.arange(96, device=cuda_device)[None, :] < cnt.clamp(max=96)[:, None]
                 for k in ("keep_idx", "bbox", "label", "score", "conf"):
                     assert torch.equal(s_["post"][k][mask], w["post"][k][mask]), k
+
+
+# ------------------------------------------------------------------------------------------
+# fused SGD step
+# ------------------------------------------------------------------------------------------
+def _sgd_golden():
+    z = np.load(os.path.join(GOLDEN, "sgd_step.npz"))
+    return z, int(z["n_tensors"])
+
+
+def test_fused_sgd_matches_the_reference_sequence_golden(cuda_device):
+    """A NEW optimizer in every iteration (models/yolov2.py:1253-1272), gradients from the golden file."""
+    from odcp_b200.optim import SGD, reset_state
+    reset_state()
+    z, n = _sgd_golden()
+    ps = [torch.nn.Parameter(torch.from_numpy(z["p0_%d" % i]).to(cuda_device)) for i in range(n)]
+    for it, lr in enumerate(z["lrs"]):
+        opt = SGD(ps, lr=float(lr), momentum=float(z["momentum"]), weight_decay=float(z["weight_decay"]))
+        opt.zero_grad()
+        for i, p in enumerate(ps):
+            p.grad = torch.from_numpy(z["fresh_g%d_%d" % (it, i)]).to(cuda_device)
+        opt.step()
+    for i, p in enumerate(ps):
+        assert np.allclose(p.detach().cpu().numpy(), z["fresh_p2_%d" % i], rtol=1e-6, atol=1e-7), i
+
+
+def test_fused_sgd_persistent_momentum_golden(cuda_device):
+    """persistent_momentum=True: buffers survive the re-created optimizers = ONE torch optimizer."""
+    from odcp_b200.optim import SGD, reset_state
+    reset_state()
+    z, n = _sgd_golden()
+    ps = [torch.nn.Parameter(torch.from_numpy(z["p0_%d" % i]).to(cuda_device)) for i in range(n)]
+    grads = [[torch.from_numpy(z["pers_g%d_%d" % (it, i)]).to(cuda_device) for i in range(n)] for it in range(3)]
+    for it in range(3):
+        opt = SGD(ps, lr=float(z["lrs"][2]), momentum=float(z["momentum"]), weight_decay=float(z["weight_decay"]),
+                  persistent_momentum=True)
+        for i, p in enumerate(ps):
+            p.grad = grads[it][i]
+        opt.step()
+    for i, p in enumerate(ps):
+        assert np.allclose(p.detach().cpu().numpy(), z["pers_p2_%d" % i], rtol=1e-6, atol=1e-7), i
+    reset_state()
+
+
+def test_fused_sgd_vs_oracle_odd_shapes_and_views(cuda_device):
+    """Tensors of awkward sizes (empty, one element, one past a chunk, not a multiple of 4), a parameter
+    that is a 4-byte aligned view, parameters without a gradient, no weight decay, no momentum; the step is
+    captured in a CUDA graph and replayed."""
+    from odcp_b200.optim import SGD, reset_state
+    reset_state()
+    rng = np.random.default_rng(5)
+    sizes = [0, 1, 3, 4, 1023, 16384, 16385, 50001]
+    host_p = [rng.standard_normal(s).astype(np.float32) for s in sizes]
+    host_g = [rng.standard_normal(s).astype(np.float32) for s in sizes]
+    for lr, mom, wd in ((0.1, 0.9, 5e-4), (0.05, 0.0, 0.0), (0.2, 0.9, 0.0)):
+        ps = []
+        for hp in host_p:
+            buf = torch.zeros(len(hp) + 1, device=cuda_device)
+            t = buf[1:]          # data_ptr % 16 == 4: scalar path
+            t.copy_(torch.from_numpy(hp))
+            ps.append(torch.nn.Parameter(t) if len(hp) % 2 else torch.nn.Parameter(torch.from_numpy(hp).to(cuda_device)))
+        extra = torch.nn.Parameter(torch.ones(7, device=cuda_device))   # never gets a gradient
+        for p, hg in zip(ps, host_g):
+            p.grad = torch.from_numpy(hg).to(cuda_device)
+        opt = SGD(ps + [extra], lr=lr, momentum=mom, weight_decay=wd)
+        opt.step()
+        want, _ = O.sgd_step_np(host_p, host_g, lr, mom, wd, bufs=None)
+        for p, w in zip(ps, want):
+            assert np.allclose(p.detach().cpu().numpy(), w, rtol=1e-6, atol=1e-7)
+        assert torch.equal(extra.detach(), torch.ones(7, device=cuda_device))
+        # graph capture: the same step again on top of the result
+        st = torch.cuda.Stream(cuda_device)
+        with torch.cuda.stream(st):
+            opt.step()   # warm: the plan is cached
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=st):
+                opt.step()
+            g.replay()
+            st.synchronize()
+        for _ in range(2):   # the warm step and the replay (capturing does not execute)
+            want, _ = O.sgd_step_np(want, host_g, lr, mom, wd, bufs=None)
+        for p, w in zip(ps, want):
+            assert np.allclose(p.detach().cpu().numpy(), w, rtol=2e-6, atol=2e-7)
+    reset_state()
+
+
+def test_fused_sgd_equals_torch_sgd_on_a_model(cuda_device):
+    """Drop-in check on a small conv net: one reference-style iteration with torch.optim.SGD and with the
+    fused step, from the same parameters and gradients."""
+    from odcp_b200.optim import SGD, reset_state
+    reset_state()
+    torch.manual_seed(3)
+    def net():
+        return torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, padding=1), torch.nn.BatchNorm2d(8), torch.nn.LeakyReLU(0.1),
+                                   torch.nn.Conv2d(8, 125, 1)).to(cuda_device)
+    a, b = net(), net()
+    b.load_state_dict(a.state_dict())
+    x = torch.randn(2, 3, 16, 16, device=cuda_device)
+    for m, cls in ((a, torch.optim.SGD), (b, SGD)):
+        opt = cls(m.parameters(), lr=1e-2, momentum=0.9, weight_decay=5e-4)
+        opt.zero_grad()
+        m(x).square().mean().backward()
+        opt.step()
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        assert torch.allclose(pa, pb, rtol=1e-6, atol=1e-7)
+    reset_state()

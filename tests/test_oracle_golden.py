@@ -127,3 +127,39 @@ def test_evaluation_matching_and_ap_match_the_reference():
     for c in range(ncls):
         ap = average_precision(tp[lab == c], sc[lab == c], int(np.sum(z["gt_labels"] == c)))
         assert np.array_equal(ap, z["ap"][c]), c
+
+
+# ------------------------------------------------------------------------------------------
+# optimizer step: the oracle's restatement against torch.optim.SGD run the way
+# the reference runs it (tests/golden/make_sgd_golden.py)
+# ------------------------------------------------------------------------------------------
+def _sgd_golden():
+    import os
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "sgd_step.npz"))
+    n = int(z["n_tensors"])
+    return z, n
+
+
+def test_sgd_oracle_fresh_optimizer_per_iteration():
+    z, n = _sgd_golden()
+    ps = [z["p0_%d" % i] for i in range(n)]
+    for it, lr in enumerate(z["lrs"]):
+        gs = [z["fresh_g%d_%d" % (it, i)] for i in range(n)]
+        ps, _ = O.sgd_step_np(ps, gs, float(lr), float(z["momentum"]), float(z["weight_decay"]), bufs=None)
+    for i in range(n):
+        assert np.allclose(ps[i], z["fresh_p2_%d" % i], rtol=1e-6, atol=1e-7), i
+        assert not np.array_equal(ps[i], z["p0_%d" % i])
+
+
+def test_sgd_oracle_persistent_momentum():
+    z, n = _sgd_golden()
+    ps = [z["p0_%d" % i] for i in range(n)]
+    bufs = None
+    for it in range(3):
+        gs = [z["pers_g%d_%d" % (it, i)] for i in range(n)]
+        ps, bufs = O.sgd_step_np(ps, gs, float(z["lrs"][2]), float(z["momentum"]), float(z["weight_decay"]), bufs=bufs)
+    for i in range(n):
+        assert np.allclose(ps[i], z["pers_p2_%d" % i], rtol=1e-6, atol=1e-7), i
+    # the two modes differ (momentum accumulates only in one of them)
+    assert not np.allclose(ps[4], z["fresh_p2_4"], rtol=1e-6, atol=1e-7)
