@@ -224,26 +224,17 @@ YH_API int yh_scale_inplace(float* x, int64_t count, const float* scale_dev, voi
  * run_one_epoch (reference models/yolov2.py:1253-1272; models/yolov1.py likewise).  Per element
  * (torch.optim.SGD): d = g + weight_decay * p; buf = d on an optimizer's first step, else
  * momentum * buf + d; p -= lr * buf.
- * A tensor list is cut into chunks of at most YH_SGD_CHUNK elements: yh_sgd_chunk_count() says how
- * many, yh_sgd_plan() fills a HOST table from host arrays of DEVICE pointers (buf_ptrs_host may be
- * NULL, or hold NULLs: no buffer is kept for that tensor), the caller copies the table to the
- * device and reuses it while the pointers stay the same; yh_sgd_step() enqueues ONE kernel.
+ *   p_ptrs_host / g_ptrs_host / buf_ptrs_host[n_tensors]: HOST arrays of DEVICE pointers to the fp32
+ *   parameters, gradients and momentum buffers (buf_ptrs_host may be NULL, or hold NULLs: no buffer is
+ *   kept for that tensor); sizes_host[n_tensors] element counts (< 2^31 each).  The list travels in the
+ *   kernel's parameter space: nothing is uploaded or retained, one launch per 96 tensors.
  *   flags: YH_SGD_FRESH_MOMENTUM -- every step is a first step (buf = d), which is what the
  *   reference does by building a new optimizer in every iteration; without it buffers persist. */
 #define YH_SGD_CHUNK 16384
 #define YH_SGD_FRESH_MOMENTUM 1
-typedef struct YhSgdChunk {
-    float* p;
-    const float* g;
-    float* buf;
-    int32_t n;
-    int32_t reserved;
-} YhSgdChunk;
-YH_API int64_t yh_sgd_chunk_count(const int64_t* sizes_host, int n_tensors);
-YH_API int yh_sgd_plan(const uint64_t* p_ptrs_host, const uint64_t* g_ptrs_host, const uint64_t* buf_ptrs_host,
-                const int64_t* sizes_host, int n_tensors, YhSgdChunk* chunks_host, int64_t n_chunks);
-YH_API int yh_sgd_step(const YhSgdChunk* chunks_dev, int64_t n_chunks, float lr, float momentum,
-                float weight_decay, int flags, void* stream);
+YH_API int yh_sgd_step(const uint64_t* p_ptrs_host, const uint64_t* g_ptrs_host, const uint64_t* buf_ptrs_host,
+                const int64_t* sizes_host, int n_tensors, float lr, float momentum, float weight_decay,
+                int flags, void* stream);
 
 #ifdef __cplusplus
 }

@@ -41,9 +41,7 @@ SIGNATURES = {
     "yh_nms": (_i, [_p, _p, _p, _i, _i, _f, _f, _i, _p, _p, _p, _sz, _p]),
     "yh_iou": (_i, [_p, _p, _i64, _p, _p]),
     "yh_scale_inplace": (_i, [_p, _i64, _p, _p]),
-    "yh_sgd_chunk_count": (_i64, [_p, _i]),
-    "yh_sgd_plan": (_i, [_p, _p, _p, _p, _i, _p, _i64]),
-    "yh_sgd_step": (_i, [_p, _i64, _f, _f, _f, _i, _p]),
+    "yh_sgd_step": (_i, [_p, _p, _p, _p, _i, _f, _f, _f, _i, _p]),
 }
 
 _lock = threading.Lock()

@@ -18,7 +18,6 @@ No CPU path: parameters and gradients must be CUDA fp32 tensors.
 """
 from __future__ import annotations
 
-import ctypes as C
 import weakref
 
 import numpy as np
@@ -26,9 +25,24 @@ import torch
 
 from . import _lib
 
-_PLANS = {}      # (device, flags-relevant key, pointer tuple) -> (device table, n_chunks)
 _BUFFERS = {}    # id(parameter) -> (weak reference to it, momentum buffer)   (persistent_momentum)
-_MAX_PLANS = 8
+
+
+def _dense(t):
+    """Non-overlapping and dense in SOME dimension order (contiguous, channels_last, ...): the elements fill
+    numel() consecutive floats, which is all an elementwise update needs."""
+    dims = sorted((st, n) for st, n in zip(t.stride(), t.shape) if n > 1)
+    want = 1
+    for st, n in dims:
+        if st != want:
+            return False
+        want *= n
+    return True
+
+
+def _same_layout(a, b):
+    """Same element order in memory (strides of size-1 dimensions are arbitrary and ignored)."""
+    return a.shape == b.shape and all(x == y for x, y, n in zip(a.stride(), b.stride(), a.shape) if n > 1)
 
 
 class SGD:
@@ -52,29 +66,6 @@ class SGD:
                 p.grad.detach_()
                 p.grad.zero_()
 
-    def _plan(self, ps, gs, bufs):
-        dev = ps[0].device
-        key = (dev.index, tuple(t.data_ptr() for t in ps), tuple(t.data_ptr() for t in gs),
-               None if bufs is None else tuple(t.data_ptr() for t in bufs), tuple(t.numel() for t in ps))
-        hit = _PLANS.get(key)
-        if hit is not None:
-            return hit
-        lib = _lib.load()
-        n = len(ps)
-        sizes = np.array([t.numel() for t in ps], dtype=np.int64)
-        pp = np.array(key[1], dtype=np.uint64)
-        gp = np.array(key[2], dtype=np.uint64)
-        bp = None if bufs is None else np.array(key[3], dtype=np.uint64)
-        n_chunks = int(lib.yh_sgd_chunk_count(sizes.ctypes.data, n))
-        table = np.zeros((max(n_chunks, 1), 4), dtype=np.uint64)  # 32-byte YhSgdChunk records
-        _lib.check("yh_sgd_plan", lib.yh_sgd_plan(pp.ctypes.data, gp.ctypes.data, None if bp is None else bp.ctypes.data,
-                                                  sizes.ctypes.data, n, table.ctypes.data, n_chunks))
-        dtab = torch.from_numpy(table.view(np.int64)).to(dev)
-        if len(_PLANS) >= _MAX_PLANS:
-            _PLANS.pop(next(iter(_PLANS)))
-        _PLANS[key] = (dtab, n_chunks)
-        return _PLANS[key]
-
     @torch.no_grad()
     def step(self):
         ps = [p for p in self.params if p.grad is not None]
@@ -84,8 +75,10 @@ class SGD:
         for p, g in zip(ps, gs):
             if not (p.is_cuda and g.is_cuda and p.dtype == torch.float32 and g.dtype == torch.float32):
                 raise RuntimeError("odcp_b200.optim.SGD needs CUDA fp32 parameters and gradients (no CPU path)")
-            if not (p.is_contiguous() and g.is_contiguous()):
-                raise RuntimeError("parameters and gradients must be contiguous")
+            # elementwise: any dense layout will do (channels_last conv weights included) as long as the
+            # parameter and its gradient share it
+            if not (_dense(p) and _same_layout(p, g)):
+                raise RuntimeError("a parameter and its gradient must be dense and share one memory layout")
         bufs, flags = None, 1  # YH_SGD_FRESH_MOMENTUM: the reference's new-optimizer-per-iteration update
         if self.persistent_momentum and self.momentum != 0.0:
             flags = 0
@@ -93,21 +86,26 @@ class SGD:
             for p, g in zip(ps, gs):
                 ent = _BUFFERS.get(id(p))
                 b = ent[1] if ent is not None and ent[0]() is p else None
-                if b is None or b.shape != p.shape or b.device != p.device:
+                if b is None or b.shape != p.shape or b.device != p.device or not _same_layout(b, p):
                     # torch: the first step's buffer is the (decayed) gradient; momentum * 0 + d gives the same
-                    b = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    b = torch.zeros_like(p, memory_format=torch.preserve_format)
                     key = id(p)
                     _BUFFERS[key] = (weakref.ref(p, lambda _r, key=key: _BUFFERS.pop(key, None)), b)
                 bufs.append(b)
         dev = ps[0].device
+        n = len(ps)
+        arr = np.empty((4, n), dtype=np.uint64)   # device pointers of p, g, buf and the element counts
+        arr[0] = [t.data_ptr() for t in ps]
+        arr[1] = [t.data_ptr() for t in gs]
+        arr[2] = [t.data_ptr() for t in bufs] if bufs is not None else 0
+        arr[3] = [t.numel() for t in ps]
         with torch.cuda.device(dev):
-            dtab, n_chunks = self._plan(ps, gs, bufs)
-            _lib.check("yh_sgd_step", _lib.load().yh_sgd_step(dtab.data_ptr(), n_chunks, self.lr, self.momentum,
-                                                              self.weight_decay, flags,
-                                                              torch.cuda.current_stream().cuda_stream))
+            _lib.check("yh_sgd_step", _lib.load().yh_sgd_step(
+                arr[0].ctypes.data, arr[1].ctypes.data, arr[2].ctypes.data if bufs is not None else None,
+                arr[3].ctypes.data, n, self.lr, self.momentum, self.weight_decay, flags,
+                torch.cuda.current_stream().cuda_stream))
 
 
 def reset_state():
-    """Forget cached chunk tables and persistent momentum buffers (tests)."""
-    _PLANS.clear()
+    """Forget the persistent momentum buffers (tests)."""
     _BUFFERS.clear()

@@ -191,27 +191,21 @@ def test_mixin_composes_with_the_unmodified_reference_model():
             del sys.modules[k]
 
 
-def test_sgd_plan_cuts_tensors_into_chunks():
-    """Host side of the fused SGD step: chunk count and table, no device needed."""
+def test_sgd_step_validates_its_tensor_list():
+    """Host side of the fused SGD step: argument validation happens before anything touches the device."""
     lib = _lib.load()
-    sizes = np.array([5, 16384, 16385, 0, 40000], dtype=np.int64)
-    n_chunks = lib.yh_sgd_chunk_count(sizes.ctypes.data, len(sizes))
-    assert n_chunks == 1 + 1 + 2 + 0 + 3
-    pp = np.array([0x1000, 0x20000, 0x400000, 0, 0x8000000], dtype=np.uint64)
+    sizes = np.array([5, 16384], dtype=np.int64)
+    pp = np.array([0x1000, 0x20000], dtype=np.uint64)
     gp = pp + np.uint64(0x10000000)
-    table = np.zeros((n_chunks, 4), dtype=np.uint64)
-    rc = lib.yh_sgd_plan(pp.ctypes.data, gp.ctypes.data, None, sizes.ctypes.data, len(sizes), table.ctypes.data, n_chunks)
-    assert rc == 0
-    n_of = (table[:, 3] & np.uint64(0xffffffff)).astype(np.int64)
-    assert n_of.tolist() == [5, 16384, 16384, 1, 16384, 16384, 40000 - 2 * 16384]
-    assert table[3, 0] == 0x400000 + 4 * 16384 and table[3, 1] == 0x400000 + 0x10000000 + 4 * 16384
-    assert (table[:, 2] == 0).all()          # no momentum buffers
-    # errors are reported, not crashed
-    assert lib.yh_sgd_plan(pp.ctypes.data, gp.ctypes.data, None, sizes.ctypes.data, len(sizes), table.ctypes.data, n_chunks + 1) < 0
-    assert b"n_chunks" in lib.yh_last_error()
+    assert lib.yh_sgd_step(None, None, None, None, 0, 0.1, 0.9, 5e-4, 1, None) == 0   # nothing to do
     bad = pp.copy(); bad[0] = 0x1002
-    assert lib.yh_sgd_plan(bad.ctypes.data, gp.ctypes.data, None, sizes.ctypes.data, len(sizes), table.ctypes.data, n_chunks) < 0
-    assert lib.yh_sgd_step(None, 0, 0.1, 0.9, 5e-4, 1, None) == 0   # nothing to do
+    assert lib.yh_sgd_step(bad.ctypes.data, gp.ctypes.data, None, sizes.ctypes.data, 2, 0.1, 0.9, 5e-4, 1, None) < 0
+    assert b"aligned" in lib.yh_last_error()
+    bad = pp.copy(); bad[1] = 0
+    assert lib.yh_sgd_step(bad.ctypes.data, gp.ctypes.data, None, sizes.ctypes.data, 2, 0.1, 0.9, 5e-4, 1, None) < 0
+    big = np.array([5, 1 << 31], dtype=np.int64)
+    assert lib.yh_sgd_step(pp.ctypes.data, gp.ctypes.data, None, big.ctypes.data, 2, 0.1, 0.9, 5e-4, 1, None) < 0
+    assert lib.yh_sgd_step(pp.ctypes.data, None, None, sizes.ctypes.data, 2, 0.1, 0.9, 5e-4, 1, None) < 0
 
 
 def test_fused_sgd_refuses_cpu_tensors():
