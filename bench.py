@@ -251,8 +251,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    if world > 1:
-        bind_to_gpu_numa_node(local_rank)
+    bind_to_gpu_numa_node(local_rank)  # (also with one rank: pinned host buffers on the GPU's own socket)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None

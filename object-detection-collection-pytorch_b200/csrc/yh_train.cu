@@ -68,9 +68,15 @@ constexpr int kMaxGrid = 2048;
 constexpr int kClsRegs = 4;               // class logits per lane kept in registers (C <= 128)
 constexpr int kWindow = 128;              // speculative record window (records) per tile
 constexpr int kWindowMax = 256;           // record window buffer: an exact window after a miss may be this long
-constexpr int kSlots = 24;                // patches (records processed during the dense pass) per tile, <= 32
+#ifndef YH_X_SLOTS
+#define YH_X_SLOTS 24
+#endif
+#ifndef YH_X_SHADOW
+#define YH_X_SHADOW 12
+#endif
+constexpr int kSlots = YH_X_SLOTS;        // patches (records processed during the dense pass) per tile, <= 32
 constexpr int kPatchFloats = 32;          // floats per patch row: 5 + C must fit (else the record waits for the end)
-constexpr int kShadowMax = 12;             // records per tile up to which they are processed during the dense pass
+constexpr int kShadowMax = YH_X_SHADOW;   // records per tile up to which they are processed during the dense pass
 constexpr int kCellSlots = 12;            // records whose cell gets a private early copy (the others wait for their chunk)
 
 #ifdef YH_X_TRACE

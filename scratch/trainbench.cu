@@ -31,7 +31,8 @@ int main(int argc, char** argv) {
     std::vector<YhGt> gt;
     std::vector<int> off(N + 1, 0);
     for (int n = 0; n < N; ++n) {
-        const int k = 1 + rng() % 5;
+        const int kmin = argc > 3 ? atoi(argv[3]) : 1, kmax = argc > 4 ? atoi(argv[4]) : 5;  // boxes per image
+        const int k = kmin + rng() % (kmax - kmin + 1);
         for (int j = 0; j < k; ++j) {
             YhGt r;
             const float w = 416.f * (0.05f + 0.55f * (rng() % 1000) / 1000.f), h = 416.f * (0.05f + 0.55f * (rng() % 1000) / 1000.f);
