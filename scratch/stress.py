@@ -8,7 +8,7 @@ from odcp_b200 import ops, synthetic, targets
 dev = torch.device("cuda:0")
 lam = synthetic.DEFAULT_LAMBDAS
 for name, case, reps in (("headline", synthetic.headline(), 300), ("cfg2+collisions", synthetic.with_collisions(synthetic.cfg2(), 60, seed=1), 300),
-                         ("cfg5", synthetic.cfg5(n=128), 60), ("cfg1", synthetic.cfg1(), 300)):
+                         ("cfg3", synthetic.cfg3(), 300), ("cfg5", synthetic.cfg5(n=128), 60), ("cfg1", synthetic.cfg1(), 300)):
     kw = dict(version=case.version, img_hw=(case.height, case.width), anchors=case.anchors, boxes_per_cell=case.a)
     y = case.y.to(dev)
     gt = targets.records_to_tensor(case.rec, dev)
@@ -17,7 +17,8 @@ for name, case, reps in (("headline", synthetic.headline(), 300), ("cfg2+collisi
     bad = 0
     for i in range(reps):
         r = ops.train_head(y, gt, off, lambdas=lam, want_resp=True, **kw)
-        p = ops.postprocess(y, conf_thre=0.5, iou_thre=0.45, max_out=128, input_ready=True, **kw)
+        # (alternating between the full class pick and the one that skips divisions: same labels and scores)
+        p = ops.postprocess(y, conf_thre=0.5, iou_thre=0.45, max_out=128, input_ready=True, want_cls_spec=(i % 2 == 0), **kw)
         cur = [r["loss"].clone(), r["terms"].clone(), r["dy"].clone(), r["resp"].clone(), p["keep_cnt"].clone(), p["keep_idx"].clone(),
                p["label"].clone(), p["score"].clone(), p["bbox"].clone()]
         if ref is None:
