@@ -68,10 +68,13 @@ def workload_config(batch, sets=None, serial=False):
     if sets is not None:
         cfg["l2"] = "%d rotating input/output buffer sets per GPU (inputs+outputs %.0f MB > 126 MB L2)" % (
             sets, sets * 2 * batch * 84500 / 1e6)
-        cfg["streams"] = "one stream, programmatic dependent launches; within a graph replay of %d steps every kernel " \
-            "but the first promises that its buffers are not in use by the kernels in front of it (rotating sets) and " \
-            "overlaps their tails; the first kernel of a replay waits for everything before it" % (sets or 0) if serial else \
-            "train head and post-process of a step on two streams (parallel graph branches), steps in order"
+        if serial:
+            cfg["streams"] = ("one stream, programmatic dependent launches; a graph replay is 4 passes over the %d buffer "
+                              "sets; every kernel but the first of a pass promises that its buffers are not in use by the "
+                              "kernels in front of it (rotating sets) and overlaps their tails; the first kernel of every "
+                              "pass waits for everything before it" % (sets or 0))
+        else:
+            cfg["streams"] = "train head and post-process of a step on two streams (parallel graph branches), steps in order"
     return cfg
 
 
@@ -323,8 +326,12 @@ def main():
         for s in sets:  # eager warm-up: allocates outputs/workspaces before any capture
             step(s)
         stream.synchronize()
-        g_full = capture(lambda: [step(s, first=(i == 0)) for i, s in enumerate(sets)])
-        g_one = [capture(lambda s=s: step(s)) for s in sets[: max(K % R, W % R, 1)]] if (K % R or W % R) else []
+        # one graph = ROUNDS passes over the R buffer sets; the first kernel of every pass waits for everything
+        # before it (no promise), so the overlap chain stays bounded by the rotation length
+        ROUNDS = 4
+        G = R * ROUNDS
+        g_full = capture(lambda: [step(s, first=(i == 0)) for _ in range(ROUNDS) for i, s in enumerate(sets)])
+        g_one = [capture(lambda s=s: step(s)) for s in sets[: min(R, max(K % G, W % G, 1))]] if (K % G or W % G) else []
         # per-kernel graphs: stream-ordered launches (only launch latency hidden) for the roofline of one
         # launch, and the overlapped variant for the sustained rate of back-to-back launches
         g_train = capture(lambda: [step(s, post=False, overlap=False) for s in sets])
@@ -333,10 +340,10 @@ def main():
         g_post_ov = capture(lambda: [step(s, train=False, first=(i == 0)) for i, s in enumerate(sets)])
 
         def run_steps(n):
-            for _ in range(n // R):
+            for _ in range(n // G):
                 g_full.replay()
-            for i in range(n % R):
-                g_one[i].replay()
+            for i in range(n % G):
+                g_one[i % len(g_one)].replay()
 
         def barrier():
             if dist is not None:

@@ -167,7 +167,11 @@ __device__ __forceinline__ void put4(float4& v, int j, float x) {
 // its gradient cno * kn * conf^2 * (1 - conf).  Approximate sigmoid (no decision depends on it) and
 // explicitly rounded steps: the dense pass and the record warp must produce identical bits.
 __device__ __forceinline__ float noobj_term(float t, float kn, float* conf_out) {
-    const float conf = __fdividef(1.0f, __fadd_rn(1.0f, __expf(-t)));
+    // (two SFU operations: ex2.approx and rcp.approx handle +-inf, 0 and NaN the way the sigmoid needs them, and
+    // the range fix-ups __expf / __fdividef wrap around them were a quarter of the dense pass' instructions)
+    float e, conf;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__fmul_rn(t, -1.4426950408889634f)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(conf) : "f"(__fadd_rn(1.0f, e)));
     *conf_out = conf;
     return __fmul_rn(__fmul_rn(kn, conf), conf);
 }
@@ -631,13 +635,42 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
                 const int lo = c * ch4, hi = min(lo + ch4, nf4);
                 yh_mbar_wait(&s_bar[c], phase);  // (empty chunks complete at once: every barrier flips once per tile)
                 if (tid == 0 && c + kAhead < kChunks) issue_chunk(c + kAhead);  // keep kAhead chunks in flight
+                if (version == 2 && two_img) {
+                    // The common case, kept lean (the kernel's issue slots are shared with the tail of the kernel
+                    // next to it): floats lf..lf+3 sit at positions m..m+3 of a predictor row, the objectness logit
+                    // (position 4) is among them iff 1 <= m <= 4; m advances by (4 * kDense) mod (5 + C) per trip
+                    // instead of being divided out; a tile touches at most two images.  Branch-free.
+                    const int mstep = (4 * kDense) % bs;
+                    int m = (4 * (lo + tid)) % bs;
+                    for (int i4 = lo + tid; i4 < hi; i4 += kDense) {
+                        const float4 v = tile4[i4];
+                        const int lf = 4 * i4;
+                        const bool has = (unsigned)(m - 1) < 4u;
+                        float tl = v.w;
+                        tl = m == 2 ? v.z : tl;
+                        tl = m == 3 ? v.y : tl;
+                        tl = m == 4 ? v.x : tl;
+                        float conf;
+                        float w = noobj_term(tl, (lf + 4 - m) < thr0 ? kn0 : kn1, &conf);
+                        w = has ? w : 0.f;
+                        sums.no += w;
+                        const float val = noobj_grad(w, conf, p.cno);
+                        float4 o;
+                        o.x = m == 4 ? val : 0.f;
+                        o.y = m == 3 ? val : 0.f;
+                        o.z = m == 2 ? val : 0.f;
+                        o.w = m == 1 ? val : 0.f;
+                        if (WRITE_DY) store4<VEC>(dt, i4, o);
+                        m += mstep;
+                        m = m >= bs ? m - bs : m;
+                    }
+                } else
                 for (int i4 = lo + tid; i4 < hi; i4 += kDense) {
                     const float4 v = tile4[i4];
                     const int lf = 4 * i4;
                     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (version == 2) {
-                        // floats lf..lf+3 sit at positions m..m+3 of a predictor row: the objectness
-                        // logit (position 4) is among them iff 1 <= m <= 4.  Branch-free.
+                        // (tiles that span more than two images: the box count is looked up per float4)
                         const int m = lf % bs;
                         const bool has = (unsigned)(m - 1) < 4u;
                         float tl = v.w;
