@@ -153,6 +153,31 @@ int main(int argc, char** argv) {
         }
     }
 #endif
+#ifdef YH_X_TRACE
+    {   // the chain of the timed region: train head, then post-process with YH_POST_INPUT_READY, on one time base
+        post_flags = YH_POST_INPUT_READY;
+        for (int rep = 0; rep < 3; ++rep) { train(sets[rep]); post(sets[rep]); CK(cudaStreamSynchronize(st)); }
+        post_flags = 0;
+        std::vector<unsigned long long> tt(4096 * 24), tn(4096 * 16);
+        yh_x_trace_copy(tt.data(), 4096 * 24);
+        yh_x_ntrace_copy(tn.data(), 4096 * 16);
+        int G = 0; while (G < 4095 && tt[G * 24] != 0) ++G;
+        unsigned long long t0 = ~0ull; for (int b = 0; b < G; ++b) t0 = std::min(t0, tt[b * 24]);
+        auto show = [&](const char* name, std::vector<double> v) {
+            if (v.empty()) return; std::sort(v.begin(), v.end());
+            printf("  chain %-24s n=%3zu min %6.0f  p10 %6.0f  med %6.0f  p90 %6.0f  max %6.0f ns\n", name, v.size(), v[0], v[v.size() / 10], v[v.size() / 2], v[v.size() * 9 / 10], v.back());
+        };
+        std::vector<double> a, b2;
+        for (int b = 0; b < G; ++b) { a.push_back((double)(tt[b * 24] - t0)); b2.push_back((double)(tt[b * 24 + 3] - t0)); }
+        show("train CTA start", a); show("train tile loop done", b2);
+        const char* nm[16] = {"nms start", "init done", "A issued+arrived", "-", "B decode done", "-", "-", "D pairs done", "D fixed point done", "-", "-", "-", "D done", "E emit done", "-", "-"};
+        for (int sl = 0; sl < 14; ++sl) {
+            if (nm[sl][0] == '-') continue;
+            std::vector<double> v; for (int b = 0; b < N; ++b) v.push_back((double)((long long)tn[b * 16 + sl] - (long long)t0));
+            show(nm[sl], v);
+        }
+    }
+#endif
     float loss; CK(cudaMemcpy(&loss, sets[0].loss, 4, cudaMemcpyDeviceToHost));
     std::vector<int> kc(N); CK(cudaMemcpy(kc.data(), sets[0].kcnt, N * 4, cudaMemcpyDeviceToHost));
     long kept = 0; for (int v : kc) kept += v;
