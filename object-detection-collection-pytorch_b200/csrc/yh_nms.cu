@@ -870,6 +870,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
 
         // ---------------- D: greedy suppression, tile by tile ----------------
         const float thr = p.iou_thre;
+        const bool thr_pos = thr > 0.f;
         for (int base = 0; base < K; base += kTile) {
             const int tn = min(kTile, K - base);
             const int W = (tn + 31) >> 5;
@@ -878,14 +879,12 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
                 bool dead = false;
                 if (jp < tn && base > 0) {
                     const float4 bj = ca.s_box[base + jp];
-                    const YhBox qj{bj.x, bj.y, bj.z, bj.w};
+                    const float aj = ca.s_area[base + jp];
                     const int lj = use_lab ? ca.s_lab[base + jp] : 0;
                     const int kept = s_kept;
                     for (int q = 0; q < kept; ++q) {
                         const int i = ca.keep[q];
-                        const float4 bi = ca.s_box[i];
-                        const YhBox qi{bi.x, bi.y, bi.z, bi.w};
-                        if (yh_iou_xyxy(qi, qj) >= thr && (!use_lab || ca.s_lab[i] == lj)) { dead = true; break; }
+                        if (suppresses_dense(ca.s_box[i], ca.s_area[i], bj, aj, thr, thr_pos) && (!use_lab || ca.s_lab[i] == lj)) { dead = true; break; }
                     }
                 }
                 const unsigned bal = __ballot_sync(0xffffffffu, dead);
@@ -905,7 +904,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
                     const int i = w * 32 + lane;
                     bool bit = false;
                     if (i < j) {
-                        bit = suppresses(ca.s_box[base + i], ca.s_area[base + i], bj, aj, thr);
+                        bit = suppresses_dense(ca.s_box[base + i], ca.s_area[base + i], bj, aj, thr, thr_pos);
                         if (use_lab) bit = bit && lj == ca.s_lab[base + i];
                     }
                     const unsigned m = __ballot_sync(0xffffffffu, bit);
