@@ -597,16 +597,27 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
             if (C <= 4 * kPickRegs && !with_spec) quad_class_pick_fast(cl, C, conf, sub, act, lab, sc, &ok);
             if (!__all_sync(0xffffffffu, ok)) group_class_pick<kPick>(cl, C, conf, sub, act, spec_out, lab, sc);
         };
-        if (use_lab) {  // label of every candidate (argmax of cls_spec)
-            for (int k0 = 0; k0 < K; k0 += kThreads / kPick) {
-                if (k0 + (32 / kPick) * warp >= K) break;
-                const int k = k0 + tid / kPick;
+        // Label and score of EVERY ranked candidate, by the warps w0 .. w0 + nw - 1 (eight candidates per warp and
+        // trip).  Class-aware suppression needs the labels before the pair tests; otherwise the pick runs on
+        // warps 1.. while warp 0 resolves the greedy order -- a latency-bound chain of ballots during which the
+        // other warps would idle -- so that the emit phase only copies.  (~10 % of the candidates are not kept
+        // and get picked for nothing: cheaper than a serial pick phase at the end of the kernel's critical path.)
+        const bool with_spec = p.out_cls_spec != nullptr;
+        const bool want_ls = p.out_label != nullptr || p.out_score != nullptr;
+        float* s_score = reinterpret_cast<float*>(ca.s_slot);  // (ranked -> unsorted slot is not needed in this mode)
+        auto pick_all = [&](int w0, int nw) {
+            for (int k0 = 8 * (warp - w0); k0 < K; k0 += 8 * nw) {  // (uniform over the warp)
+                const int k = k0 + (lane >> 2);
                 const bool act = k < K;
                 int lab;
                 float sc;
                 pick(act ? win + (fsh + cls_off(ca.s_idx[k])) : nullptr, act ? ca.s_conf[k] : 0.f, act, false, nullptr, &lab, &sc);
-                if (act && sub == 0) ca.s_lab[k] = lab;
+                if (act && sub == 0) { ca.s_lab[k] = lab; s_score[k] = sc; }
             }
+        };
+        const bool picked = !with_spec && (use_lab || want_ls);  // emit finds label and score in shared memory
+        if (use_lab) {
+            pick_all(0, kWarps);
             __syncthreads();
         }
 
@@ -635,6 +646,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
         }
         __syncthreads();
         NT(7);
+        if (warp != 0 && picked && !use_lab) pick_all(1, kWarps - 1);
         if (warp == 0) {
             unsigned alive[kTileWords], dead0[kTileWords];
 #pragma unroll
@@ -717,11 +729,16 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
                     if (p.out_bbox) p.out_bbox[o] = ca.s_box[i];
                 }
             }
-            if (want_cls) {
+            if (picked) {
+                if (act && sub == 2) {
+                    if (p.out_label) p.out_label[o] = ca.s_lab[i];
+                    if (p.out_score) p.out_score[o] = s_score[i];
+                }
+            } else if (want_cls) {
                 int lab;
                 float sc;
-                pick(act ? win + (fsh + cls_off(idx)) : nullptr, conf, act, p.out_cls_spec != nullptr,
-                     (act && p.out_cls_spec) ? p.out_cls_spec + o * C : nullptr, &lab, &sc);
+                pick(act ? win + (fsh + cls_off(idx)) : nullptr, conf, act, with_spec,
+                     (act && with_spec) ? p.out_cls_spec + o * C : nullptr, &lab, &sc);
                 if (act && sub == 2) {
                     if (p.out_label) p.out_label[o] = lab;
                     if (p.out_score) p.out_score[o] = sc;
