@@ -533,8 +533,9 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
     //      the unsorted lists), then decodes one axis of the box (x: tx, tw; y: ty, th);
     //   D  the i < j pairs are enumerated densely over all threads (the triangle folded into a
     //      K/2 x (K-1) rectangle), set bits go to the mask with atomicOr (rare), then the fixed-point
-    //      resolution of the greedy order by one warp, as in the general path;
-    //   E  four lanes per kept box, class pick without the divisions that cannot matter.
+    //      resolution of the greedy order by one warp, as in the general path -- while the other warps pick
+    //      label and score of every candidate (four lanes per box, without the divisions that cannot matter);
+    //   E  four lanes per kept box copy the record out.
     auto rest_img = [&](auto lab_tag) {
         constexpr bool LAB = decltype(lab_tag)::value;
         const float* win = reinterpret_cast<const float*>(smem_raw);
