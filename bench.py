@@ -54,7 +54,7 @@ def parse_args():
                     help="issue the post-process of a step on a second stream (fork/join inside the step). "
                          "Default: one stream; the post-process is launched as a programmatic dependent with "
                          "YH_POST_INPUT_READY, so it already overlaps the train head's tail")
-    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 200)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 400)")
     return ap.parse_args()
 
 
@@ -450,7 +450,7 @@ def main():
     # ---- e2e: host buffers in, host buffers out
     e2e = None
     if not args.no_e2e:
-        ke = args.e2e_steps or max(20, min(K, 200))
+        ke = args.e2e_steps or max(20, min(K, 400))
         pipe = HostHeadPipeline(B, case.s_h, case.s_w, case.a, case.c, img_hw=(case.height, case.width),
                                 anchors=case.anchors, lambdas=lam, conf_thre=CONF_THRE, iou_thre=IOU_THRE,
                                 max_out=MAX_OUT, max_boxes=m_local, depth=3, device=dev)
