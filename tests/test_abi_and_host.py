@@ -215,3 +215,43 @@ def test_fused_sgd_refuses_cpu_tensors():
     p.grad = torch.ones(4)
     with pytest.raises(RuntimeError, match="CUDA"):
         SGD([p], lr=0.1, momentum=0.9, weight_decay=5e-4).step()
+
+
+def test_pair_enumeration_of_the_postprocess_covers_the_triangle():
+    """Host mirror of the dense pair enumeration in yh_nms.cu (rest_img, phase D): the i < j pairs of K ranked
+    candidates are the cells of a K/2 x (K-1) rectangle, addressed through a float reciprocal instead of an
+    integer division.  Every pair exactly once, and the float quotient equals the integer one, for every K the
+    shared-memory path handles."""
+    f32 = np.float32
+    for k in range(0, 257):
+        ke = k + (k & 1)
+        cols, total = ke - 1, (ke >> 1) * (ke - 1)
+        if total == 0:
+            continue
+        inv = f32(1.0) / f32(cols)
+        # the device uses an approximate reciprocal: allow it to be off by a few ulp in either direction
+        for fudge in (f32(1.0), f32(1.0) + f32(4e-7), f32(1.0) - f32(4e-7)):
+            pr = np.arange(total, dtype=np.int64)
+            r = ((pr.astype(f32) + f32(0.5)) * (inv * fudge)).astype(np.int64)
+            assert np.array_equal(r, pr // cols), (k, float(fudge))
+        c = pr - r * cols
+        i = np.where(c >= r, r, ke - 1 - r)
+        j = np.where(c >= r, c + 1, ke - 1 - c)
+        ok = j < k
+        assert (i[ok] < j[ok]).all()
+        pairs = set(zip(i[ok].tolist(), j[ok].tolist()))
+        assert len(pairs) == ok.sum() == k * (k - 1) // 2
+
+
+def test_threshold_band_of_the_postprocess_is_safe():
+    """Host mirror of postprocess_impl's logit band: for thresholds in [0.01, 0.99] the kernel decides
+    sigmoid(t) >= thr on the logit when |t - logit(thr)| >= 1e-3.  In float32 the sigmoid at the band's edges must
+    be on the right side of the threshold by far more than its own rounding (a few ulp)."""
+    f32 = np.float32
+    for thr in np.concatenate([np.linspace(0.01, 0.99, 197), [0.5, 0.3, 0.9]]):
+        t0 = np.log(thr / (1.0 - thr))
+        lo, hi = f32(t0 - 1e-3), f32(t0 + 1e-3)
+        sig = lambda t: f32(1.0) / (f32(1.0) + np.exp(-t, dtype=f32))
+        ulp = np.spacing(f32(thr))
+        assert sig(hi) - f32(thr) > 40 * ulp, thr
+        assert f32(thr) - sig(lo) > 40 * ulp, thr
