@@ -28,11 +28,16 @@ struct DecodeParams {
     int tma_in;
 };
 
+// TV/TA/TC != 0 fix version / boxes per cell / classes at compile time (the divisions by C and A of the
+// coalesced sweeps become multiplications); 0 keeps them as run-time values from the geometry.
+template <int TV, int TA, int TC>
 __global__ void __launch_bounds__(kThreads) yh_decode_kernel(const DecodeParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const YhGeom& g = p.g;
     const int tid = threadIdx.x;
-    const int cf = g.cell_floats, bs = g.box_stride, A = g.a, C = g.c;
+    const int version = TV ? TV : g.version;
+    const int A = TA ? TA : g.a, C = TC ? TC : g.c;
+    const int bs = version == 2 ? 5 + C : 5, cf = version == 2 ? A * (5 + C) : 5 * A + C;
     const int chunk_floats = p.cells_per_chunk * cf;
     float* in = reinterpret_cast<float*>(smem_raw);
     float* s_conf = in + chunk_floats;                       // [rows]
@@ -68,7 +73,7 @@ __global__ void __launch_bounds__(kThreads) yh_decode_kernel(const DecodeParams 
     const int nrows = ncell * A;
     const long long row0 = cell0 * A;  // global predictor index of the chunk's first row
     // class groups: one softmax per predictor (v2) or per cell (v1)
-    const int ngroups = g.version == 2 ? nrows : ncell;
+    const int ngroups = version == 2 ? nrows : ncell;
 
     for (int u = tid; u < nrows; u += kThreads) {
         const int lcell = u / A, a = u - lcell * A;
@@ -78,7 +83,7 @@ __global__ void __launch_bounds__(kThreads) yh_decode_kernel(const DecodeParams 
         const float* bp = in + lcell * cf + a * bs;
         const float sx = yh_sigmoid(bp[0]), sy = yh_sigmoid(bp[1]);
         float wa, ha;
-        if (g.version == 2) {
+        if (version == 2) {
             wa = expf(bp[2]);
             ha = expf(bp[3]);
         } else {
@@ -96,23 +101,28 @@ __global__ void __launch_bounds__(kThreads) yh_decode_kernel(const DecodeParams 
     }
     if (!p.cls_prob && !p.cls_spec) return;
 
+    // softmax statistics, one thread per class group; the exponentials replace the logits in the staged chunk
+    // (nothing reads the class logits again), so the coalesced sweep below only divides
     for (int q = tid; q < ngroups; q += kThreads) {
-        const float* cl = g.version == 2 ? in + q * bs + 5 : in + q * cf + 5 * A;
+        float* cl = version == 2 ? in + q * bs + 5 : in + q * cf + 5 * A;
         float mx = -INFINITY;
         for (int c = 0; c < C; ++c) mx = fmaxf(mx, cl[c]);
         float se = 0.f;
-        for (int c = 0; c < C; ++c) se += expf(cl[c] - mx);
-        s_mx[q] = mx;
+        for (int c = 0; c < C; ++c) {
+            const float e = expf(cl[c] - mx);
+            cl[c] = e;
+            se += e;
+        }
         s_inv[q] = se;
     }
     __syncthreads();
 
-    if (g.version == 2) {
+    if (version == 2) {
         const int total = nrows * C;
         const long long o0 = row0 * C;
         for (int i = tid; i < total; i += kThreads) {
             const int u = i / C, c = i - u * C;
-            const float pc = __fdiv_rn(expf(in[u * bs + 5 + c] - s_mx[u]), s_inv[u]);
+            const float pc = __fdiv_rn(in[u * bs + 5 + c], s_inv[u]);
             if (p.cls_prob) p.cls_prob[o0 + i] = pc;
             if (p.cls_spec) p.cls_spec[o0 + i] = __fmul_rn(pc, s_conf[u]);
         }
@@ -122,7 +132,7 @@ __global__ void __launch_bounds__(kThreads) yh_decode_kernel(const DecodeParams 
             const long long o0 = cell0 * C;
             for (int i = tid; i < total; i += kThreads) {
                 const int q = i / C, c = i - q * C;
-                p.cls_prob[o0 + i] = __fdiv_rn(expf(in[q * cf + 5 * A + c] - s_mx[q]), s_inv[q]);
+                p.cls_prob[o0 + i] = __fdiv_rn(in[q * cf + 5 * A + c], s_inv[q]);
             }
         }
         if (p.cls_spec) {
@@ -131,11 +141,27 @@ __global__ void __launch_bounds__(kThreads) yh_decode_kernel(const DecodeParams 
             for (int i = tid; i < total; i += kThreads) {
                 const int u = i / C, c = i - u * C;
                 const int q = u / A;
-                const float pc = __fdiv_rn(expf(in[q * cf + 5 * A + c] - s_mx[q]), s_inv[q]);
+                const float pc = __fdiv_rn(in[q * cf + 5 * A + c], s_inv[q]);
                 p.cls_spec[o0 + i] = __fmul_rn(pc, s_conf[u]);
             }
         }
     }
+}
+
+template <int TV, int TA, int TC>
+int launch_decode(const DecodeParams& p, unsigned grid, size_t smem, void* stream) {
+    static size_t configured[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (smem > 48 * 1024 && smem > configured[dev]) {
+        int rc = yh_check_cuda(cudaFuncSetAttribute(yh_decode_kernel<TV, TA, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                               "cudaFuncSetAttribute(decode)");
+        if (rc) return rc;
+        configured[dev] = smem;
+    }
+    yh_decode_kernel<TV, TA, TC><<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+    return yh_check_cuda(cudaGetLastError(), "yh_decode launch");
 }
 
 int decode_impl(int version, const float* y, int n, int s_h, int s_w, int a, int c,
@@ -162,20 +188,12 @@ int decode_impl(int version, const float* y, int n, int s_h, int s_w, int a, int
     p.tma_in = ((uintptr_t)y & 15) == 0;
     const size_t smem = (size_t)p.cells_per_chunk * cf * 4 + (size_t)3 * p.cells_per_chunk * a * 4 + 16;
     YH_REQUIRE(smem <= 227 * 1024, YH_ERR_UNSUPPORTED, "cell too wide for shared memory (%d floats)", cf);
-    static size_t configured[64] = {0};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64) dev = 0;
-    if (smem > 48 * 1024 && smem > configured[dev]) {
-        rc = yh_check_cuda(cudaFuncSetAttribute(yh_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                           "cudaFuncSetAttribute(decode)");
-        if (rc) return rc;
-        configured[dev] = smem;
-    }
     const long long grid = (p.total_cells + p.cells_per_chunk - 1) / p.cells_per_chunk;
     YH_REQUIRE(grid < (1ll << 31), YH_ERR_UNSUPPORTED, "too many chunks");
-    yh_decode_kernel<<<(unsigned)grid, kThreads, smem, (cudaStream_t)stream>>>(p);
-    return yh_check_cuda(cudaGetLastError(), "yh_decode launch");
+    // compile-time geometries for the shapes the reference uses (VOC: YOLOv2 5 anchors x 20 classes, YOLOv1 B=2, C=20)
+    if (version == 2 && a == 5 && c == 20) return launch_decode<2, 5, 20>(p, (unsigned)grid, smem, stream);
+    if (version == 1 && a == 2 && c == 20) return launch_decode<1, 2, 20>(p, (unsigned)grid, smem, stream);
+    return launch_decode<0, 0, 0>(p, (unsigned)grid, smem, stream);
 }
 
 }  // namespace

@@ -52,6 +52,15 @@ def run(name, case, conf_thre, iou_thre=0.45):
 
     t_train = time_graph(train, sets)
     t_post = time_graph(post, sets)
+    # predict(): the six decoded outputs (49 floats per predictor)
+    dec_out = [ops.decode(s["y"], **kw) for s in sets[:2]]
+    lib_kw = dict(kw)
+
+    def dec(s):
+        ops.decode(s["y"], **lib_kw)
+
+    t_dec = time_graph(dec, sets[:2], reps=20)
+    del dec_out
     kept = int(sets[0]["post"]["keep_cnt"].clamp(max=128).sum().item())
     p = case.image_bytes
     b_train = 2 * p * case.n + 48 * case.m
@@ -60,7 +69,9 @@ def run(name, case, conf_thre, iou_thre=0.45):
                           train_us=round(t_train, 2), train_MB=round(b_train / 1e6, 2),
                           train_frac=round(b_train / t_train / 1e3 / PEAK, 3),
                           post_us=round(t_post, 2), post_MB=round(b_post / 1e6, 2),
-                          post_frac=round(b_post / t_post / 1e3 / PEAK, 3), kept_per_image=round(kept / case.n, 1))), flush=True)
+                          post_frac=round(b_post / t_post / 1e3 / PEAK, 3), kept_per_image=round(kept / case.n, 1),
+                          decode_us_incl_alloc=round(t_dec, 2),
+                          decode_MB=round((p * case.n + 49 * 4 * case.n * case.s_h * case.s_w * case.a) / 1e6, 2))), flush=True)
 
 
 run("cfg1 v1 7x7 B=2 N=8", synthetic.cfg1(), 0.5)
