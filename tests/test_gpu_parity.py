@@ -999,3 +999,33 @@ def test_fused_sgd_equals_torch_sgd_on_a_model(cuda_device):
     for pa, pb in zip(a.parameters(), b.parameters()):
         assert torch.allclose(pa, pb, rtol=1e-6, atol=1e-7)
     reset_state()
+
+
+# ------------------------------------------------------------------------------------------
+# detect(): the dict of lists (reference models/yolov2.py:651-745)
+# ------------------------------------------------------------------------------------------
+def test_detect_returns_the_reference_dict_from_the_golden_head(cuda_device):
+    """detect(img) and detect_batch on the head-only model with a head tensor from the golden file: the
+    lists must hold what the reference's predict -> nms -> argmax chain produced for that image
+    (v2_nms_default.npz was generated with the reference's default thresholds 0.9 / 0.5)."""
+    from odcp_b200.models.yolov2 import YOLOv2Head
+    case, z = load_golden("v2_nms_default.npz")
+    assert float(z["conf_thre"]) == 0.9 and float(z["iou_thre"]) == 0.5
+    cnt = z["nms_cnt"]
+    start = np.concatenate([[0], np.cumsum(cnt)])
+    m = YOLOv2Head(num_cls=case.c).to(cuda_device)
+    img = np.zeros((case.height, case.width, 3), dtype=np.float32)
+    for n in range(case.n):
+        m.set_head_output(case.y[n:n + 1].to(cuda_device))
+        d = m.detect(img)  # the reference's defaults: conf 0.9, IoU 0.5
+        sl = slice(start[n], start[n + 1])
+        assert sorted(d) == ["bbox_list", "cls_spec_conf_score_list", "conf_score_list", "lbl_list"]
+        assert len(d["bbox_list"]) == cnt[n] > 0
+        assert np.allclose(np.array(d["bbox_list"]), z["nms_bbox"][sl], rtol=1e-5, atol=1e-4)
+        assert np.allclose(np.array(d["conf_score_list"]), z["nms_conf"][sl], rtol=1e-6, atol=1e-7)
+        assert d["lbl_list"] == [m.cls_list[i] for i in z["nms_cls_spec"][sl].argmax(-1)]
+        assert np.allclose(np.array(d["cls_spec_conf_score_list"]), z["nms_cls_spec"][sl].max(-1), rtol=1e-5, atol=1e-7)
+    m.set_head_output(case.y.to(cuda_device))
+    many = m.detect_batch(torch.zeros(case.n, case.height, case.width, 3, device=cuda_device), 0.9, 0.5)
+    assert [len(d["bbox_list"]) for d in many] == cnt.tolist()
+    assert np.allclose(np.array(many[1]["bbox_list"]), z["nms_bbox"][start[1]:start[2]], rtol=1e-5, atol=1e-4)
