@@ -105,6 +105,7 @@ int main(int argc, char** argv) {
     run("train+post (input ready)", tb + floats * 4, [&](Set& s) { int rc = train(s); return rc ? rc : post(s); });
     train_ov = true;
     run("train+post (both overlapped)", tb + floats * 4, [&](Set& s) { int rc = train(s); return rc ? rc : post(s); });
+    run("post+train (both overlapped)", tb + floats * 4, [&](Set& s) { int rc = post(s); return rc ? rc : train(s); });
     run("train (overlapped, back to back)", tb, train);
     post_flags = 0;
     run("train overlapped + post plain", tb + floats * 4, [&](Set& s) { int rc = train(s); return rc ? rc : post(s); });
