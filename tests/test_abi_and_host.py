@@ -185,6 +185,16 @@ def test_mixin_composes_with_the_unmodified_reference_model():
         ours = list(inspect.signature(HeadOps.get_loss).parameters)
         theirs = list(inspect.signature(ref_v2.YOLOv2.get_loss).parameters)
         assert len(ours) == len(theirs) == 14 and ours[-5:] == theirs[-5:]  # self + 13 arguments, same lambda names
+        # the optimizer: run_one_epoch resolves the module-level name `SGD` (models/yolov2.py:7, :1254)
+        import torch.optim
+        from odcp_b200.models import patch_reference
+        from odcp_b200.optim import SGD as FusedSGD
+        assert ref_v2.SGD is torch.optim.SGD
+        assert "SGD(" in inspect.getsource(ref_v2.YOLOv2.run_one_epoch)
+        patch_reference(ref_yolov2=ref_v2, fused_sgd=True)
+        assert ref_v2.SGD is FusedSGD and ref_v2.YOLOv2.get_loss is HeadOps.get_loss
+        for kw in ("lr", "momentum", "weight_decay"):  # the keywords the reference passes
+            assert kw in inspect.signature(FusedSGD.__init__).parameters
     finally:
         sys.path.remove("/root/reference")
         for k in [k for k in sys.modules if k == "models" or k.startswith("models.") or k == "config"]:
