@@ -331,7 +331,10 @@ def main():
         ROUNDS = 4
         G = R * ROUNDS
         g_full = capture(lambda: [step(s, first=(i == 0)) for _ in range(ROUNDS) for i, s in enumerate(sets)])
-        g_one = [capture(lambda s=s: step(s)) for s in sets[: min(R, max(K % G, W % G, 1))]] if (K % G or W % G) else []
+        # step counts that are not a multiple of G: one more graph of exactly the remaining steps (same chain)
+        g_rem = {}
+        for rem in {K % G, W % G} - {0}:
+            g_rem[rem] = capture(lambda rem=rem: [step(sets[j % R], first=(j % R == 0)) for j in range(rem)])
         # per-kernel graphs: stream-ordered launches (only launch latency hidden) for the roofline of one
         # launch, and the overlapped variant for the sustained rate of back-to-back launches
         g_train = capture(lambda: [step(s, post=False, overlap=False) for s in sets])
@@ -342,8 +345,8 @@ def main():
         def run_steps(n):
             for _ in range(n // G):
                 g_full.replay()
-            for i in range(n % G):
-                g_one[i % len(g_one)].replay()
+            if n % G:
+                g_rem[n % G].replay()
 
         def barrier():
             if dist is not None:
