@@ -711,6 +711,22 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
         if (tid == 0) p.keep_cnt[img] = kept;
         const int nout = min(kept, p.max_out);
         const bool want_cls = p.out_cls_spec || p.out_label || p.out_score;
+        if (picked || !want_cls) {
+            // nothing left to compute: one thread per kept box copies its record out
+            for (int t = tid; t < nout; t += kThreads) {
+                const int i = ca.keep[t];
+                const size_t o = (size_t)img * p.max_out + t;
+                p.keep_idx[o] = ca.s_idx[i];
+                if (p.out_conf) p.out_conf[o] = ca.s_conf[i];
+                if (p.out_bbox) p.out_bbox[o] = ca.s_box[i];
+                if (picked) {
+                    if (p.out_label) p.out_label[o] = ca.s_lab[i];
+                    if (p.out_score) p.out_score[o] = s_score[i];
+                }
+            }
+            NT(13);
+            return;
+        }
         for (int t0 = 0; t0 < nout; t0 += kThreads / kPick) {
             if (t0 + (32 / kPick) * warp >= nout) break;
             const int t = t0 + tid / kPick;
@@ -730,12 +746,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
                     if (p.out_bbox) p.out_bbox[o] = ca.s_box[i];
                 }
             }
-            if (picked) {
-                if (act && sub == 2) {
-                    if (p.out_label) p.out_label[o] = ca.s_lab[i];
-                    if (p.out_score) p.out_score[o] = s_score[i];
-                }
-            } else if (want_cls) {
+            if (want_cls) {  // (cls_spec rows requested: the full pick, four lanes per kept box)
                 int lab;
                 float sc;
                 pick(act ? win + (fsh + cls_off(idx)) : nullptr, conf, act, with_spec,
