@@ -55,6 +55,16 @@ def parse_args():
                          "Default: one stream; the post-process is launched as a programmatic dependent with "
                          "YH_POST_INPUT_READY, so it already overlaps the train head's tail")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 400)")
+    ap.add_argument("--e2e-return-dy", action="store_true",
+                    help="e2e: also copy dL/dy (21.6 MB) back to the host every step.  Default: the gradient stays on "
+                         "the device (where the backbone's backward consumes it); the step's host-side result is the "
+                         "loss, its five terms and the kept boxes")
+    ap.add_argument("--repeats", type=int, default=0,
+                    help="repetitions of the timed K-step region (median reported); 0 = enough for ~25 ms of "
+                         "device time, between 3 and 15")
+    ap.add_argument("--gate-us", type=float, default=150.0,
+                    help="device-side gate in front of every timed region: the GPU spins this long while the host "
+                         "enqueues the start event, the K steps and the stop event, so the region holds no launch gap")
     return ap.parse_args()
 
 
@@ -215,6 +225,33 @@ def nvml_index(local_rank):
     return local_rank
 
 
+def source_stamp():
+    """Hash of the kernel sources (csrc/*.cu, *.cuh, include/*.h): ties an ncu capture to the build it profiled."""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    pkg = os.path.join(ROOT, "object-detection-collection-pytorch_b200", "csrc")
+    for f in sorted(glob.glob(os.path.join(pkg, "*.cu")) + glob.glob(os.path.join(pkg, "*.cuh")) +
+                    glob.glob(os.path.join(ROOT, "include", "*.h"))):
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic():
+    """DRAM bytes per launch of the dominant kernel from the ncu --set full capture under profiles/
+    (profiles/traffic.json, written by profiles/ncu_traffic.py).  Only a capture of THIS build counts: the file
+    carries the source stamp of the build it profiled, a stale one is reported as null."""
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(prof))
+    except Exception:  # noqa: BLE001
+        return None, "no profiles/traffic.json"
+    if t.get("source_stamp") != source_stamp():
+        return None, "profiles/traffic.json is from another build (stamp %s != %s)" % (t.get("source_stamp"), source_stamp())
+    return t.get("dram_bytes_per_launch"), t.get("source")
+
+
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
@@ -352,36 +389,55 @@ def main():
             if dist is not None:
                 dist.barrier()
 
+        # Warm-up: W steps, then two rehearsals of the timed region itself, so every graph the region
+        # replays (the remainder graph of K % G steps included) has been uploaded and run before time starts.
         run_steps(W)
         stream.synchronize()
+        sm_hz = 1e6 * float(torch.cuda.get_device_properties(dev).clock_rate) / 1e3  # clock_rate is in kHz
+        gate_cycles = int(args.gate_us * 1e-6 * sm_hz)
 
-        # ---- timed region: exactly K steps, device time, max over ranks
+        def timed_region(ev0, ev1):
+            """Exactly K steps between two events.  A gate kernel keeps the GPU busy while the host
+            enqueues ev0, the graph launches and ev1: the region then starts with its first kernel already
+            queued behind the event (no idle-GPU launch latency inside it)."""
+            if gate_cycles > 0:
+                torch.cuda._sleep(gate_cycles)
+            ev0.record(stream)
+            run_steps(K)
+            ev1.record(stream)
+
+        for _ in range(2):
+            timed_region(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            stream.synchronize()
+
+        # ---- timed: `reps` regions of exactly K steps each, device time, barrier + synchronize on both
+        # sides of every region; per region the MAX over ranks, reported: the median region (min/max next to it)
+        est_ms = max(K * 0.014, 1e-3)
+        reps = args.repeats or int(min(15, max(3, round(25.0 / est_ms))))
         sampler = ClockSampler(nvml_index(local_rank))
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
         barrier()
         torch.cuda.synchronize()
         sampler.start()
-        ev0.record(stream)
-        run_steps(K)
-        ev1.record(stream)
-        torch.cuda.synchronize()
-        barrier()
-        ms = ev0.elapsed_time(ev1)
-        window = "timed region"
-        if len(sampler.samples) < 5:  # the timed region was too short to sample: keep the same load on
+        for ev0, ev1 in evs:
+            barrier()
+            torch.cuda.synchronize()
+            timed_region(ev0, ev1)
+            torch.cuda.synchronize()
+            barrier()
+        region_ms = torch.tensor([a.elapsed_time(b) for a, b in evs], device=dev, dtype=torch.float64)
+        window = "the %d timed regions" % reps
+        if len(sampler.samples) < 5:  # the timed regions were too short to sample: keep the same load on
             t_end = time.perf_counter() + 0.25
             while time.perf_counter() < t_end:
                 g_full.replay()
             stream.synchronize()
-            window = "timed region + 0.25 s of the same graph replayed right after it"
+            window = "the %d timed regions + 0.25 s of the same graph replayed right after them" % reps
         sampler.stop()
         if dist is not None:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-            # the only data-path exchange: the scalar loss terms (6 floats per step), reduced in a batch
-            terms = torch.stack([torch.cat([s["out"]["terms"], s["out"]["loss"].reshape(1)]) for s in sets])
-            dist.all_reduce(terms)
+            dist.all_reduce(region_ms, op=dist.ReduceOp.MAX)
+        region_ms = sorted(float(v) for v in region_ms.tolist())
+        ms = region_ms[len(region_ms) // 2]
         loss_value = float(sets[0]["out"]["loss"].item())
 
         # ---- per-kernel durations (train head alone / post-process alone), same rotation
@@ -422,33 +478,31 @@ def main():
     def gbs(nbytes, ms_):
         return nbytes / (ms_ * 1e-3) / 1e9
 
-    achieved = gbs(train_bytes, train_ov_ms)
+    # The dominant kernel's launch duration is the stream-ordered one (every launch starts after the one in
+    # front of it has completed: what a drop-in caller behind a conv gets, and what ncu's serialised per-launch
+    # time corresponds to).  The issue interval of back-to-back launches with the overlap promise -- the regime
+    # of the timed region -- is reported under `sustained`, the whole step of the timed region under `step`.
+    achieved = gbs(train_bytes, train_ms)
     roofline = {"bound": "hbm",
                 "kernel": "yh_train_kernel (fused decode+assign+loss+dL/dy) + its one-warp finalize dependent",
-                "regime": "back-to-back launches over the rotating buffer sets, programmatic dependent launches "
-                          "with the overlap promise (yh_v2_train_overlapped) as in the timed region; duration = "
-                          "CUDA-event time of the graph / launches",
+                "regime": "stream-ordered launches over the rotating buffer sets (each launch starts after the previous "
+                          "one has completed; only launch latency hidden); duration = CUDA-event time of the graph / launches",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": train_bytes,
-                "us_per_launch": train_ov_ms * 1e3,
-                "isolated": {"what": "stream-ordered launches: each launch starts after the previous one has completed "
-                                     "(only launch latency hidden)",
-                             "train_us_per_launch": train_ms * 1e3, "train_achieved": gbs(train_bytes, train_ms),
-                             "train_frac": gbs(train_bytes, train_ms) / peak,
-                             "post_us_per_launch": post_ms * 1e3, "post_frac": gbs(post_bytes, post_ms) / peak},
-                "postprocess_kernel": {"us_per_launch": post_ov_ms * 1e3, "algorithmic_bytes_per_launch": post_bytes,
-                                       "achieved": gbs(post_bytes, post_ov_ms), "frac": gbs(post_bytes, post_ov_ms) / peak,
-                                       "regime": "back-to-back launches with YH_POST_INPUT_READY"},
+                "us_per_launch": train_ms * 1e3,
+                "sustained": {"what": "back-to-back launches with the overlap promise (yh_v2_train_overlapped / "
+                                      "YH_POST_INPUT_READY), as in the timed region: issue interval = graph time / launches",
+                              "train_us_per_launch": train_ov_ms * 1e3, "train_achieved": gbs(train_bytes, train_ov_ms),
+                              "train_frac": gbs(train_bytes, train_ov_ms) / peak,
+                              "post_us_per_launch": post_ov_ms * 1e3, "post_frac": gbs(post_bytes, post_ov_ms) / peak},
+                "postprocess_kernel": {"us_per_launch": post_ms * 1e3, "algorithmic_bytes_per_launch": post_bytes,
+                                       "achieved": gbs(post_bytes, post_ms), "frac": gbs(post_bytes, post_ms) / peak,
+                                       "regime": "stream-ordered launches"},
                 "step": {"what": "train head + post-process of the timed region (the north-star target: >= 0.60)",
                          "algorithmic_bytes": train_bytes + post_bytes, "us": ms / K * 1e3,
                          "achieved": gbs(train_bytes + post_bytes, ms / K),
                          "frac": gbs(train_bytes + post_bytes, ms / K) / peak}}
-    prof = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(prof):
-        try:
-            roofline["traffic"] = json.load(open(prof)).get("yh_train_kernel_dram_bytes_per_launch")
-        except Exception:  # noqa: BLE001
-            pass
+    roofline["traffic"], roofline["traffic_source"] = measured_traffic()
 
     # ---- e2e: host buffers in, host buffers out
     e2e = None
@@ -456,7 +510,8 @@ def main():
         ke = args.e2e_steps or max(20, min(K, 400))
         pipe = HostHeadPipeline(B, case.s_h, case.s_w, case.a, case.c, img_hw=(case.height, case.width),
                                 anchors=case.anchors, lambdas=lam, conf_thre=CONF_THRE, iou_thre=IOU_THRE,
-                                max_out=MAX_OUT, max_boxes=m_local, depth=3, device=dev)
+                                max_out=MAX_OUT, max_boxes=m_local, depth=3, device=dev,
+                                compute_dy=True, return_dy=args.e2e_return_dy)
         gt_h = targets.records_to_tensor(case.rec)
         off_h = torch.from_numpy(case.gt_off)
         for d in range(pipe.depth):  # fill every slot's pinned staging buffers once (the "producer")
@@ -492,8 +547,9 @@ def main():
         assert abs(float(res["loss"]) - loss_value) <= 1e-6 * abs(loss_value), (float(res["loss"]), loss_value)
         e2e = {"value": images * ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes(m_local),
                "d2h_bytes_per_step": pipe.d2h_bytes(), "steps": ke, "ms_per_step": 1e3 * e2e_s / ke,
-               "path": "HostHeadPipeline: pinned host y+GT -> H2D -> yh_v2_train + yh_v2_postprocess -> D2H loss, "
-                       "dL/dy, kept boxes; 3 slots, copy/compute streams overlapped"}
+               "path": "HostHeadPipeline: pinned host y+GT -> H2D -> yh_v2_train (loss + dL/dy) + yh_v2_postprocess -> "
+                       "D2H of loss, terms and kept boxes%s; 3 slots, copy/compute streams overlapped"
+                       % (" and dL/dy" if args.e2e_return_dy else " (dL/dy is computed every step and stays on the device)")}
 
     # ---- CPU baseline (rank 0, N=1 only)
     cpu = None
@@ -508,7 +564,10 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / K, "repeats": reps,
+            "region_ms": {"median": ms, "min": region_ms[0], "max": region_ms[-1],
+                          "what": "device time of the K-step region, max over ranks, per repetition"},
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(B, R, not args.two_streams),
             "clocks": sampler.summary(window), "e2e": e2e, "gpu_launches": 3 * K,
             "roofline": roofline, "cpu_baseline": cpu, "loss": loss_value,

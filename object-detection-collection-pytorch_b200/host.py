@@ -22,7 +22,11 @@ from . import ops
 class HostHeadPipeline:
     def __init__(self, n, s_h, s_w, a, c, *, version=2, img_hw, anchors=None, lambdas, conf_thre=0.5,
                  iou_thre=0.45, max_out=128, max_boxes=None, depth=3, device=None, return_dy=True,
-                 class_aware=False):
+                 compute_dy=True, class_aware=False):
+        """`compute_dy`: the train head also produces dL/dy (the backward of get_loss).  `return_dy`: that
+        gradient is copied back to host memory as well; with return_dy=False it stays in the slot's device
+        buffer (`device_dy(ticket)`), which is where a caller whose backbone runs on the GPU consumes it --
+        the step's host-side result is then the loss, the five terms and the detections."""
         if not torch.cuda.is_available():
             raise RuntimeError("HostHeadPipeline needs a CUDA device (no CPU path)")
         self.dev = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
@@ -30,6 +34,7 @@ class HostHeadPipeline:
         self.img_hw, self.anchors, self.lambdas = img_hw, anchors, lambdas
         self.conf_thre, self.iou_thre, self.max_out = conf_thre, iou_thre, max_out
         self.class_aware = class_aware
+        self.compute_dy = bool(compute_dy or return_dy)
         self.return_dy = return_dy
         self.depth = depth
         self.max_boxes = int(max_boxes if max_boxes is not None else 128 * n)
@@ -130,7 +135,7 @@ class HostHeadPipeline:
             self.s_run.wait_event(s["ev_in"])
             ops.train_head(s["y"], s["gt"][:m], s["off"], version=self.version, img_hw=self.img_hw,
                            lambdas=self.lambdas, anchors=self.anchors, boxes_per_cell=self.a,
-                           m_global=m_global, want_grad=self.return_dy,
+                           m_global=m_global, want_grad=self.compute_dy,
                            out=dict(dy=s["dy"], loss=s["loss"], terms=s["terms"]))
             self.s_run.wait_event(s["ev_post"])
             s["ev_run"].record(self.s_run)
@@ -149,6 +154,10 @@ class HostHeadPipeline:
         can write the head tensor there directly and pass staged=True."""
         s = self.slots[(self._ticket if ticket is None else ticket) % self.depth]
         return s["h_y"], s["h_gt"], s["h_off"]
+
+    def device_dy(self, ticket):
+        """The device tensor holding dL/dy of step `ticket` (valid until the slot is reused)."""
+        return self.slots[ticket % self.depth]["dy"] if self.compute_dy else None
 
     def result(self, ticket):
         """Block until step `ticket` is back in host memory; returns views of the pinned result
