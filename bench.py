@@ -45,15 +45,19 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=4000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (0: the workload's own: 256 / 512)")
     ap.add_argument("--sets", type=int, default=8, help="rotating buffer sets (total must exceed L2)")
     ap.add_argument("--cpu-sample", type=int, default=32, help="images in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--two-streams", action="store_true",
-                    help="issue the post-process of a step on a second stream (fork/join inside the step). "
-                         "Default: one stream; the post-process is launched as a programmatic dependent with "
-                         "YH_POST_INPUT_READY, so it already overlaps the train head's tail")
+    ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS),
+                    help="headline: the configuration the north-star target is quoted on (YOLOv2 13x13x5, C=20, 1..5 "
+                         "boxes/image); cfg5: BASELINE config 5 (19x19, batch 512 unless --batch, 50..100 boxes/image)")
+    ap.add_argument("--unfused", action="store_true",
+                    help="a step = the two separate calls (yh_v2_train + yh_v2_postprocess: 3 launches, y read twice) "
+                         "instead of the fused step (yh_v2_train_post: 2 launches, y read once)")
+    ap.add_argument("--no-collective", action="store_true",
+                    help="N > 1: leave the in-kernel peer-memory reduction of the loss terms out of the steps")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 400)")
     ap.add_argument("--e2e-return-dy", action="store_true",
                     help="e2e: also copy dL/dy (21.6 MB) back to the host every step.  Default: the gradient stays on "
@@ -68,23 +72,46 @@ def parse_args():
     return ap.parse_args()
 
 
-def workload_config(batch, sets=None, serial=False):
+def _headline_case(n):
+    from odcp_b200 import synthetic
+    return synthetic.headline(n=n)
+
+
+def _cfg5_case(n):
+    from odcp_b200 import synthetic
+    return synthetic.cfg5(n=n)
+
+
+WORKLOADS = {
+    "headline": dict(case=_headline_case, batch=256, grid=[13, 13], image=[416, 416], boxes="U{1..5}",
+                     cands="~50 of 845", name="yolov2_head_13x13x5_c20"),
+    "cfg5": dict(case=_cfg5_case, batch=512, grid=[19, 19], image=[608, 608], boxes="U{50..100}",
+                 cands="~100 of 1805", name="yolov2_head_19x19x5_c20_dense_gt"),
+}
+
+
+def workload_config(workload, batch, sets=None, set_bytes=0, fused=True, collective=None):
+    w = WORKLOADS[workload]
     cfg = {
-        "workload": "yolov2_head_13x13x5_c20_b%d_train(decode+assign+loss+bwd)+postprocess(conf%.2f,nms_iou%.2f)"
-                    % (batch, CONF_THRE, IOU_THRE),
-        "batch_per_gpu": batch, "grid": [13, 13], "anchors": 5, "classes": 20, "image": [416, 416],
-        "gt_boxes_per_image": "U{1..5}", "candidates_per_image": "~50 of 845",
+        "workload": "%s_b%d_train(decode+assign+loss+bwd)+postprocess(conf%.2f,nms_iou%.2f)"
+                    % (w["name"], batch, CONF_THRE, IOU_THRE),
+        "batch_per_gpu": batch, "grid": w["grid"], "anchors": 5, "classes": 20, "image": w["image"],
+        "gt_boxes_per_image": w["boxes"], "candidates_per_image": w["cands"],
     }
     if sets is not None:
-        cfg["l2"] = "%d rotating input/output buffer sets per GPU (inputs+outputs %.0f MB > 126 MB L2)" % (
-            sets, sets * 2 * batch * 84500 / 1e6)
-        if serial:
-            cfg["streams"] = ("one stream, programmatic dependent launches; a graph replay is 4 passes over the %d buffer "
-                              "sets; every kernel but the first of a pass promises that its buffers are not in use by the "
-                              "kernels in front of it (rotating sets) and overlaps their tails; the first kernel of every "
-                              "pass waits for everything before it" % (sets or 0))
-        else:
-            cfg["streams"] = "train head and post-process of a step on two streams (parallel graph branches), steps in order"
+        cfg["l2"] = "%d rotating buffer sets per GPU, inputs + outputs + workspace distinct per set (%.0f MB > 126 MB L2)" % (
+            sets, sets * set_bytes / 1e6)
+        cfg["step"] = ("fused step: ONE call yh_v2_train_post = train kernel (lists the NMS candidates while it streams y) + "
+                       "candidates-only post-process kernel (also finishes the loss); y read once" if fused else
+                       "two separate calls: yh_v2_train (+ finalize kernel) + yh_v2_postprocess; y read twice")
+        cfg["streams"] = ("one stream, programmatic dependent launches; a graph replay is 4 passes over the %d buffer sets; "
+                          "every call but the first of a pass is an overlapped call (include/yolohead.h, THE OVERLAP "
+                          "CONTRACT) and runs next to the tails of the kernels in front of it; the first call of every "
+                          "pass waits for everything before it" % sets)
+        cfg["timing"] = ("the timed K-step region is rehearsed twice (its own graphs), starts behind a device-side gate "
+                         "kernel and is repeated; value = the median region, max over ranks per region")
+        if collective is not None:
+            cfg["collective"] = collective
     return cfg
 
 
@@ -99,10 +126,10 @@ def cpu_port_step(case, lambdas):
     O.postprocess_torch(case.y, case.height, case.width, case.version, case.anchors, CONF_THRE, IOU_THRE)
 
 
-def time_cpu_port(sample, reps, warm):
+def time_cpu_port(sample, reps, warm, workload="headline"):
     from odcp_b200 import synthetic
     torch.set_num_threads(os.cpu_count() or 1)
-    case = synthetic.headline(n=sample)
+    case = WORKLOADS[workload]["case"](sample)
     for _ in range(warm):
         cpu_port_step(case, synthetic.DEFAULT_LAMBDAS)
     ts = []
@@ -124,7 +151,7 @@ def run_reference(args):
     sample = args.cpu_sample
     steps = max(1, min(args.steps, 20))
     warm = max(1, min(args.warmup, 2))
-    case, ts = time_cpu_port(sample, steps, warm)
+    case, ts = time_cpu_port(sample, steps, warm, args.workload)
     total = float(np.sum(ts))
     value = sample * len(ts) / total
     cores = torch.get_num_threads()
@@ -132,11 +159,12 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": len(ts), "warmup": warm, "ms_per_step": 1e3 * total / len(ts), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.batch),
+        "config": workload_config(args.workload, args.batch or WORKLOADS[args.workload]["batch"]),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "%d-image sample of the batch-%d workload per step (the reference's per-box "
                                    "replication grows as M*S*S*A); torch %s CPU, %d threads, os.cpu_count()=%s"
-                                   % (sample, args.batch, torch.__version__, cores, os.cpu_count())},
+                                   % (sample, args.batch or WORKLOADS[args.workload]["batch"], torch.__version__, cores,
+                                      os.cpu_count())},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -301,57 +329,69 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    K, W, R, B = args.steps, max(args.warmup, 3), args.sets, args.batch
+    K, W, R = args.steps, max(args.warmup, 3), args.sets
+    B = args.batch or WORKLOADS[args.workload]["batch"]
     lam = synthetic.DEFAULT_LAMBDAS
-    case = synthetic.headline(n=B)
-    kw = dict(version=2, img_hw=(case.height, case.width), anchors=case.anchors)
+    case = WORKLOADS[args.workload]["case"](B)
+    conf_thre, iou_thre = CONF_THRE, IOU_THRE
+    kw = dict(img_hw=(case.height, case.width), anchors=case.anchors)
     m_local = case.m
     m_global = m_local * world  # every rank holds a shard with the same box count (weak scaling)
+    fused = not args.unfused
 
-    # rotating buffer sets: distinct addresses, > L2 in total
+    # Sharded batch (N > 1): the six loss sums of all ranks are summed INSIDE the step's last kernel over NVLink
+    # peer memory (odcp_b200.dist.PeerExchange, csrc/yh_finalize.cuh) -- the scalar-loss reduction of the
+    # north star, in the timed region, every step, without an NCCL call.
+    xch = None
+    if dist is not None and not args.no_collective:
+        from odcp_b200.dist import PeerExchange
+        xch = PeerExchange(device=dev)
+
+    # rotating buffer sets: distinct addresses (inputs, outputs, workspace), > L2 in total
     gt = targets.records_to_tensor(case.rec, dev)
     off = torch.from_numpy(case.gt_off).to(dev)
     y0 = case.y.to(dev)
-    sets = []
-    for i in range(R):
-        s = dict(y=y0.clone(), gt=gt.clone(), off=off.clone(),
-                 out=dict(dy=torch.empty_like(y0), loss=torch.empty((), device=dev), terms=torch.empty(5, device=dev)))
-        sets.append(s)
+    sets = [dict(y=y0.clone(), gt=gt.clone(), off=off.clone(), res=None, res_nc=None, lists=None, tr=None, tr_ov=None,
+                 post=None) for _ in range(R)]
+    set_bytes = 2 * y0.numel() * 4
 
     stream = torch.cuda.Stream(dev)
-    side = torch.cuda.Stream(dev)
-    fork_ev = [torch.cuda.Event() for _ in range(2)]
 
-    # Overlap of consecutive kernels (programmatic dependent launch).  Every kernel of this path is
-    # launched as a programmatic dependent, which hides launch latency.  On top of that a call may
-    # promise that its buffers are not touched by the kernels still draining in front of it
-    # (`input_ready`): the kernel then runs next to their tails and only waits for them before it
-    # completes (yh_v2_train_overlapped, YH_POST_INPUT_READY).  The bench rotates R buffer sets, so the
-    # promise holds for every step of a graph replay except that a set comes round again in the NEXT
-    # replay: the first kernel of every captured graph is therefore launched without the promise -- it
-    # waits at its start for everything before it -- which bounds the overlap chain to one replay.
-    def run_post(s, ready=True):
-        s["post"] = ops.postprocess(s["y"], conf_thre=CONF_THRE, iou_thre=IOU_THRE, max_out=MAX_OUT,
-                                    want_cls_spec=False, out=s.get("post"), input_ready=ready, **kw)
+    # One step = train head (decode + assignment + loss + dL/dy) + post-process (threshold + NMS + class pick) of
+    # the same head tensor.  Default: the fused step, ONE call (yh_v2_train_post): the train kernel lists the
+    # candidates while it streams y, the post-process kernel works from those lists and also finishes the loss --
+    # 2 launches, y read once.  --unfused: the two separate calls (3 launches, y read twice).
+    # Overlap of consecutive kernels: every kernel of the path is a programmatic dependent launch.  A call may
+    # additionally promise that none of its buffers is in use by any kernel launched since the last call without
+    # that promise (rotating sets, include/yolohead.h "THE OVERLAP CONTRACT"); it then runs next to the tails of
+    # the kernels in front of it.  The first call of every pass over the R sets makes no promise -- it waits at
+    # its start for everything before it -- which bounds the overlap chain to the rotation length.
+    def step(s, first, exchange=xch, key="res"):
+        if fused:
+            s[key] = ops.train_post(s["y"], s["gt"], s["off"], lambdas=lam, conf_thre=conf_thre, iou_thre=iou_thre,
+                                    m_global=m_global, max_out=MAX_OUT, want_cls_spec=False, out=s[key],
+                                    overlapped=not first, exchange=exchange, **kw)
+        else:
+            tr = ops.train_head(s["y"], s["gt"], s["off"], version=2, lambdas=lam, m_global=m_global,
+                                out=(s[key] or {}).get("train"), input_ready=not first, exchange=exchange, **kw)
+            po = ops.postprocess(s["y"], version=2, conf_thre=conf_thre, iou_thre=iou_thre, max_out=MAX_OUT,
+                                 want_cls_spec=False, out=(s[key] or {}).get("post"), input_ready=True, **kw)
+            s[key] = dict(train=tr, post=po)
 
-    def step(s, post=True, train=True, first=True, overlap=True):
-        """One step = one train-head call + one post-process call on the same head tensor, in stream
-        order (with --two-streams: fork/join inside the step, parallel branches of the captured graph).
-        `first`: first step of a captured graph (its first kernel makes no promise)."""
-        both = post and train and args.two_streams
-        if both:
-            fork_ev[0].record(stream)
-            side.wait_event(fork_ev[0])
-            with torch.cuda.stream(side):
-                run_post(s, ready=False)
-                fork_ev[1].record(side)
-        if train:
-            ops.train_head(s["y"], s["gt"], s["off"], lambdas=lam, m_global=m_global, out=s["out"],
-                           input_ready=overlap and not first and not args.two_streams, **kw)
-        if both:
-            stream.wait_event(fork_ev[1])
-        elif post:
-            run_post(s, ready=overlap and not args.two_streams and (train or not first))
+    # the kernels on their own (for the roofline lines): stream-ordered and overlapped
+    def train_only(s, overlapped=False):
+        key = "tr_ov" if overlapped else "tr"
+        s[key] = ops.train_head(s["y"], s["gt"], s["off"], version=2, lambdas=lam, m_global=m_global, out=s[key],
+                                input_ready=overlapped, **kw)
+
+    def lists_only(s):  # the fused step's train kernel alone (candidate listing on, no post-process kernel)
+        s["lists"] = ops.train_post(s["y"], s["gt"], s["off"], lambdas=lam, conf_thre=conf_thre, iou_thre=iou_thre,
+                                    m_global=m_global, max_out=MAX_OUT, want_cls_spec=False, out=s["lists"],
+                                    lists_only=True, **kw)
+
+    def post_only(s):
+        s["post"] = ops.postprocess(s["y"], version=2, conf_thre=conf_thre, iou_thre=iou_thre, max_out=MAX_OUT,
+                                    want_cls_spec=False, out=s["post"], **kw)
 
     def capture(fn):
         g = torch.cuda.CUDAGraph()
@@ -361,27 +401,41 @@ def main():
 
     with torch.cuda.stream(stream):
         for s in sets:  # eager warm-up: allocates outputs/workspaces before any capture
-            step(s)
+            step(s, True)
+            stream.synchronize()
+            step(s, False)  # (the overlapped form as well: it owns its workspace)
+            if xch is not None:
+                step(s, True, exchange=None, key="res_nc")
+                stream.synchronize()
+                step(s, False, exchange=None, key="res_nc")
+            train_only(s)
+            train_only(s, True)
+            post_only(s)
+            if fused:
+                lists_only(s)
         stream.synchronize()
-        # one graph = ROUNDS passes over the R buffer sets; the first kernel of every pass waits for everything
-        # before it (no promise), so the overlap chain stays bounded by the rotation length
+        # one graph = ROUNDS passes over the R buffer sets
         ROUNDS = 4
         G = R * ROUNDS
-        g_full = capture(lambda: [step(s, first=(i == 0)) for _ in range(ROUNDS) for i, s in enumerate(sets)])
+        g_full = capture(lambda: [step(s, i == 0) for _ in range(ROUNDS) for i, s in enumerate(sets)])
         # step counts that are not a multiple of G: one more graph of exactly the remaining steps (same chain)
         g_rem = {}
-        for rem in {K % G, W % G} - {0}:
-            g_rem[rem] = capture(lambda rem=rem: [step(sets[j % R], first=(j % R == 0)) for j in range(rem)])
-        # per-kernel graphs: stream-ordered launches (only launch latency hidden) for the roofline of one
-        # launch, and the overlapped variant for the sustained rate of back-to-back launches
-        g_train = capture(lambda: [step(s, post=False, overlap=False) for s in sets])
-        g_post = capture(lambda: [step(s, train=False, overlap=False) for s in sets])
-        g_train_ov = capture(lambda: [step(s, post=False, first=(i == 0)) for i, s in enumerate(sets)])
-        g_post_ov = capture(lambda: [step(s, train=False, first=(i == 0)) for i, s in enumerate(sets)])
+        if K % G:
+            g_rem[K % G] = capture(lambda: [step(sets[j % R], j % R == 0) for j in range(K % G)])
+        if W % G and W % G not in g_rem:
+            g_rem[W % G] = capture(lambda: [step(sets[j % R], j % R == 0) for j in range(W % G)])
+        g_train = capture(lambda: [train_only(s) for s in sets])
+        g_train_ov = capture(lambda: [train_only(s, i > 0) for i, s in enumerate(sets)])
+        g_post = capture(lambda: [post_only(s) for s in sets])
+        g_step_iso = capture(lambda: [step(s, True) for s in sets])
+        g_lists = capture(lambda: [lists_only(s) for s in sets]) if fused else None
+        g_full_nc = None
+        if xch is not None:  # the same chain without the exchange, to report what the collective costs
+            g_full_nc = capture(lambda: [step(s, i == 0, exchange=None, key="res_nc") for _ in range(ROUNDS) for i, s in enumerate(sets)])
 
-        def run_steps(n):
+        def run_steps(n, full=g_full):
             for _ in range(n // G):
-                g_full.replay()
+                full.replay()
             if n % G:
                 g_rem[n % G].replay()
 
@@ -396,56 +450,69 @@ def main():
         sm_hz = 1e6 * float(torch.cuda.get_device_properties(dev).clock_rate) / 1e3  # clock_rate is in kHz
         gate_cycles = int(args.gate_us * 1e-6 * sm_hz)
 
-        def timed_region(ev0, ev1):
+        def timed_region(ev0, ev1, full=g_full):
             """Exactly K steps between two events.  A gate kernel keeps the GPU busy while the host
             enqueues ev0, the graph launches and ev1: the region then starts with its first kernel already
             queued behind the event (no idle-GPU launch latency inside it)."""
             if gate_cycles > 0:
                 torch.cuda._sleep(gate_cycles)
             ev0.record(stream)
-            run_steps(K)
+            run_steps(K, full)
             ev1.record(stream)
 
         for _ in range(2):
+            barrier()
             timed_region(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             stream.synchronize()
 
-        # ---- timed: `reps` regions of exactly K steps each, device time, barrier + synchronize on both
+        # ---- timed: `n_regions` regions of exactly K steps each, device time, barrier + synchronize on both
         # sides of every region; per region the MAX over ranks, reported: the median region (min/max next to it)
-        est_ms = max(K * 0.014, 1e-3)
-        reps = args.repeats or int(min(15, max(3, round(25.0 / est_ms))))
+        est_ms = max(K * 0.012, 1e-3)
+        n_regions = args.repeats or int(min(15, max(3, round(25.0 / est_ms))))
+
+        def time_regions(full):
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_regions)]
+            for ev0, ev1 in evs:
+                barrier()
+                torch.cuda.synchronize()
+                timed_region(ev0, ev1, full)
+                torch.cuda.synchronize()
+                barrier()
+            t = torch.tensor([a.elapsed_time(b) for a, b in evs], device=dev, dtype=torch.float64)
+            if dist is not None:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return sorted(float(v) for v in t.tolist())
+
         sampler = ClockSampler(nvml_index(local_rank))
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
         barrier()
         torch.cuda.synchronize()
         sampler.start()
-        for ev0, ev1 in evs:
-            barrier()
-            torch.cuda.synchronize()
-            timed_region(ev0, ev1)
-            torch.cuda.synchronize()
-            barrier()
-        region_ms = torch.tensor([a.elapsed_time(b) for a, b in evs], device=dev, dtype=torch.float64)
-        window = "the %d timed regions" % reps
+        region_ms = time_regions(g_full)
+        window = "the %d timed regions" % n_regions
         if len(sampler.samples) < 5:  # the timed regions were too short to sample: keep the same load on
-            t_end = time.perf_counter() + 0.25
-            while time.perf_counter() < t_end:
+            barrier()
+            for _ in range(int(0.25 / (G * 12e-6)) + 1):
                 g_full.replay()
             stream.synchronize()
-            window = "the %d timed regions + 0.25 s of the same graph replayed right after them" % reps
+            window = "the %d timed regions + 0.25 s of the same graph replayed right after them" % n_regions
         sampler.stop()
-        if dist is not None:
-            dist.all_reduce(region_ms, op=dist.ReduceOp.MAX)
-        region_ms = sorted(float(v) for v in region_ms.tolist())
         ms = region_ms[len(region_ms) // 2]
-        loss_value = float(sets[0]["out"]["loss"].item())
+        ms_nc = None
+        if g_full_nc is not None and K % G == 0:
+            r_nc = time_regions(g_full_nc)
+            ms_nc = r_nc[len(r_nc) // 2]
+        res0 = sets[0]["res"]
+        loss_value = float(res0["train"]["loss"].item())
+        terms_value = [float(v) for v in res0["train"]["terms"].tolist()]
 
-        # ---- per-kernel durations (train head alone / post-process alone), same rotation
+        # ---- per-kernel durations, same rotation
         def time_graph(g, reps):
             for _ in range(3):
                 g.replay()
             stream.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if gate_cycles > 0:
+                torch.cuda._sleep(gate_cycles)
             a.record(stream)
             for _ in range(reps):
                 g.replay()
@@ -457,13 +524,14 @@ def main():
         train_ms = time_graph(g_train, reps)
         post_ms = time_graph(g_post, reps)
         train_ov_ms = time_graph(g_train_ov, reps)
-        post_ov_ms = time_graph(g_post_ov, reps)
+        step_iso_ms = time_graph(g_step_iso, reps)
+        lists_ms = time_graph(g_lists, reps) if g_lists is not None else None
 
     images = B * world
     value = images * K / (ms * 1e-3)
 
     # ---- roofline of the dominant kernel (fused train head)
-    kept = sets[0]["post"]["keep_cnt"].clamp(max=MAX_OUT).sum().item()
+    kept = int(res0["post"]["keep_cnt"].clamp(max=MAX_OUT).sum().item())
     p_bytes = case.image_bytes
     train_bytes = 2 * p_bytes * B + 48 * m_local
     post_bytes = p_bytes * B + 28 * kept
@@ -472,36 +540,44 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
-    # The timed region runs the kernels as an overlapped launch chain, so the dominant kernel's average launch
-    # duration in that regime is the issue interval of back-to-back launches (graph time / launches).  The
-    # isolated figure (every launch waits for the one in front of it to complete) is reported next to it.
+
     def gbs(nbytes, ms_):
         return nbytes / (ms_ * 1e-3) / 1e9
 
-    # The dominant kernel's launch duration is the stream-ordered one (every launch starts after the one in
-    # front of it has completed: what a drop-in caller behind a conv gets, and what ncu's serialised per-launch
-    # time corresponds to).  The issue interval of back-to-back launches with the overlap promise -- the regime
-    # of the timed region -- is reported under `sustained`, the whole step of the timed region under `step`.
-    achieved = gbs(train_bytes, train_ms)
+    # The dominant kernel is the train head: in the fused step the candidate-listing variant of yh_train_kernel.
+    # Its launch duration is the stream-ordered one (every launch starts after the one in front of it has
+    # completed: what a drop-in caller behind a conv gets, and what ncu's serialised per-launch time corresponds
+    # to).  The whole step of the timed region (overlapped launch chain) is reported under `step`.
+    dom_ms = lists_ms if lists_ms is not None else train_ms
+    achieved = gbs(train_bytes, dom_ms)
+    step_bytes = train_bytes + post_bytes
     roofline = {"bound": "hbm",
-                "kernel": "yh_train_kernel (fused decode+assign+loss+dL/dy) + its one-warp finalize dependent",
+                "kernel": ("yh_train_kernel<CAND> (fused decode+assign+loss+dL/dy, listing the NMS candidates) + its one-warp "
+                           "finalize dependent" if fused else
+                           "yh_train_kernel (fused decode+assign+loss+dL/dy) + its one-warp finalize dependent"),
                 "regime": "stream-ordered launches over the rotating buffer sets (each launch starts after the previous "
                           "one has completed; only launch latency hidden); duration = CUDA-event time of the graph / launches",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": train_bytes,
-                "us_per_launch": train_ms * 1e3,
-                "sustained": {"what": "back-to-back launches with the overlap promise (yh_v2_train_overlapped / "
-                                      "YH_POST_INPUT_READY), as in the timed region: issue interval = graph time / launches",
-                              "train_us_per_launch": train_ov_ms * 1e3, "train_achieved": gbs(train_bytes, train_ov_ms),
-                              "train_frac": gbs(train_bytes, train_ov_ms) / peak,
-                              "post_us_per_launch": post_ov_ms * 1e3, "post_frac": gbs(post_bytes, post_ov_ms) / peak},
-                "postprocess_kernel": {"us_per_launch": post_ms * 1e3, "algorithmic_bytes_per_launch": post_bytes,
-                                       "achieved": gbs(post_bytes, post_ms), "frac": gbs(post_bytes, post_ms) / peak,
-                                       "regime": "stream-ordered launches"},
-                "step": {"what": "train head + post-process of the timed region (the north-star target: >= 0.60)",
-                         "algorithmic_bytes": train_bytes + post_bytes, "us": ms / K * 1e3,
-                         "achieved": gbs(train_bytes + post_bytes, ms / K),
-                         "frac": gbs(train_bytes + post_bytes, ms / K) / peak}}
+                "us_per_launch": dom_ms * 1e3,
+                "separate_kernels": {"what": "the kernels of the two separate calls, stream-ordered launches (the drop-in "
+                                             "get_loss / detect path) and back-to-back train-head launches with the overlap promise",
+                                     "train_us_per_launch": train_ms * 1e3, "train_frac": gbs(train_bytes, train_ms) / peak,
+                                     "train_overlapped_us_per_launch": train_ov_ms * 1e3,
+                                     "train_overlapped_frac": gbs(train_bytes, train_ov_ms) / peak,
+                                     "post_us_per_launch": post_ms * 1e3, "post_algorithmic_bytes": post_bytes,
+                                     "post_frac": gbs(post_bytes, post_ms) / peak},
+                "step": {"what": "train head + post-process of the timed region (the north-star target: >= 0.60 of the HBM "
+                                 "roofline on SURVEY 8(d)'s algorithmic bytes 3P + 48k + 28K' per image)",
+                         "algorithmic_bytes": step_bytes, "us": ms / K * 1e3,
+                         "achieved": gbs(step_bytes, ms / K), "frac": gbs(step_bytes, ms / K) / peak,
+                         "stream_ordered_us": step_iso_ms * 1e3, "stream_ordered_frac": gbs(step_bytes, step_iso_ms) / peak}}
+    if fused:
+        # the fused step does not read y a second time: its own minimum traffic is 2P + 48k + 28K' per image
+        # (+ the candidate rows written and read back: ~1/15 of P each way, counted as overhead, not as algorithmic)
+        fb = train_bytes + 28 * kept
+        roofline["step"]["fused_minimum_bytes"] = fb
+        roofline["step"]["frac_of_fused_minimum"] = gbs(fb, ms / K) / peak
     roofline["traffic"], roofline["traffic_source"] = measured_traffic()
 
     # ---- e2e: host buffers in, host buffers out
@@ -544,18 +620,28 @@ def main():
             t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t.item())
-        assert abs(float(res["loss"]) - loss_value) <= 1e-6 * abs(loss_value), (float(res["loss"]), loss_value)
+        # (the pipeline runs without the exchange: its loss is this rank's share, 1 / world of the reduced one --
+        #  every rank holds the same shard here)
+        want_loss = loss_value / world if xch is not None else loss_value
+        assert abs(float(res["loss"]) - want_loss) <= 1e-5 * abs(want_loss), (float(res["loss"]), want_loss)
         e2e = {"value": images * ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes(m_local),
                "d2h_bytes_per_step": pipe.d2h_bytes(), "steps": ke, "ms_per_step": 1e3 * e2e_s / ke,
-               "path": "HostHeadPipeline: pinned host y+GT -> H2D -> yh_v2_train (loss + dL/dy) + yh_v2_postprocess -> "
+               "path": "HostHeadPipeline: pinned host y+GT -> H2D -> yh_v2_train_post (loss + dL/dy + kept boxes) -> "
                        "D2H of loss, terms and kept boxes%s; 3 slots, copy/compute streams overlapped"
                        % (" and dL/dy" if args.e2e_return_dy else " (dL/dy is computed every step and stays on the device)")}
+
+    collective = None
+    if world > 1:
+        collective = ("every step: the six loss sums of all %d ranks summed inside the step's last kernel over NVLink peer "
+                      "memory (56-byte peer stores + sequence words, csrc/yh_finalize.cuh); terms/loss of the whole sharded "
+                      "batch on every rank; no NCCL call in the timed region" % world) if xch is not None else \
+                     "none in the timed region (--no-collective): every rank reports the partial terms of its shard"
 
     # ---- CPU baseline (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sample = args.cpu_sample
-        _, ts = time_cpu_port(sample, reps=5, warm=1)
+        _, ts = time_cpu_port(sample, reps=5, warm=1, workload=args.workload)
         cpu = {"value": sample / float(np.min(ts)), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                "sample": "%d-image sample of the same workload, best of 5 after 1 warm-up (%.2f s of CPU work); "
                          "oracle/ torch-CPU port of get_loss+backward and the per-image nms loop; "
@@ -564,14 +650,20 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "repeats": reps,
+            "ms_per_step": ms / K, "repeats": n_regions,
             "region_ms": {"median": ms, "min": region_ms[0], "max": region_ms[-1],
                           "what": "device time of the K-step region, max over ranks, per repetition"},
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(B, R, not args.two_streams),
-            "clocks": sampler.summary(window), "e2e": e2e, "gpu_launches": 3 * K,
-            "roofline": roofline, "cpu_baseline": cpu, "loss": loss_value,
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.workload, B, R, set_bytes + (sets[0]["res"].get("_ws").numel() if fused else 0),
+                                      fused, collective),
+            "clocks": sampler.summary(window), "e2e": e2e, "gpu_launches": (2 if fused else 3) * K,
+            "roofline": roofline, "cpu_baseline": cpu, "loss": loss_value, "terms": terms_value,
         }
+        if world > 1:
+            line["collective_in_timed_region"] = xch is not None
+            if ms_nc is not None:
+                line["without_collective"] = {"ms_per_step": ms_nc / K, "value": images * K / (ms_nc * 1e-3)}
         emit(line)
     if dist is not None:
         dist.destroy_process_group()

@@ -42,8 +42,9 @@ extern "C" {
 #define YH_API
 #endif
 
-#define YH_ABI_VERSION 1
+#define YH_ABI_VERSION 2
 #define YH_MAX_ANCHORS 16
+#define YH_MAX_RANKS 16
 
 #define YH_OK 0
 #define YH_ERR_INVALID (-1)   /* bad argument (null pointer, non-positive size, ...)        */
@@ -102,12 +103,18 @@ YH_API int yh_v1_train(const float* y, int n, int s_h, int s_w, int b, int c,
                 const float* lambdas_host, float* dy, float* terms, float* loss,
                 int32_t* resp, float* iou_resp, void* ws, size_t ws_bytes, void* stream);
 
-/* The same two calls for callers that can promise more (HostHeadPipeline and bench.py do): NONE of
- * this call's buffers (y, gt, gt_off, dy, terms, loss, resp, iou_resp) is read or written by the
- * two kernels launched immediately before it on `stream`.  The kernel then starts while those
- * kernels are still draining -- it is launched as a programmatic dependent and only waits for them
- * before it touches the workspace (shared with the previous launch) and before it completes, so
- * stream order is kept for everything launched afterwards.  Same results, bit for bit. */
+/* The same two calls for callers that can promise more (HostHeadPipeline and bench.py do).
+ * THE OVERLAP CONTRACT (also YH_POST_INPUT_READY and YH_STEP_OVERLAPPED below): an overlapped call starts
+ * while the kernels in front of it on `stream` are still running -- it is launched as a programmatic
+ * dependent and only waits for them right before it completes (the train head: before it publishes its sums),
+ * so stream order still holds for everything launched after it.  Those kernels may themselves be overlapped
+ * calls, so the set of kernels running concurrently reaches back to the last launch on the stream that was
+ * NOT overlapped (a stream-ordered entry point of this library or any foreign kernel: both wait at their start
+ * for everything before them).  The promise therefore is: NONE of this call's buffers -- inputs, outputs AND
+ * workspace -- is read or written by ANY kernel launched on `stream` since the last non-overlapped launch
+ * (reading the same read-only input, e.g. a post-process on the y its train head reads, is fine).  In
+ * practice: rotate R complete buffer sets (workspace included) and issue every R-th call stream-ordered.
+ * A caller that cannot promise this uses the stream-ordered entry points.  Same results, bit for bit. */
 YH_API int yh_v2_train_overlapped(const float* y, int n, int s_h, int s_w, int a, int c,
                 const float* anchors_wh_host, float img_h, float img_w,
                 const YhGt* gt, const int32_t* gt_off, int m_local, int m_global,
@@ -166,11 +173,10 @@ YH_API int yh_build_targets(const double* boxes_xyxy, const int32_t* labels, con
  * Replaces the predict -> nms -> argmax chain of detect() (reference models/yolov2.py:694-731,
  * models/yolov1.py:491-534) with models/utils.py:68-164 nms applied PER IMAGE.
  *   flags: bit 0 (YH_POST_CLASS_AWARE) 0 reproduces the reference (class-agnostic), 1 only lets
- *   boxes with the same argmax class suppress each other; bit 1 (YH_POST_INPUT_READY) is a promise
- *   by the caller that y was NOT written by the kernel launched immediately before this call on
- *   `stream` (typically that kernel is the train head, which only reads y): the kernel then starts
- *   on y while that kernel is still draining and only waits for it before it exits, so stream order
- *   is kept for everything launched afterwards.
+ *   boxes with the same argmax class suppress each other; bit 1 (YH_POST_INPUT_READY): an overlapped call
+ *   under THE OVERLAP CONTRACT above (y not written, outputs and workspace not touched by any kernel launched
+ *   since the last non-overlapped launch on `stream`): the kernel starts while those kernels are still
+ *   draining and only waits for them before it exits.
  *   Outputs per image, first keep_cnt[n] (<= max_out) entries valid, in descending confidence:
  *   keep_idx[N,max_out] predictor index; out_bbox[N,max_out,4]; out_conf[N,max_out];
  *   out_cls_spec[N,max_out,C] (may be NULL); out_label[N,max_out]; out_score[N,max_out].
@@ -190,6 +196,66 @@ YH_API int yh_v1_postprocess(const float* y, int n, int s_h, int s_w, int b, int
                       int32_t* keep_idx, int32_t* keep_cnt, float* out_bbox, float* out_conf,
                       float* out_cls_spec, int32_t* out_label, float* out_score,
                       void* ws, size_t ws_bytes, void* stream);
+
+/* ---- the fused step: train head + post-process of the SAME head tensor, y read once -------------------
+ * yh_v2_train followed by yh_v2_postprocess reads y twice; here the train head's dense pass (which already
+ * takes the sigmoid of every objectness logit) also lists the predictors with conf >= conf_thre -- their
+ * 5 + C logits go to a compact per-tile list in the workspace (~50 of 845 predictors per image at the
+ * reference's thresholds) -- and the post-process kernel ranks, decodes, suppresses and emits from those
+ * lists alone: ~1/15 of the head tensor instead of all of it, a small CTA per image.  It also turns the loss
+ * sums into terms/loss (no separate finalize launch).  Results are bit-identical to the two separate calls;
+ * images whose lists overflow (more than 64 candidates in a tile, more than 256 in an image) fall back to
+ * reading y inside the same kernel.  Inputs the fused form does not cover (unaligned y, tiles spanning more
+ * than two images) run the two kernels of the separate calls instead -- same results.
+ *   flags: YH_STEP_CLASS_AWARE (as YH_POST_CLASS_AWARE), YH_STEP_OVERLAPPED (THE OVERLAP CONTRACT above, for
+ *   all buffers of this call including ws).
+ *   xch_host: NULL on one GPU.  Sharded batches: see YhExchange -- the loss terms of all ranks are summed
+ *   inside the kernel over peer memory; every rank's terms/loss then hold the values of the whole batch.
+ *   ws: yh_train_post_workspace_bytes() bytes, zero-filled once when allocated (calls leave it reusable). */
+#define YH_STEP_CLASS_AWARE 1
+#define YH_STEP_OVERLAPPED 2
+#define YH_STEP_NO_POST 4 /* train head with candidate listing only (the lists stay in ws, terms/loss by the
+                             finalize kernel, the post-process outputs are not touched): times the fused
+                             train kernel alone */
+
+/* Peer-memory exchange of the loss sums between the ranks of a sharded batch (one process per GPU).  Every
+ * rank allocates yh_exchange_bytes() bytes of device memory, zero-filled once, and maps the buffers of all
+ * ranks into its own address space (CUDA IPC / peer access; odcp_b200.dist.PeerExchange does it with torch);
+ * slots[q] is rank q's buffer as seen from THIS process, slots[rank] the local one.  Every rank must make the
+ * same sequence of exchanging calls.  HOST struct, read during the call only. */
+typedef struct YhExchange {
+    int32_t rank, world;
+    uint64_t* slots[YH_MAX_RANKS];
+} YhExchange;
+YH_API size_t yh_exchange_bytes(void);
+
+YH_API size_t yh_train_post_workspace_bytes(int n, int s_h, int s_w, int a, int c);
+YH_API int yh_v2_train_post(const float* y, int n, int s_h, int s_w, int a, int c,
+                     const float* anchors_wh_host, float img_h, float img_w,
+                     const YhGt* gt, const int32_t* gt_off, int m_local, int m_global,
+                     const float* lambdas_host, float* dy, float* terms, float* loss,
+                     int32_t* resp, float* iou_resp,
+                     float conf_thre, float iou_thre, int flags, int max_out,
+                     int32_t* keep_idx, int32_t* keep_cnt, float* out_bbox, float* out_conf,
+                     float* out_cls_spec, int32_t* out_label, float* out_score,
+                     const YhExchange* xch_host, void* ws, size_t ws_bytes, void* stream);
+
+/* yh_v2_train / yh_v1_train for a sharded batch: the same call (flags: YH_STEP_OVERLAPPED or 0) whose
+ * finalize step sums the loss terms of all ranks over peer memory (xch_host as above; NULL: one GPU).
+ * Replaces the all-reduce of six floats SURVEY 8(e) assigns to NCCL with 56-byte peer stores inside the
+ * kernel that already ends the call. */
+YH_API int yh_v2_train_sharded(const float* y, int n, int s_h, int s_w, int a, int c,
+                const float* anchors_wh_host, float img_h, float img_w,
+                const YhGt* gt, const int32_t* gt_off, int m_local, int m_global,
+                const float* lambdas_host, float* dy, float* terms, float* loss,
+                int32_t* resp, float* iou_resp, int flags, const YhExchange* xch_host,
+                void* ws, size_t ws_bytes, void* stream);
+YH_API int yh_v1_train_sharded(const float* y, int n, int s_h, int s_w, int b, int c,
+                float img_h, float img_w,
+                const YhGt* gt, const int32_t* gt_off, int m_local, int m_global,
+                const float* lambdas_host, float* dy, float* terms, float* loss,
+                int32_t* resp, float* iou_resp, int flags, const YhExchange* xch_host,
+                void* ws, size_t ws_bytes, void* stream);
 
 /* Batched true-positive matching for evaluation: the per-detection loop of evaluate_model
  * (reference models/utils.py:231-262).  A detection is a true positive at level L iff a ground-truth

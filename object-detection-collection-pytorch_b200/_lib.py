@@ -12,13 +12,19 @@ import threading
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libyolohead.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
+MAX_RANKS = 16
 
 _p = C.c_void_p
 _i = C.c_int
 _f = C.c_float
 _sz = C.c_size_t
 _i64 = C.c_int64
+
+class YhExchange(C.Structure):
+    """include/yolohead.h YhExchange: peer-mapped exchange buffers of all ranks (host struct)."""
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("slots", C.c_void_p * MAX_RANKS)]
+
 
 # name -> (restype, argtypes); mirrors include/yolohead.h one to one
 SIGNATURES = {
@@ -29,6 +35,12 @@ SIGNATURES = {
     "yh_v1_train": (_i, [_p, _i, _i, _i, _i, _i, _f, _f, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "yh_v2_train_overlapped": (_i, [_p, _i, _i, _i, _i, _i, _p, _f, _f, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "yh_v1_train_overlapped": (_i, [_p, _i, _i, _i, _i, _i, _f, _f, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "yh_exchange_bytes": (_sz, []),
+    "yh_train_post_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "yh_v2_train_post": (_i, [_p, _i, _i, _i, _i, _i, _p, _f, _f, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p,
+                              _f, _f, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "yh_v2_train_sharded": (_i, [_p, _i, _i, _i, _i, _i, _p, _f, _f, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p, _sz, _p]),
+    "yh_v1_train_sharded": (_i, [_p, _i, _i, _i, _i, _i, _f, _f, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p, _sz, _p]),
     "yh_v2_decode": (_i, [_p, _i, _i, _i, _i, _i, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p]),
     "yh_v1_decode": (_i, [_p, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p, _p, _p, _p, _p]),
     "yh_compact_workspace_bytes": (_sz, [_i, _i]),

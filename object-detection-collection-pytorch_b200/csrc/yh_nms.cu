@@ -39,14 +39,18 @@
 #include <string.h>
 
 #include "yh_common.cuh"
+#include "yh_finalize.cuh"
 
 namespace {
 
 #ifndef YH_X_NMS_THREADS
 #define YH_X_NMS_THREADS 512
 #endif
-constexpr int kThreads = YH_X_NMS_THREADS;
-constexpr int kWarps = kThreads / 32;
+constexpr int kThreadsFull = YH_X_NMS_THREADS;  // threads per CTA of the kernels that read the head tensor
+#ifndef YH_X_CAND_THREADS
+#define YH_X_CAND_THREADS 256
+#endif
+constexpr int kThreadsCand = YH_X_CAND_THREADS;  // ... of the candidates-only kernel of the fused step
 constexpr int kTile = 256;             // ranked candidates per suppression tile
 constexpr int kTileWords = kTile / 32;
 constexpr int kSmemCand = 256;         // candidates held in shared memory
@@ -61,6 +65,7 @@ constexpr int kGroups = 4;             // whole-image mode: the image arrives in
 constexpr int kImgBytesMax = YH_X_NMS_IMG_BYTES;
 
 enum { SRC_HEAD = 0, SRC_DECODED = 2 };
+enum { MODE_GENERAL = 0, MODE_IMG = 1, MODE_CAND = 2 };
 
 #ifdef YH_X_TRACE
 __device__ unsigned long long g_ntrace[4096 * 16];
@@ -111,6 +116,8 @@ struct NmsParams {
     int stage_bytes;         // shared memory in front of the candidate arrays (staged rows, or the whole image)
     int slot_floats;         // floats per staged row slot (multiple of 4)
     unsigned magic_sw;       // ceil(2^32 / s_w): cell / s_w == umulhi(cell, magic_sw) for cell < 2^16
+    YhCandBuf cand;          // MODE_CAND: the candidate lists the train head of the same step wrote
+    YhFinalParams fin;       // MODE_CAND: the loss totals -> terms / loss, done by one extra CTA of this kernel
 };
 
 struct Cand {
@@ -307,8 +314,14 @@ __device__ __forceinline__ bool suppresses_dense(const float4& bi, float ai, con
 // IMG: the image's whole slice of the head tensor is staged in shared memory by kGroups bulk copies
 // issued at the start (ONE global round trip, no per-candidate copies); otherwise the objectness
 // logits are read with strided loads and only the candidates' rows are staged.
-template <int TV, int TA, int TC, bool IMG>
-__global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const NmsParams p) {
+// MODE_CAND (the fused step): the candidates come from the lists the train head's dense pass wrote -- one bulk copy
+// per tile list, ~50 rows of 5 + C logits per image instead of the image -- and the lean path below runs on those rows;
+// an image whose lists overflowed is processed from the head tensor by the general path, in the same CTA.  One CTA
+// beyond the images turns the train head's loss totals into terms and loss.
+template <int TV, int TA, int TC, int MODE, int NTH>
+__global__ void __launch_bounds__(NTH, NTH >= 512 ? 2 : 3) yh_nms_kernel(const NmsParams p) {
+    constexpr int kThreads = NTH, kWarps = NTH / 32;
+    constexpr bool IMG = MODE == MODE_IMG, CANDM = MODE == MODE_CAND;
     extern __shared__ __align__(128) unsigned char smem_raw[];  // [staged rows or image | candidate arrays]
     __shared__ unsigned int mask[kTile * kTileWords];
     __shared__ unsigned int rem0[kTileWords];
@@ -320,6 +333,12 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
     const YhGeom& g = p.g;
     const int img = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (CANDM && img == p.n) {  // the extra CTA: the train head's totals -> terms and loss (it has completed after the wait)
+        yh_grid_launch_dependents();
+        yh_grid_dependency_wait();
+        if (warp == 0) yh_finalize_warp(p.fin, lane);
+        return;
+    }
     const int P = p.p;
     const bool head = p.src == SRC_HEAD;
     const int A = TA ? TA : g.a, C = TC ? TC : p.c;
@@ -333,7 +352,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
     auto carve_ws = [&]() -> Cand { return p.ws ? carve(p.ws + (size_t)img * p.ws_per_image, P) : ca; };
 
     NT(0);
-    if (IMG) {  // the single-tile path sets suppression bits with atomicOr
+    if (IMG || CANDM) {  // the single-tile path sets suppression bits with atomicOr
         for (int q = tid; q < kTile * kTileWords / 4; q += kThreads) reinterpret_cast<uint4*>(mask)[q] = make_uint4(0u, 0u, 0u, 0u);
     }
     if (tid == 0) {
@@ -341,7 +360,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
         s_kept = 0;
         yh_mbar_init(&bar, kThreads);
         yh_mbar_init(&bar_list, kThreads);
-        if (IMG) {
+        if (IMG || CANDM) {
 #pragma unroll
             for (int q = 0; q < kGroups; ++q) yh_mbar_init(&bar_img[q], 1);
         }
@@ -349,8 +368,15 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
     }
     // (programmatic dependent launch: the prologue above overlaps the previous kernel's tail; global
     // memory is only touched once that kernel has completed)
-    if (!p.late_wait) yh_grid_dependency_wait();
-    yh_grid_launch_dependents();
+    if (CANDM) {
+        // the lists are the previous kernel's output: always wait for it -- but let the NEXT kernel of the stream go
+        // first (an overlapped train head of the next step streams next to this kernel's latency-bound phases)
+        yh_grid_launch_dependents();
+        yh_grid_dependency_wait();
+    } else {
+        if (!p.late_wait) yh_grid_dependency_wait();
+        yh_grid_launch_dependents();
+    }
     // IMG: the image's aligned window [image start - fsh, ...) goes to shared memory in kGroups pieces cut at
     // unit boundaries (v2: predictors, v1: cells) rounded down to 16 bytes; window float w is image float w - fsh
     const int img_units = (TV ? TV : p.g.version) == 2 ? p.p : p.g.cells;
@@ -411,6 +437,77 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
 
     NT(1);
     uint32_t tx = 0;
+    // ---------------- A (candidate lists of the fused step) ----------------
+    // The image's cells lie in tiles t_lo..t_hi of the train head; a tile holds one list for its first image and one
+    // for its second.  One warp reads the lists' lengths, and -- if no list overflowed and the image has at most
+    // kSmemCand candidates -- fetches each list with ONE bulk copy into consecutive row slots.
+    const int cstride = TC ? ((5 + TC + 1 + 3) & ~3) : p.cand.stride;  // floats per list entry
+    bool cand_lean = false;
+    if (CANDM) {
+        if (warp == 0) {
+            const int R = p.cand.tile_cells, cells = g.cells;
+            const int t_lo = (img * cells) / R, t_hi = ((img + 1) * cells - 1) / R;
+            int total = 0, cnt0 = 0, side0 = 0;
+            bool over = false;
+            for (int tb = t_lo; tb <= t_hi; tb += 32) {  // pass 1: lengths
+                const int t = tb + lane;
+                int cnt = 0, side = 0;
+                if (t <= t_hi) {
+                    const int2 c2 = __ldcg(p.cand.tile_cnt + t);
+                    side = ((t * R) / cells == img) ? 0 : 1;
+                    cnt = side ? c2.y : c2.x;
+                }
+                if (tb == t_lo) { cnt0 = cnt; side0 = side; }
+                over = over || cnt > kYhCandCap;
+                total += cnt;
+            }
+            for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+            over = __any_sync(0xffffffffu, over) || total > kSmemCand;
+            if (!over) {
+                int base = 0;
+                uint32_t mytx = 0;
+                for (int tb = t_lo; tb <= t_hi; tb += 32) {  // pass 2: one bulk copy per non-empty list
+                    const int t = tb + lane;
+                    int cnt = cnt0, side = side0;
+                    if (tb != t_lo) {
+                        cnt = 0;
+                        if (t <= t_hi) {
+                            const int2 c2 = __ldcg(p.cand.tile_cnt + t);
+                            side = ((t * R) / cells == img) ? 0 : 1;
+                            cnt = side ? c2.y : c2.x;
+                        }
+                    }
+                    int inc = cnt;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (lane >= o) inc += v;
+                    }
+                    if (cnt > 0) {
+                        const uint32_t bytes = (uint32_t)(cnt * cstride) * 4u;
+                        yh_bulk_load(stage + (size_t)(base + inc - cnt) * cstride,
+                                     p.cand.rows + ((size_t)t * 2 + side) * kYhCandCap * cstride, bytes, &bar_img[0]);
+                        mytx += bytes;
+                    }
+                    base += __shfl_sync(0xffffffffu, inc, 31);
+                }
+                for (int o = 16; o > 0; o >>= 1) mytx += __shfl_xor_sync(0xffffffffu, mytx, o);
+                if (lane == 0) {
+                    if (mytx) yh_mbar_expect_tx(&bar_img[0], mytx);
+                    else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(yh_smem_u32(&bar_img[0])) : "memory");
+                }
+            }
+            if (lane == 0) s_count = over ? -1 : total;
+        }
+        __syncthreads();
+        cand_lean = s_count >= 0;
+        if (cand_lean) {
+            yh_mbar_wait(&bar_img[0], 0);  // the rows have landed
+        } else {
+            __syncthreads();
+            if (tid == 0) s_count = 0;  // this image continues from the head tensor (general path below)
+            __syncthreads();
+        }
+    }
     if (IMG) {
         // ---------------- A (whole image): each warp group thresholds its piece as it lands ----------------
         const float* win = reinterpret_cast<const float*>(smem_raw);
@@ -459,7 +556,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
                 }
             }
         }
-    } else
+    } else if (!cand_lean)
     // ---------------- A: threshold + stage the survivors' rows ----------------
     for (int base = 0; base < P; base += kThreads * kLoadUnroll) {
         float val[kLoadUnroll];
@@ -541,11 +638,16 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
         const float* win = reinterpret_cast<const float*>(smem_raw);
         Cand ca = carve(smem_raw + p.stage_bytes, kSmemCand);
         const bool use_lab = LAB && p.class_aware != 0;
+        // where the logits of a candidate are: in the staged image, or (MODE_CAND) in its row slot
+        auto box_row = [&](int k, int ik) -> const float* { return CANDM ? win + k * cstride : win + (fsh + box_off(ik)); };
+        auto cls_row = [&](int ranked) -> const float* {
+            return CANDM ? win + ca.s_slot[ranked] * cstride + 5 : win + (fsh + cls_off(ca.s_idx[ranked]));
+        };
 
         // ---------------- B: rank + decode ----------------
-        {
-            const int k = tid >> 1, ax = tid & 1;  // candidate, axis
-            if ((tid & ~31) < 2 * K) {  // (whole warps)
+        for (int kb = 0; kb < K; kb += kThreads / 2) {
+            const int k = kb + (tid >> 1), ax = tid & 1;  // candidate, axis
+            if (kb + ((tid & ~31) >> 1) < K) {  // (whole warps)
                 const bool on = k < K;
                 const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(ca.u_conf);
                 const unsigned long long kk = on ? keys[k] : 0ull;
@@ -564,7 +666,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
                 // this lane's axis of the box: lo/hi corner coordinate (same roundings as yh_decode_box)
                 float lo = 0.f, hi = 0.f;
                 if (on) {
-                    const float* row = win + (fsh + box_off(ik));
+                    const float* row = box_row(k, ik);
                     const float tc = row[ax], ts = row[2 + ax];
                     const float sc = yh_sigmoid(tc);
                     const float sa = v2 ? expf(ts) : yh_sigmoid(ts);
@@ -583,6 +685,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
                     ca.s_area[rank] = __fmul_rn(__fsub_rn(hi, lo), __fsub_rn(ohi, olo));
                     ca.s_idx[rank] = ik;
                     ca.s_conf[rank] = ck;
+                    if (CANDM) ca.s_slot[rank] = k;
                 }
             }
         }
@@ -605,14 +708,14 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
         // and get picked for nothing: cheaper than a serial pick phase at the end of the kernel's critical path.)
         const bool with_spec = p.out_cls_spec != nullptr;
         const bool want_ls = p.out_label != nullptr || p.out_score != nullptr;
-        float* s_score = reinterpret_cast<float*>(ca.s_slot);  // (ranked -> unsorted slot is not needed in this mode)
+        float* s_score = ca.u_conf;  // (the sort keys there are dead once phase B is through)
         auto pick_all = [&](int w0, int nw) {
             for (int k0 = 8 * (warp - w0); k0 < K; k0 += 8 * nw) {  // (uniform over the warp)
                 const int k = k0 + (lane >> 2);
                 const bool act = k < K;
                 int lab;
                 float sc;
-                pick(act ? win + (fsh + cls_off(ca.s_idx[k])) : nullptr, act ? ca.s_conf[k] : 0.f, act, false, nullptr, &lab, &sc);
+                pick(act ? cls_row(k) : nullptr, act ? ca.s_conf[k] : 0.f, act, false, nullptr, &lab, &sc);
                 if (act && sub == 0) { ca.s_lab[k] = lab; s_score[k] = sc; }
             }
         };
@@ -749,7 +852,7 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
             if (want_cls) {  // (cls_spec rows requested: the full pick, four lanes per kept box)
                 int lab;
                 float sc;
-                pick(act ? win + (fsh + cls_off(idx)) : nullptr, conf, act, with_spec,
+                pick(act ? cls_row(i) : nullptr, conf, act, with_spec,
                      (act && with_spec) ? p.out_cls_spec + o * C : nullptr, &lab, &sc);
                 if (act && sub == 2) {
                     if (p.out_label) p.out_label[o] = lab;
@@ -760,13 +863,18 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
         NT(13);
     };
 
-    if (IMG && !overflow) {
+    if ((IMG && !overflow) || cand_lean) {
         // the common case first, and out of the way of everything below
         // (logit, predictor) -> sort key: confidence bits in the high word (positive floats order like
         // integers), complement of the predictor index in the low word (ties: lower index first)
         for (int k = tid; k < K; k += kThreads) {
-            const int2 e = pairs[k];
-            pairs[k] = make_int2(~e.y, __float_as_int(yh_sigmoid(__int_as_float(e.x))));
+            if (CANDM) {
+                const float* row = reinterpret_cast<const float*>(smem_raw) + k * cstride;
+                pairs[k] = make_int2(~__float_as_int(row[bs]), __float_as_int(yh_sigmoid(row[4])));
+            } else {
+                const int2 e = pairs[k];
+                pairs[k] = make_int2(~e.y, __float_as_int(yh_sigmoid(__int_as_float(e.x))));
+            }
         }
         __syncthreads();
         if (!with_labels) rest_img(FastTag<false>{});
@@ -1053,24 +1161,25 @@ __global__ void __launch_bounds__(kThreads, 1024 / kThreads) yh_nms_kernel(const
     if (p.late_wait) yh_grid_dependency_wait();
 }
 
-template <int TV, int TA, int TC, bool IMG>
+template <int TV, int TA, int TC, int MODE, int NTH>
 int launch_variant(const NmsParams& p, size_t smem, void* stream) {
     static size_t configured[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) dev = 0;
     if (smem > 32 * 1024 && smem > configured[dev]) {
-        int rc = yh_check_cuda(cudaFuncSetAttribute(yh_nms_kernel<TV, TA, TC, IMG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+        int rc = yh_check_cuda(cudaFuncSetAttribute(yh_nms_kernel<TV, TA, TC, MODE, NTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                                "cudaFuncSetAttribute(nms)");
         if (rc) return rc;
         configured[dev] = smem;
     }
-    return yh_check_cuda(yh_launch_pdl(yh_nms_kernel<TV, TA, TC, IMG>, dim3((unsigned)p.n), dim3(kThreads), smem,
-                                       (cudaStream_t)stream, p),
+    // (MODE_CAND: one CTA beyond the images finishes the train head's loss)
+    return yh_check_cuda(yh_launch_pdl(yh_nms_kernel<TV, TA, TC, MODE, NTH>, dim3((unsigned)p.n + (MODE == MODE_CAND ? 1u : 0u)),
+                                       dim3(NTH), smem, (cudaStream_t)stream, p),
                          "yh_nms launch");
 }
 
-int launch(NmsParams& p, void* ws, size_t ws_bytes, void* stream) {
+int launch(NmsParams& p, void* ws, size_t ws_bytes, void* stream, bool cand_mode = false) {
     YH_REQUIRE(p.n > 0 && p.p > 0, YH_ERR_INVALID, "n and predictors per image must be positive");
     YH_REQUIRE(p.max_out >= 0, YH_ERR_INVALID, "max_out < 0");
     YH_REQUIRE(p.keep_cnt && (p.max_out == 0 || p.keep_idx), YH_ERR_INVALID, "keep_idx / keep_cnt is NULL");
@@ -1084,6 +1193,15 @@ int launch(NmsParams& p, void* ws, size_t ws_bytes, void* stream) {
         p.ws = reinterpret_cast<unsigned char*>(ws);
         p.ws_per_image = cand_bytes(p.p);
     }
+    if (cand_mode) {
+        // shared memory: kSmemCand row slots for the lists' entries, then the candidate arrays; an image that
+        // falls back to the head tensor stages nothing (its rows are read from global memory)
+        p.stage_slots = 0;
+        p.stage_bytes = kSmemCand * p.cand.stride * 4;
+        const size_t smem = (size_t)p.stage_bytes + cand_bytes(kSmemCand);
+        if (p.g.a == 5 && p.c == 20) return launch_variant<2, 5, 20, MODE_CAND, kThreadsCand>(p, smem, stream);
+        return launch_variant<2, 0, 0, MODE_CAND, kThreadsCand>(p, smem, stream);
+    }
     // whole-image staging: the image's aligned window (<= 3 floats of shift in front, padded to 16 bytes)
     // fits next to a second CTA's; needs bulk copies (aligned y) and C >= 3 (then the floats past the last
     // whole 16 bytes of the tensor, which arrive by plain loads, are never an objectness logit)
@@ -1093,22 +1211,23 @@ int launch(NmsParams& p, void* ws, size_t ws_bytes, void* stream) {
     const size_t smem = (size_t)p.stage_bytes + cand_bytes(kSmemCand);
     // compile-time geometries for the shapes the reference uses (VOC: YOLOv2 5 anchors x 20 classes,
     // YOLOv1 B=2, C=20); anything else, and decoded-box input, runs the run-time-geometry variant
+    constexpr int NTF = kThreadsFull;
     if (img_mode) {
-        if (p.g.version == 2 && p.g.a == 5 && p.c == 20) return launch_variant<2, 5, 20, true>(p, smem, stream);
-        if (p.g.version == 1 && p.g.a == 2 && p.c == 20) return launch_variant<1, 2, 20, true>(p, smem, stream);
-        return launch_variant<0, 0, 0, true>(p, smem, stream);
+        if (p.g.version == 2 && p.g.a == 5 && p.c == 20) return launch_variant<2, 5, 20, MODE_IMG, NTF>(p, smem, stream);
+        if (p.g.version == 1 && p.g.a == 2 && p.c == 20) return launch_variant<1, 2, 20, MODE_IMG, NTF>(p, smem, stream);
+        return launch_variant<0, 0, 0, MODE_IMG, NTF>(p, smem, stream);
     }
-    if (p.src == SRC_HEAD && p.g.version == 2 && p.g.a == 5 && p.c == 20) return launch_variant<2, 5, 20, false>(p, smem, stream);
-    if (p.src == SRC_HEAD && p.g.version == 1 && p.g.a == 2 && p.c == 20) return launch_variant<1, 2, 20, false>(p, smem, stream);
-    return launch_variant<0, 0, 0, false>(p, smem, stream);
+    if (p.src == SRC_HEAD && p.g.version == 2 && p.g.a == 5 && p.c == 20) return launch_variant<2, 5, 20, MODE_GENERAL, NTF>(p, smem, stream);
+    if (p.src == SRC_HEAD && p.g.version == 1 && p.g.a == 2 && p.c == 20) return launch_variant<1, 2, 20, MODE_GENERAL, NTF>(p, smem, stream);
+    return launch_variant<0, 0, 0, MODE_GENERAL, NTF>(p, smem, stream);
 }
 
-int postprocess_impl(int version, const float* y, int n, int s_h, int s_w, int a, int c,
+// everything a head-tensor post-process needs but the launch
+int fill_head_params(NmsParams& p, int version, const float* y, int n, int s_h, int s_w, int a, int c,
                      const float* anchors_wh_host, float img_h, float img_w, float conf_thre,
-                     float iou_thre, int class_aware, int max_out, int32_t* keep_idx, int32_t* keep_cnt,
+                     float iou_thre, int flags, int max_out, int32_t* keep_idx, int32_t* keep_cnt,
                      float* out_bbox, float* out_conf, float* out_cls_spec, int32_t* out_label,
-                     float* out_score, void* ws, size_t ws_bytes, void* stream) {
-    NmsParams p;
+                     float* out_score) {
     memset(&p, 0, sizeof(p));
     int rc = yh_make_geom(&p.g, version, n, s_h, s_w, a, c, anchors_wh_host, img_h, img_w);
     if (rc) return rc;
@@ -1118,23 +1237,9 @@ int postprocess_impl(int version, const float* y, int n, int s_h, int s_w, int a
     p.y = y;
     p.n = n; p.p = p.g.preds; p.c = c;
     p.conf_thre = conf_thre; p.iou_thre = iou_thre;
-    // sigmoid(t) >= thr needs t >= logit(thr) up to a few ulp; reject only with a wide margin
-    // (the margins are in logit units: 1e-3 there moves the sigmoid by 1e-3 * conf * (1 - conf), >= 1e-5 for
-    // thresholds in [0.01, 0.99] -- far beyond the few ulp of expf and the division; outside that range only a
-    // wide reject margin is used and every other logit takes the sigmoid)
-    p.to_accept = INFINITY;
-    if (!(conf_thre > 0.f)) p.to_reject = -INFINITY;          // everything passes (or thr is NaN)
-    else if (conf_thre > 1.f) p.to_reject = INFINITY;         // nothing can pass
-    else if (conf_thre >= 0.01f && conf_thre <= 0.99f) {
-        const double t = log((double)conf_thre / (1.0 - (double)conf_thre));
-        p.to_reject = (float)(t - 1e-3);
-        p.to_accept = (float)(t + 1e-3);
-    } else {
-        const double t = conf_thre < 0.9999999 ? log((double)conf_thre / (1.0 - (double)conf_thre)) : 16.0;
-        p.to_reject = (float)((t < 16.0 ? t : 16.0) - 0.01);
-    }
-    p.class_aware = (class_aware & YH_POST_CLASS_AWARE) != 0; p.max_out = max_out;
-    p.late_wait = (class_aware & YH_POST_INPUT_READY) != 0;
+    yh_conf_band(conf_thre, &p.to_reject, &p.to_accept);
+    p.class_aware = (flags & YH_POST_CLASS_AWARE) != 0; p.max_out = max_out;
+    p.late_wait = (flags & YH_POST_INPUT_READY) != 0;
     p.keep_idx = keep_idx; p.keep_cnt = keep_cnt;
     p.out_bbox = reinterpret_cast<float4*>(out_bbox);
     p.out_conf = out_conf; p.out_cls_spec = out_cls_spec; p.out_label = out_label; p.out_score = out_score;
@@ -1149,12 +1254,121 @@ int postprocess_impl(int version, const float* y, int n, int s_h, int s_w, int a
     p.slot_floats = 8 + ((c + 3 + 3) & ~3);
     int slots = kStageBytesMax / (p.slot_floats * 4);
     p.stage_slots = slots < kSmemCand ? slots : kSmemCand;
+    return YH_OK;
+}
+
+int postprocess_impl(int version, const float* y, int n, int s_h, int s_w, int a, int c,
+                     const float* anchors_wh_host, float img_h, float img_w, float conf_thre,
+                     float iou_thre, int class_aware, int max_out, int32_t* keep_idx, int32_t* keep_cnt,
+                     float* out_bbox, float* out_conf, float* out_cls_spec, int32_t* out_label,
+                     float* out_score, void* ws, size_t ws_bytes, void* stream) {
+    NmsParams p;
+    int rc = fill_head_params(p, version, y, n, s_h, s_w, a, c, anchors_wh_host, img_h, img_w, conf_thre, iou_thre,
+                              class_aware, max_out, keep_idx, keep_cnt, out_bbox, out_conf, out_cls_spec, out_label, out_score);
+    if (rc) return rc;
     return launch(p, ws, ws_bytes, stream);
+}
+
+// layout of the fused step's workspace: [train sums 256 B | tile counts | candidate rows | general post-process workspace]
+struct StepLayout {
+    int tile_cells, num_tiles, grid, stride;
+    size_t off_cnt, off_rows, off_post, total;
+    bool fusable;  // the tiles touch at most two images (the candidate lists have two sides)
+};
+int step_layout(StepLayout* L, int n, int s_h, int s_w, int a, int c) {
+    const long long cells = (long long)s_h * s_w;
+    const int cf = a * (5 + c);
+    int rc = yh_train_tiling((long long)n * cells, cf, &L->tile_cells, &L->num_tiles, &L->grid);
+    if (rc) {
+        yh_set_error("cell too wide for the shared-memory stage (%d floats per cell)", cf);
+        return rc;
+    }
+    L->stride = (5 + c + 1 + 3) & ~3;
+    L->fusable = L->tile_cells <= cells;
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    L->off_cnt = up(yh_train_workspace_bytes());
+    L->off_rows = up(L->off_cnt + (size_t)L->num_tiles * sizeof(int2));
+    L->off_post = up(L->off_rows + (size_t)L->num_tiles * 2 * kYhCandCap * L->stride * 4);
+    L->total = up(L->off_post + yh_postprocess_workspace_bytes(n, (int)(cells * a)));
+    return YH_OK;
 }
 
 }  // namespace
 
+void yh_conf_band(float conf_thre, float* to_reject, float* to_accept) {
+    // sigmoid(t) >= thr needs t >= logit(thr) up to a few ulp; reject only with a wide margin
+    // (the margins are in logit units: 1e-3 there moves the sigmoid by 1e-3 * conf * (1 - conf), >= 1e-5 for
+    // thresholds in [0.01, 0.99] -- far beyond the few ulp of expf and the division; outside that range only a
+    // wide reject margin is used and every other logit takes the sigmoid)
+    *to_accept = INFINITY;
+    if (!(conf_thre > 0.f)) *to_reject = -INFINITY;          // everything passes (or thr is NaN)
+    else if (conf_thre > 1.f) *to_reject = INFINITY;         // nothing can pass
+    else if (conf_thre >= 0.01f && conf_thre <= 0.99f) {
+        const double t = log((double)conf_thre / (1.0 - (double)conf_thre));
+        *to_reject = (float)(t - 1e-3);
+        *to_accept = (float)(t + 1e-3);
+    } else {
+        const double t = conf_thre < 0.9999999 ? log((double)conf_thre / (1.0 - (double)conf_thre)) : 16.0;
+        *to_reject = (float)((t < 16.0 ? t : 16.0) - 0.01);
+    }
+}
+
 extern "C" {
+
+size_t yh_train_post_workspace_bytes(int n, int s_h, int s_w, int a, int c) {
+    StepLayout L;
+    if (n <= 0 || s_h <= 0 || s_w <= 0 || a <= 0 || c <= 0 || step_layout(&L, n, s_h, s_w, a, c)) return 0;
+    return L.total;
+}
+
+int yh_v2_train_post(const float* y, int n, int s_h, int s_w, int a, int c, const float* anchors_wh_host,
+                     float img_h, float img_w, const YhGt* gt, const int32_t* gt_off, int m_local, int m_global,
+                     const float* lambdas_host, float* dy, float* terms, float* loss, int32_t* resp, float* iou_resp,
+                     float conf_thre, float iou_thre, int flags, int max_out, int32_t* keep_idx, int32_t* keep_cnt,
+                     float* out_bbox, float* out_conf, float* out_cls_spec, int32_t* out_label, float* out_score,
+                     const YhExchange* xch_host, void* ws, size_t ws_bytes, void* stream) {
+    YH_REQUIRE(n > 0 && s_h > 0 && s_w > 0 && a > 0 && c > 0, YH_ERR_INVALID, "n, grid, anchors and classes must be positive");
+    StepLayout L;
+    int rc = step_layout(&L, n, s_h, s_w, a, c);
+    if (rc) return rc;
+    YH_REQUIRE(ws && ws_bytes >= L.total, YH_ERR_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, L.total);
+    YH_REQUIRE(((uintptr_t)ws & 255) == 0, YH_ERR_INVALID, "workspace must be 256-byte aligned");
+    unsigned char* base = reinterpret_cast<unsigned char*>(ws);
+    const int overlapped = (flags & YH_STEP_OVERLAPPED) ? 1 : 0;
+    const int post_flags = (flags & YH_STEP_CLASS_AWARE) ? YH_POST_CLASS_AWARE : 0;
+    const bool aligned = ((uintptr_t)y & 15) == 0 && ((uintptr_t)dy & 15) == 0;
+    if (!(L.fusable && aligned)) {
+        // not covered by the fused form: the two kernels of the separate calls, same results
+        rc = yh_train_impl(2, y, n, s_h, s_w, a, c, anchors_wh_host, img_h, img_w, gt, gt_off, m_local, m_global,
+                           lambdas_host, dy, terms, loss, resp, iou_resp, base, yh_train_workspace_bytes(), stream,
+                           overlapped, xch_host, nullptr, nullptr);
+        if (rc) return rc;
+        return postprocess_impl(2, y, n, s_h, s_w, a, c, anchors_wh_host, img_h, img_w, conf_thre, iou_thre,
+                                post_flags | (overlapped ? YH_POST_INPUT_READY : 0), max_out, keep_idx, keep_cnt, out_bbox,
+                                out_conf, out_cls_spec, out_label, out_score, base + L.off_post, L.total - L.off_post, stream);
+    }
+    NmsParams p;  // (validated before anything is launched)
+    rc = fill_head_params(p, 2, y, n, s_h, s_w, a, c, anchors_wh_host, img_h, img_w, conf_thre, iou_thre, post_flags, max_out,
+                          keep_idx, keep_cnt, out_bbox, out_conf, out_cls_spec, out_label, out_score);
+    if (rc) return rc;
+    YH_REQUIRE(keep_cnt && (max_out == 0 || keep_idx) && max_out >= 0, YH_ERR_INVALID, "keep_idx / keep_cnt is NULL or max_out < 0");
+    YH_REQUIRE(((uintptr_t)out_bbox & 15) == 0, YH_ERR_INVALID, "out_bbox must be 16-byte aligned");
+    YhCandBuf cb;
+    cb.rows = reinterpret_cast<float*>(base + L.off_rows);
+    cb.tile_cnt = reinterpret_cast<int2*>(base + L.off_cnt);
+    cb.stride = L.stride;
+    cb.tile_cells = L.tile_cells;
+    cb.num_tiles = L.num_tiles;
+    cb.to_reject = p.to_reject; cb.to_accept = p.to_accept; cb.conf_thre = conf_thre;
+    const bool no_post = (flags & YH_STEP_NO_POST) != 0;
+    rc = yh_train_impl(2, y, n, s_h, s_w, a, c, anchors_wh_host, img_h, img_w, gt, gt_off, m_local, m_global,
+                       lambdas_host, dy, terms, loss, resp, iou_resp, base, yh_train_workspace_bytes(), stream,
+                       overlapped, xch_host, &cb, no_post ? nullptr : &p.fin);
+    if (rc || no_post) return rc;
+    p.cand = cb;
+    p.late_wait = 0;
+    return launch(p, base + L.off_post, L.total - L.off_post, stream, true);
+}
 
 size_t yh_postprocess_workspace_bytes(int n, int preds_per_image) {
     if (n <= 0 || preds_per_image <= kSmemCand) return 16;

@@ -39,8 +39,10 @@
 //     trips at the very end of its critical path; -DYH_X_ONE_KERNEL keeps that variant);
 //   * launched as a programmatic dependent: the prologue overlaps the previous kernel's tail.
 #include <limits.h>
+#include <string.h>
 
 #include "yh_common.cuh"
+#include "yh_finalize.cuh"
 
 namespace {
 
@@ -121,6 +123,7 @@ struct TrainParams {
     float lam[5];
     double inv_den[5];    // 1/(2M), 1/(2M), 1/M, 1/(M(P-1)), 1/M
     float cxy, cwh, cconf, cno, ccls;  // gradient coefficients (see train_impl)
+    YhCandBuf cand;       // fused step (CAND kernels): where the dense pass lists the predictors with conf >= conf_thre
 };
 
 struct WarpSums {
@@ -359,7 +362,11 @@ __device__ __forceinline__ int process_record(const TrainParams& p, const int ve
 // TV/TA/TC != 0 fix version / boxes per cell / classes at compile time (index arithmetic folds,
 // divisions become multiplies); 0 keeps them as run-time values from the geometry.
 // VEC: y and dy are 16-byte aligned (float4 accesses); otherwise the same code with scalar accesses.
-template <bool WRITE_DY, bool VEC, int TV, int TA, int TC>
+// CAND (fused step, yh_v2_train_post; v2, tiles of at most two images): the dense pass also lists the predictors
+// whose confidence reaches conf_thre -- decided on the logit it holds anyway, the sigmoid only inside a narrow band
+// around logit(conf_thre) -- and after the tile barrier their rows are copied from the shared-memory tile to the
+// tile's candidate lists in the workspace, which is all the post-process of the same step reads.
+template <bool WRITE_DY, bool VEC, int TV, int TA, int TC, bool CAND>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const TrainParams p) {
     extern __shared__ __align__(128) float s_tile[];  // the tile's slice of y
     __shared__ __align__(16) int4 s_win[3 * kWindowMax];  // window of ground-truth records (speculative, or exact after a miss)
@@ -376,6 +383,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
     __shared__ int s_ncell;           // records of the list with a private cell copy
     __shared__ int s_collide;         // bit i: patch i shares its cell with another patch (applied in order)
     __shared__ int s_ready;           // tile index + 1 once the record list of that tile is published
+    __shared__ int s_cand[CAND ? 2 * kYhCandCap : 2];  // CAND: tile-local float offsets of the candidates' rows, per image of the tile
+    __shared__ int s_ccnt[2];                          // ... and how many (may exceed kYhCandCap: the list is then incomplete)
 
     const YhGeom& g = p.g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -395,6 +404,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
         for (int c = 0; c <= kChunks + 2; ++c) yh_mbar_init(&s_bar[c], 1);
         yh_mbar_fence_init();
         s_ready = 0;
+        s_ccnt[0] = 0;
+        s_ccnt[1] = 0;
     }
     // everything above overlaps the tail of the previous kernel of the stream (programmatic dependent
     // launch); nothing below may run before that kernel has completed: it may have produced y, and it
@@ -519,6 +530,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
             // TMA producer: the window first (everything the record warp does hangs on it), then the
             // first chunks of the tile
             yh_fence_proxy_async();  // (multi-tile: the stage was read through the generic proxy)
+            if (CAND && t != (int)blockIdx.x) {  // (ordered before the streaming warps' first hit by chunk 0's mbarrier)
+                s_ccnt[0] = 0;
+                s_ccnt[1] = 0;
+            }
             if (wn > 0) {
                 yh_mbar_expect_tx(&s_bar[kChunks], (uint32_t)wn * 48u);
                 yh_bulk_load(s_win, p.gt + w0, (uint32_t)wn * 48u, &s_bar[kChunks]);
@@ -628,6 +643,15 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
             return true;
         };
 
+        // CAND: objectness logit `tl` of the predictor whose row starts at tile-local float `row0` reaches the threshold?
+        // (rare: ~6 % of the predictors at the reference's settings; same rule as the post-process kernel's phase A)
+        auto cand_hit = [&](float tl, int row0) {
+            if (tl >= p.cand.to_accept || yh_sigmoid(tl) >= p.cand.conf_thre) {
+                const int side = row0 < thr0 ? 0 : 1;
+                const int slot = atomicAdd(&s_ccnt[side], 1);
+                if (slot < kYhCandCap) s_cand[side * kYhCandCap + slot] = row0;
+            }
+        };
         if (!record_warp) {
             // ================= streaming warps: the dense pass =================
             const float4* tile4 = reinterpret_cast<const float4*>(s_tile);
@@ -650,6 +674,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
                         tl = m == 2 ? v.z : tl;
                         tl = m == 3 ? v.y : tl;
                         tl = m == 4 ? v.x : tl;
+                        if (CAND && has && tl >= p.cand.to_reject) cand_hit(tl, lf - m);
                         float conf;
                         float w = noobj_term(tl, (lf + 4 - m) < thr0 ? kn0 : kn1, &conf);
                         w = has ? w : 0.f;
@@ -677,6 +702,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
                         tl = m == 2 ? v.z : tl;
                         tl = m == 3 ? v.y : tl;
                         tl = m == 4 ? v.x : tl;
+                        if (CAND && has && tl >= p.cand.to_reject) cand_hit(tl, lf - m);
                         float conf;
                         float w = noobj_term(tl, kn_of(lf + 4 - m), &conf);
                         w = has ? w : 0.f;
@@ -712,6 +738,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
                 const bool is_to = version == 2 ? (pc % bs == 4) : (pc < 5 * A && pc % 5 == 4);
                 float o = 0.f;
                 if (is_to) {
+                    if (CAND && s_tile[lf] >= p.cand.to_reject) cand_hit(s_tile[lf], lf - 4);
                     float conf;
                     const float w = noobj_term(s_tile[lf], kn_of(lf), &conf);
                     sums.no += w;
@@ -824,6 +851,26 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
         XT(1);
         __syncthreads();  // the tile's dense dL/dy is written (and visible to the whole CTA); patches are ready
         XT(2);
+        if (CAND) {
+            // the tile's candidate rows -> its two lists in the workspace (the tile is still in shared memory);
+            // entry = [5 + C logits | predictor index inside its image]
+            const int cn0 = s_ccnt[0], cn1 = s_ccnt[1];
+            if (tid == 0) p.cand.tile_cnt[t] = make_int2(cn0, cn1);
+            const int k0 = min(cn0, kYhCandCap), k1 = min(cn1, kYhCandCap);
+            float* region = p.cand.rows + (size_t)t * (2 * kYhCandCap) * p.cand.stride;
+            for (int i = warp; i < k0 + k1; i += kWarps) {
+                const int side = i >= k0 ? 1 : 0, j = side ? i - k0 : i;
+                const int row0 = s_cand[side * kYhCandCap + j];
+                float* dst = region + (size_t)(side * kYhCandCap + j) * p.cand.stride;
+                for (int q = lane; q < bs; q += 32) dst[q] = s_tile[row0 + q];
+                if (lane == 0) {
+                    const int lcell = row0 / cf;
+                    const int an = (row0 - lcell * cf) / bs;
+                    const int gcell = c0 + lcell;
+                    dst[bs] = __int_as_float((gcell - (gcell / cells) * cells) * A + an);
+                }
+            }
+        }
         const int nrec = s_nrec, npatch = s_npatch;
         // (no records left over: the sums folded before the barrier are final and get published
         //  right after the patch stores, without another CTA barrier)
@@ -941,54 +988,25 @@ extern "C" YH_API int yh_x_rcycles_copy(unsigned int* host, int n) {
 }
 #endif
 
-struct FinalParams {
-    unsigned long long* acc;
-    float* terms;
-    float* loss;
-    float lam[5];
-    double inv_den[5];
-};
-
-// Totals -> terms and loss (reference models/yolov2.py:1132-1138), and the workspace back to zero for the
-// next launch.  Launched as a programmatic dependent right behind yh_train_kernel.
-__global__ void __launch_bounds__(32) yh_train_finalize_kernel(const FinalParams f) {
+// Totals -> terms and loss (reference models/yolov2.py:1132-1138; sharded batches: summed over all ranks through
+// peer memory first, yh_finalize.cuh), and the workspace back to zero for the next launch.  Launched as a
+// programmatic dependent right behind yh_train_kernel.  (The fused step has no such launch: one extra CTA of its
+// post-process kernel does this.)
+__global__ void __launch_bounds__(32) yh_train_finalize_kernel(const YhFinalParams f) {
     yh_grid_launch_dependents();
     yh_grid_dependency_wait();  // the train kernel has completed and its sums are visible
-    if (threadIdx.x == 0) {
-        constexpr double kFix = 4294967296.0;
-        unsigned long long a[7];
-#pragma unroll
-        for (int q = 0; q < 7; ++q) a[q] = __ldcg(f.acc + q);
-        double tot[6];
-#pragma unroll
-        for (int q = 0; q < 6; ++q) tot[q] = (double)a[q] / kFix;
-        const unsigned bad = (unsigned)a[6];
-        const double nan = __longlong_as_double(0x7ff8000000000000ll);
-        const double t0 = (bad & 1u) ? nan : tot[0] * f.inv_den[0];
-        const double t1 = (bad & 2u) ? nan : tot[1] * f.inv_den[1];
-        const double t2 = (bad & 4u) ? nan : tot[2] * f.inv_den[2];
-        const double t3 = (bad & 24u) ? nan : (tot[3] - tot[4]) * f.inv_den[3];
-        const double t4 = (bad & 32u) ? nan : tot[5] * f.inv_den[4];
-        f.terms[0] = (float)t0; f.terms[1] = (float)t1; f.terms[2] = (float)t2;
-        f.terms[3] = (float)t3; f.terms[4] = (float)t4;
-        f.loss[0] = (float)(f.lam[0] * t0 + f.lam[1] * t1 + f.lam[2] * t2 + f.lam[3] * t3 + f.lam[4] * t4);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) f.acc[q] = 0ull;  // ready for the next launch
-    }
+    yh_finalize_warp(f, (int)threadIdx.x);
 }
 
-int launch_finalize(const TrainParams& p, cudaStream_t stream) {
+int launch_finalize(const YhFinalParams& f, cudaStream_t stream) {
 #ifdef YH_X_ONE_KERNEL
     return 0;
 #else
-    FinalParams f;
-    f.acc = p.acc; f.terms = p.terms; f.loss = p.loss;
-    for (int i = 0; i < 5; ++i) { f.lam[i] = p.lam[i]; f.inv_den[i] = p.inv_den[i]; }
     return yh_check_cuda(yh_launch_pdl(yh_train_finalize_kernel, dim3(1), dim3(32), 0, stream, f), "yh_train_finalize launch");
 #endif
 }
 
-template <bool WDY, bool VEC, int TV, int TA, int TC>
+template <bool WDY, bool VEC, int TV, int TA, int TC, bool CAND>
 int launch_variant(const TrainParams& p, int grid, cudaStream_t stream) {
     const size_t smem = (((size_t)p.tile_cells * p.g.cell_floats + 3) & ~(size_t)3) * 4 + 16 +
                         (size_t)p.cell_slots * p.cell_slot_floats * 4;
@@ -997,13 +1015,13 @@ int launch_variant(const TrainParams& p, int grid, cudaStream_t stream) {
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) dev = 0;
     if (smem > configured[dev]) {
-        int rc = yh_check_cuda(cudaFuncSetAttribute(yh_train_kernel<WDY, VEC, TV, TA, TC>,
+        int rc = yh_check_cuda(cudaFuncSetAttribute(yh_train_kernel<WDY, VEC, TV, TA, TC, CAND>,
                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                                "cudaFuncSetAttribute(train)");
         if (rc) return rc;
         configured[dev] = smem;
     }
-    return yh_check_cuda(yh_launch_pdl(yh_train_kernel<WDY, VEC, TV, TA, TC>, dim3(grid), dim3(kThreads), smem, stream, p),
+    return yh_check_cuda(yh_launch_pdl(yh_train_kernel<WDY, VEC, TV, TA, TC, CAND>, dim3(grid), dim3(kThreads), smem, stream, p),
                          "yh_train launch");
 }
 
@@ -1013,16 +1031,71 @@ int launch_geometry(const TrainParams& p, int grid, cudaStream_t stream) {
     // compile-time geometries for the shapes the reference trains: YOLOv2 5 anchors x 20 classes
     // (VOC, models/yolov2.py:49-70) and YOLOv1 B=2, C=20 (config.py:7-11); anything else runs the
     // same kernel with run-time geometry
-    if (g.version == 2 && g.a == 5 && g.c == 20) return launch_variant<WDY, VEC, 2, 5, 20>(p, grid, stream);
-    if (g.version == 1 && g.a == 2 && g.c == 20) return launch_variant<WDY, VEC, 1, 2, 20>(p, grid, stream);
-    return launch_variant<WDY, VEC, 0, 0, 0>(p, grid, stream);
+    if (g.version == 2 && g.a == 5 && g.c == 20) return launch_variant<WDY, VEC, 2, 5, 20, false>(p, grid, stream);
+    if (g.version == 1 && g.a == 2 && g.c == 20) return launch_variant<WDY, VEC, 1, 2, 20, false>(p, grid, stream);
+    return launch_variant<WDY, VEC, 0, 0, 0, false>(p, grid, stream);
 }
 
-int train_impl(int version, const float* y, int n, int s_h, int s_w, int a, int c,
-               const float* anchors_wh_host, float img_h, float img_w, const YhGt* gt,
-               const int32_t* gt_off, int m_local, int m_global, const float* lambdas_host,
-               float* dy, float* terms, float* loss, int32_t* resp, float* iou_resp, void* ws,
-               size_t ws_bytes, void* stream, int late_wait = 0) {
+// the candidate-listing variants of the fused step (v2, aligned tensors only)
+template <bool WDY>
+int launch_geometry_cand(const TrainParams& p, int grid, cudaStream_t stream) {
+    const YhGeom& g = p.g;
+    if (g.a == 5 && g.c == 20) return launch_variant<WDY, true, 2, 5, 20, true>(p, grid, stream);
+    return launch_variant<WDY, true, 2, 0, 0, true>(p, grid, stream);
+}
+
+void tiling(long long total_cells, int cf, int* tile_cells, int* num_tiles, int* grid) {
+    // tiles: whole quads of cells (16-byte aligned starts), at most kTileBytesMax bytes, and a tile
+    // count that fills the resident CTA slots evenly (one tile per CTA when the tensor is small)
+    int slots = yh_sm_count() * kCtasPerSm;
+    if (slots > kMaxGrid) slots = kMaxGrid;
+    const long long quads_total = (total_cells + 3) / 4;
+    long long max_q = kTileBytesMax / (16ll * cf);
+    if (max_q < 1) max_q = 1;
+    long long rounds = (quads_total + slots * max_q - 1) / (slots * max_q);  // tiles per CTA
+    if (rounds < 1) rounds = 1;
+    long long qpt = (quads_total + slots * rounds - 1) / (slots * rounds);    // quads per tile
+    if (qpt < 1) qpt = 1;
+    const long long tiles = (quads_total + qpt - 1) / qpt;
+    *tile_cells = (int)(qpt * 4);
+    *num_tiles = (int)tiles;
+    *grid = (int)(tiles < slots ? tiles : slots);
+}
+
+}  // namespace
+
+int yh_train_tiling(long long total_cells, int cell_floats, int* tile_cells, int* num_tiles, int* grid) {
+    if (total_cells <= 0 || cell_floats <= 0 || kTileBytesMax / (16ll * cell_floats) < 1) return YH_ERR_UNSUPPORTED;
+    tiling(total_cells, cell_floats, tile_cells, num_tiles, grid);
+    return YH_OK;
+}
+
+int yh_fill_exchange(YhFinalParams* f, const YhExchange* xch_host) {
+    f->rank = 0;
+    f->world = 1;
+    for (int q = 0; q < YH_MAX_RANKS; ++q) f->peer[q] = nullptr;
+    if (!xch_host || xch_host->world <= 1) return YH_OK;
+    YH_REQUIRE(xch_host->world <= YH_MAX_RANKS && xch_host->rank >= 0 && xch_host->rank < xch_host->world, YH_ERR_INVALID,
+               "bad exchange: rank %d of %d (at most %d ranks)", xch_host->rank, xch_host->world, YH_MAX_RANKS);
+    for (int q = 0; q < xch_host->world; ++q) {
+        YH_REQUIRE(xch_host->slots[q] && ((uintptr_t)xch_host->slots[q] & 7) == 0, YH_ERR_INVALID,
+                   "exchange buffer of rank %d is NULL or misaligned", q);
+        f->peer[q] = reinterpret_cast<unsigned long long*>(xch_host->slots[q]);
+    }
+    f->rank = xch_host->rank;
+    f->world = xch_host->world;
+    return YH_OK;
+}
+
+// The train head of every entry point.  `cand` != NULL (fused step): the CAND kernel, candidate lists into *cand;
+// the caller checked that the fused form applies.  `fin_out` != NULL: the finalize step is left to the caller
+// (its parameters go to *fin_out), otherwise the one-warp finalize kernel is launched behind the train kernel.
+int yh_train_impl(int version, const float* y, int n, int s_h, int s_w, int a, int c,
+                  const float* anchors_wh_host, float img_h, float img_w, const YhGt* gt,
+                  const int32_t* gt_off, int m_local, int m_global, const float* lambdas_host,
+                  float* dy, float* terms, float* loss, int32_t* resp, float* iou_resp, void* ws,
+                  size_t ws_bytes, void* stream, int late_wait, const YhExchange* xch_host,
+                  const YhCandBuf* cand, YhFinalParams* fin_out) {
     TrainParams p;
     int rc = yh_make_geom(&p.g, version, n, s_h, s_w, a, c, anchors_wh_host, img_h, img_w);
     if (rc) return rc;
@@ -1065,75 +1138,101 @@ int train_impl(int version, const float* y, int n, int s_h, int s_w, int a, int 
     p.cno = (float)(lambdas_host[3] * 2.0 / (M * P1));
     p.ccls = (float)(lambdas_host[4] * 2.0 / M);
 
-    // tiles: whole quads of cells (16-byte aligned starts), at most kTileBytesMax bytes, and a tile
-    // count that fills the resident CTA slots evenly (one tile per CTA when the tensor is small)
-    int slots = yh_sm_count() * kCtasPerSm;
-    if (slots > kMaxGrid) slots = kMaxGrid;
-    const long long quads_total = (total_cells + 3) / 4;
-    const long long max_q = kTileBytesMax / (16ll * cf);
-    YH_REQUIRE(max_q >= 1, YH_ERR_UNSUPPORTED, "cell too wide for the shared-memory stage (%d floats per cell)", cf);
-    long long rounds = (quads_total + slots * max_q - 1) / (slots * max_q);  // tiles per CTA
-    if (rounds < 1) rounds = 1;
-    long long qpt = (quads_total + slots * rounds - 1) / (slots * rounds);    // quads per tile
-    if (qpt < 1) qpt = 1;
-    const long long tiles = (quads_total + qpt - 1) / qpt;
-    p.tile_cells = (int)(qpt * 4);
-    p.num_tiles = (int)tiles;
-    const int grid = (int)(tiles < slots ? tiles : slots);
+    YH_REQUIRE(kTileBytesMax / (16ll * cf) >= 1, YH_ERR_UNSUPPORTED, "cell too wide for the shared-memory stage (%d floats per cell)", cf);
+    int grid = 0;
+    tiling(total_cells, cf, &p.tile_cells, &p.num_tiles, &grid);
 
     // private cell copies: as many as fit next to kCtasPerSm CTAs' tiles in the SM's shared memory
     p.total_floats = total_cells * cf;
     p.cell_slot_floats = (cf + 6 + 3) & ~3;
     {
-        const long long per_cta = (227ll * 1024) / kCtasPerSm - 1024 - 18 * 1024;  // minus reserve and static arrays
+        const long long per_cta = (227ll * 1024) / kCtasPerSm - 1024 - (cand ? 19 : 18) * 1024;  // minus reserve and static arrays
         const long long left = per_cta - ((long long)p.tile_cells * cf * 4 + 32);
         long long slots = left > 0 ? left / (p.cell_slot_floats * 4ll) : 0;
         p.cell_slots = (int)(slots < kCellSlots ? slots : kCellSlots);
     }
+    memset(&p.cand, 0, sizeof(p.cand));
+    YhFinalParams f;
+    f.acc = p.acc; f.terms = p.terms; f.loss = p.loss;
+    for (int i = 0; i < 5; ++i) { f.lam[i] = p.lam[i]; f.inv_den[i] = p.inv_den[i]; }
+    rc = yh_fill_exchange(&f, xch_host);
+    if (rc) return rc;
+
     const bool vec = ((uintptr_t)y & 15) == 0 && ((uintptr_t)dy & 15) == 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (dy) rc = vec ? launch_geometry<true, true>(p, grid, st) : launch_geometry<true, false>(p, grid, st);
-    else rc = vec ? launch_geometry<false, true>(p, grid, st) : launch_geometry<false, false>(p, grid, st);
+    if (cand) {
+        YH_REQUIRE(version == 2 && vec && p.tile_cells <= p.g.cells && cand->tile_cells == p.tile_cells &&
+                   cand->num_tiles == p.num_tiles, YH_ERR_INVALID, "internal: fused step on an input it does not cover");
+        p.cand = *cand;
+        rc = dy ? launch_geometry_cand<true>(p, grid, st) : launch_geometry_cand<false>(p, grid, st);
+    } else if (dy) {
+        rc = vec ? launch_geometry<true, true>(p, grid, st) : launch_geometry<true, false>(p, grid, st);
+    } else {
+        rc = vec ? launch_geometry<false, true>(p, grid, st) : launch_geometry<false, false>(p, grid, st);
+    }
     if (rc) return rc;
-    return launch_finalize(p, st);
+    if (fin_out) {
+        *fin_out = f;
+        return YH_OK;
+    }
+    return launch_finalize(f, st);
 }
-
-}  // namespace
 
 extern "C" {
 
 size_t yh_train_workspace_bytes(void) { return 256; }
+size_t yh_exchange_bytes(void) { return kYhXchBytes; }
 
 int yh_v2_train(const float* y, int n, int s_h, int s_w, int a, int c, const float* anchors_wh_host,
                 float img_h, float img_w, const YhGt* gt, const int32_t* gt_off, int m_local,
                 int m_global, const float* lambdas_host, float* dy, float* terms, float* loss,
                 int32_t* resp, float* iou_resp, void* ws, size_t ws_bytes, void* stream) {
-    return train_impl(2, y, n, s_h, s_w, a, c, anchors_wh_host, img_h, img_w, gt, gt_off, m_local,
-                      m_global, lambdas_host, dy, terms, loss, resp, iou_resp, ws, ws_bytes, stream);
+    return yh_train_impl(2, y, n, s_h, s_w, a, c, anchors_wh_host, img_h, img_w, gt, gt_off, m_local,
+                         m_global, lambdas_host, dy, terms, loss, resp, iou_resp, ws, ws_bytes, stream, 0, nullptr, nullptr, nullptr);
 }
 
 int yh_v1_train(const float* y, int n, int s_h, int s_w, int b, int c, float img_h, float img_w,
                 const YhGt* gt, const int32_t* gt_off, int m_local, int m_global,
                 const float* lambdas_host, float* dy, float* terms, float* loss, int32_t* resp,
                 float* iou_resp, void* ws, size_t ws_bytes, void* stream) {
-    return train_impl(1, y, n, s_h, s_w, b, c, nullptr, img_h, img_w, gt, gt_off, m_local, m_global,
-                      lambdas_host, dy, terms, loss, resp, iou_resp, ws, ws_bytes, stream);
+    return yh_train_impl(1, y, n, s_h, s_w, b, c, nullptr, img_h, img_w, gt, gt_off, m_local, m_global,
+                         lambdas_host, dy, terms, loss, resp, iou_resp, ws, ws_bytes, stream, 0, nullptr, nullptr, nullptr);
 }
 
 int yh_v2_train_overlapped(const float* y, int n, int s_h, int s_w, int a, int c, const float* anchors_wh_host,
                            float img_h, float img_w, const YhGt* gt, const int32_t* gt_off, int m_local,
                            int m_global, const float* lambdas_host, float* dy, float* terms, float* loss,
                            int32_t* resp, float* iou_resp, void* ws, size_t ws_bytes, void* stream) {
-    return train_impl(2, y, n, s_h, s_w, a, c, anchors_wh_host, img_h, img_w, gt, gt_off, m_local,
-                      m_global, lambdas_host, dy, terms, loss, resp, iou_resp, ws, ws_bytes, stream, 1);
+    return yh_train_impl(2, y, n, s_h, s_w, a, c, anchors_wh_host, img_h, img_w, gt, gt_off, m_local,
+                         m_global, lambdas_host, dy, terms, loss, resp, iou_resp, ws, ws_bytes, stream, 1, nullptr, nullptr, nullptr);
 }
 
 int yh_v1_train_overlapped(const float* y, int n, int s_h, int s_w, int b, int c, float img_h, float img_w,
                            const YhGt* gt, const int32_t* gt_off, int m_local, int m_global,
                            const float* lambdas_host, float* dy, float* terms, float* loss, int32_t* resp,
                            float* iou_resp, void* ws, size_t ws_bytes, void* stream) {
-    return train_impl(1, y, n, s_h, s_w, b, c, nullptr, img_h, img_w, gt, gt_off, m_local, m_global,
-                      lambdas_host, dy, terms, loss, resp, iou_resp, ws, ws_bytes, stream, 1);
+    return yh_train_impl(1, y, n, s_h, s_w, b, c, nullptr, img_h, img_w, gt, gt_off, m_local, m_global,
+                         lambdas_host, dy, terms, loss, resp, iou_resp, ws, ws_bytes, stream, 1, nullptr, nullptr, nullptr);
+}
+
+int yh_v2_train_sharded(const float* y, int n, int s_h, int s_w, int a, int c, const float* anchors_wh_host,
+                        float img_h, float img_w, const YhGt* gt, const int32_t* gt_off, int m_local,
+                        int m_global, const float* lambdas_host, float* dy, float* terms, float* loss,
+                        int32_t* resp, float* iou_resp, int flags, const YhExchange* xch_host, void* ws,
+                        size_t ws_bytes, void* stream) {
+    return yh_train_impl(2, y, n, s_h, s_w, a, c, anchors_wh_host, img_h, img_w, gt, gt_off, m_local,
+                         m_global, lambdas_host, dy, terms, loss, resp, iou_resp, ws, ws_bytes, stream,
+                         (flags & YH_STEP_OVERLAPPED) ? 1 : 0, xch_host, nullptr, nullptr);
+}
+
+int yh_v1_train_sharded(const float* y, int n, int s_h, int s_w, int b, int c, float img_h, float img_w,
+                        const YhGt* gt, const int32_t* gt_off, int m_local, int m_global,
+                        const float* lambdas_host, float* dy, float* terms, float* loss, int32_t* resp,
+                        float* iou_resp, int flags, const YhExchange* xch_host, void* ws, size_t ws_bytes,
+                        void* stream) {
+    return yh_train_impl(1, y, n, s_h, s_w, b, c, nullptr, img_h, img_w, gt, gt_off, m_local, m_global,
+                         lambdas_host, dy, terms, loss, resp, iou_resp, ws, ws_bytes, stream,
+                         (flags & YH_STEP_OVERLAPPED) ? 1 : 0, xch_host, nullptr, nullptr);
 }
 
 }  // extern "C"

@@ -51,6 +51,51 @@ def reduce_terms(terms, loss, group=None):
     return buf[:5], buf[5]
 
 
+class PeerExchange:
+    """Peer-mapped exchange buffers for the in-kernel reduction of the loss terms (include/yolohead.h
+    YhExchange, csrc/yh_finalize.cuh): every rank allocates yh_exchange_bytes() of zeroed device memory, the
+    CUDA IPC handles travel through the process group once (`all_gather_object`), every rank opens its peers'
+    buffers (NVLink peer access on one node), and from then on a sharded train call sums the six loss sums of
+    all ranks with 56-byte peer stores inside the kernel that ends the call -- no NCCL call per step.
+
+        xch = PeerExchange(group)            # collective: every rank of the group must call it
+        ops.train_head(..., m_global=M, exchange=xch)   /   ops.train_post(..., exchange=xch)
+
+    Every rank must make the same sequence of exchanging calls (as with any collective).  One node only
+    (CUDA IPC); `reduce_terms` below is the NCCL/gloo form of the same reduction."""
+
+    def __init__(self, group=None, device=None):
+        import torch.distributed as dist
+        from . import _lib
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerExchange needs an initialised process group")
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > _lib.MAX_RANKS:
+            raise ValueError("at most %d ranks" % _lib.MAX_RANKS)
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        nbytes = int(_lib.load().yh_exchange_bytes())
+        # a private allocation (not a slice of a cached block another tensor may share) whose storage is exported
+        self.local = torch.zeros(max(nbytes, 4096), dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize(dev)
+        handle = self.local.untyped_storage()._share_cuda_()
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle, group=group)
+        self._peers = []  # keep the opened storages alive
+        ptrs = []
+        for q, h in enumerate(handles):
+            if q == self.rank:
+                ptrs.append(self.local.data_ptr())
+                continue
+            st = torch.UntypedStorage._new_shared_cuda(*h)
+            self._peers.append(st)
+            ptrs.append(st.data_ptr())
+        self.struct = _lib.YhExchange()
+        self.struct.rank, self.struct.world = self.rank, self.world
+        for q, ptr in enumerate(ptrs):
+            self.struct.slots[q] = ptr
+        dist.barrier(group=group)  # every rank has opened every buffer before anyone uses them
+
+
 def ddp_gradient_scale(world):
     """DDP averages parameter gradients over ranks; the shards' dL/dy are already normalised by
     the global box count, so multiplying the local loss by `world` makes the averaged gradient

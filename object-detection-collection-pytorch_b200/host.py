@@ -6,10 +6,10 @@ tensor and ground truth live in HOST memory.
     t = pipe.submit(y_host, gt_host, gt_off_host)       # enqueue H2D -> kernels -> D2H
     res = pipe.result(t)                                 # loss, dL/dy, kept boxes in host memory
 
-Each submit stages its inputs through pinned buffers, runs the fused train head and the
-post-process kernels (libyolohead, C ABI) and brings loss, dL/dy and the detections back.  Four
-streams (H2D, train head, post-process, D2H) and `depth` slots let consecutive steps overlap on the two PCIe
-directions; nothing is computed on the CPU.
+Each submit stages its inputs through pinned buffers, runs the fused step (train head + post-process,
+libyolohead's yh_v2_train_post through the C ABI; YOLOv1: the two separate kernels) and brings the loss,
+its terms, the detections and -- on request -- dL/dy back.  Three streams (H2D, kernels, D2H) and `depth`
+slots let consecutive steps overlap on the two PCIe directions; nothing is computed on the CPU.
 """
 from __future__ import annotations
 
@@ -41,7 +41,7 @@ class HostHeadPipeline:
         shape = (n, s_h, s_w, a, 5 + c) if version == 2 else (n, s_h, s_w, 5 * a + c)
         self.shape = shape
         d, f32, i32 = self.dev, torch.float32, torch.int32
-        self.s_h2d, self.s_run, self.s_post, self.s_d2h = (torch.cuda.Stream(d) for _ in range(4))
+        self.s_h2d, self.s_run, self.s_d2h = (torch.cuda.Stream(d) for _ in range(3))
         self.slots = []
         # Small inputs (records + offsets) and small outputs (terms, loss, detections) are packed into
         # one buffer each, so a step is two host-to-device and two device-to-host copies: every
@@ -86,6 +86,8 @@ class HostHeadPipeline:
                 ev_in=torch.cuda.Event(), ev_run=torch.cuda.Event(), ev_post=torch.cuda.Event(), ev_out=torch.cuda.Event(),
                 busy=False, post=post,
             )
+            s["res"] = dict(train=dict(dy=s["dy"] if self.compute_dy else None, loss=s["loss"], terms=s["terms"]),
+                            post={k: v for k, v in post.items() if k != "_ws"}, _ws=None)
             self.slots.append(s)
         self._ticket = 0
 
@@ -122,22 +124,24 @@ class HostHeadPipeline:
                 s["gt"][:m].copy_(s["h_gt"][:m], non_blocking=True)
                 s["off"].copy_(s["h_off"], non_blocking=True)
             s["ev_in"].record(self.s_h2d)
-        # the two calls of a step are independent: they run on two streams
-        with torch.cuda.stream(self.s_post):
-            self.s_post.wait_event(s["ev_in"])
-            s["post"] = ops.postprocess(s["y"], version=self.version, img_hw=self.img_hw,
-                                        conf_thre=self.conf_thre, iou_thre=self.iou_thre,
-                                        anchors=self.anchors, boxes_per_cell=self.a,
-                                        class_aware=self.class_aware, max_out=self.max_out,
-                                        want_cls_spec=False, out=s["post"], input_ready=True)
-            s["ev_post"].record(self.s_post)
         with torch.cuda.stream(self.s_run):
             self.s_run.wait_event(s["ev_in"])
-            ops.train_head(s["y"], s["gt"][:m], s["off"], version=self.version, img_hw=self.img_hw,
-                           lambdas=self.lambdas, anchors=self.anchors, boxes_per_cell=self.a,
-                           m_global=m_global, want_grad=self.compute_dy,
-                           out=dict(dy=s["dy"], loss=s["loss"], terms=s["terms"]))
-            self.s_run.wait_event(s["ev_post"])
+            if self.version == 2:
+                # the fused step: train head + post-process, the head tensor read once (yh_v2_train_post)
+                s["res"] = ops.train_post(s["y"], s["gt"][:m], s["off"], img_hw=self.img_hw, lambdas=self.lambdas,
+                                          anchors=self.anchors, conf_thre=self.conf_thre, iou_thre=self.iou_thre,
+                                          m_global=m_global, want_grad=self.compute_dy, class_aware=self.class_aware,
+                                          max_out=self.max_out, want_cls_spec=False, out=s["res"])
+            else:
+                ops.train_head(s["y"], s["gt"][:m], s["off"], version=self.version, img_hw=self.img_hw,
+                               lambdas=self.lambdas, anchors=self.anchors, boxes_per_cell=self.a,
+                               m_global=m_global, want_grad=self.compute_dy,
+                               out=dict(dy=s["dy"], loss=s["loss"], terms=s["terms"]))
+                s["post"] = ops.postprocess(s["y"], version=self.version, img_hw=self.img_hw,
+                                            conf_thre=self.conf_thre, iou_thre=self.iou_thre,
+                                            anchors=self.anchors, boxes_per_cell=self.a,
+                                            class_aware=self.class_aware, max_out=self.max_out,
+                                            want_cls_spec=False, out=s["post"])
             s["ev_run"].record(self.s_run)
         with torch.cuda.stream(self.s_d2h):
             self.s_d2h.wait_event(s["ev_run"])

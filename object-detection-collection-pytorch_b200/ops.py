@@ -68,17 +68,28 @@ def head_shape(y, version, a=None):
     return n, s_h, s_w, a, d - 5 * a
 
 
+def _exchange_arg(exchange):
+    """ctypes pointer to the YhExchange of a dist.PeerExchange (None: single GPU)."""
+    if exchange is None:
+        return None
+    return C.byref(exchange.struct)
+
+
 def train_head(y, gt, gt_off, *, version, img_hw, lambdas, anchors=None, boxes_per_cell=None,
-               m_global=None, want_grad=True, want_resp=False, out=None, input_ready=False):
+               m_global=None, want_grad=True, want_resp=False, out=None, input_ready=False, exchange=None):
     """Fused decode + assignment + loss (+ dL/dy) -- yh_v2_train / yh_v1_train.
 
     y       head tensor (CUDA fp32), gt int32 [M,12] records sorted by image (targets.py),
     gt_off  int32 [N+1] CSR offsets, img_hw (H, W) of the network input,
     lambdas dict with the five reference weights or a sequence of five floats.
     Returns dict(loss 0-dim, terms[5], dy or None, resp/iou_resp or None).
-    `input_ready=True` promises that none of this call's tensors is read or written by the two
-    kernels launched just before it on the current stream (yh_v*_train_overlapped): the kernel then
-    overlaps their tails.
+    `input_ready=True` is the overlap contract of include/yolohead.h (yh_v*_train_overlapped): NONE of this
+    call's tensors -- y, gt, gt_off, the outputs in `out` and the workspace `out["_tws"]` -- is read or written
+    by ANY kernel launched on the current stream since the last call that was not overlapped; the kernel then
+    runs next to the tails of the kernels in front of it.  Overlapped calls need their own workspace per buffer
+    set: pass the same `out` dict again for the same set (it then carries `_tws`).
+    `exchange`: a dist.PeerExchange -- the loss terms of all ranks are summed inside the finalize kernel over
+    peer memory (yh_v*_train_sharded); terms/loss then hold the values of the whole sharded batch.
     """
     y = _require_cuda_f32(y, "y")
     n, s_h, s_w, a, c = head_shape(y, version, boxes_per_cell)
@@ -92,9 +103,14 @@ def train_head(y, gt, gt_off, *, version, img_hw, lambdas, anchors=None, boxes_p
     m_local = int(gt.shape[0])
     m_glob = m_local if m_global is None else int(m_global)
     lam = [lambdas[k] for k in LAMBDA_KEYS] if isinstance(lambdas, dict) else list(lambdas)
-    out = out or {}
+    out = out if out is not None else {}
     with torch.cuda.device(dev):
-        ws = _train_workspace(dev)
+        if input_ready:  # an overlapped call must not share its workspace with the calls it overlaps
+            ws = out.get("_tws")
+            if ws is None:
+                ws = out["_tws"] = torch.zeros(int(_lib.load().yh_train_workspace_bytes()), dtype=torch.uint8, device=dev)
+        else:
+            ws = _train_workspace(dev)
         dy = out.get("dy") if want_grad else None
         if want_grad and dy is None:
             dy = torch.empty_like(y)
@@ -116,16 +132,103 @@ def train_head(y, gt, gt_off, *, version, img_hw, lambdas, anchors=None, boxes_p
         if version == 2:
             if anchors is None or len(anchors) != a:
                 raise ValueError("anchors must list %d (w,h) pairs" % a)
-            _lib.call("yh_v2_train_overlapped" if input_ready else "yh_v2_train", _ptr(y), n, s_h, s_w, a, c, _anchors_host(anchors),
-                      float(img_hw[0]), float(img_hw[1]), _ptr(gt), _ptr(gt_off), m_local, m_glob,
-                      lam_h, _ptr(dy), _ptr(terms), _ptr(loss), _ptr(resp), _ptr(iou_resp),
-                      _ptr(ws), ws.numel(), _stream())
+            if exchange is not None:
+                _lib.call("yh_v2_train_sharded", _ptr(y), n, s_h, s_w, a, c, _anchors_host(anchors),
+                          float(img_hw[0]), float(img_hw[1]), _ptr(gt), _ptr(gt_off), m_local, m_glob,
+                          lam_h, _ptr(dy), _ptr(terms), _ptr(loss), _ptr(resp), _ptr(iou_resp),
+                          STEP_OVERLAPPED if input_ready else 0, _exchange_arg(exchange), _ptr(ws), ws.numel(), _stream())
+            else:
+                _lib.call("yh_v2_train_overlapped" if input_ready else "yh_v2_train", _ptr(y), n, s_h, s_w, a, c, _anchors_host(anchors),
+                          float(img_hw[0]), float(img_hw[1]), _ptr(gt), _ptr(gt_off), m_local, m_glob,
+                          lam_h, _ptr(dy), _ptr(terms), _ptr(loss), _ptr(resp), _ptr(iou_resp),
+                          _ptr(ws), ws.numel(), _stream())
         else:
-            _lib.call("yh_v1_train_overlapped" if input_ready else "yh_v1_train", _ptr(y), n, s_h, s_w, a, c,
-                      float(img_hw[0]), float(img_hw[1]), _ptr(gt), _ptr(gt_off), m_local, m_glob,
-                      lam_h, _ptr(dy), _ptr(terms), _ptr(loss), _ptr(resp), _ptr(iou_resp),
-                      _ptr(ws), ws.numel(), _stream())
-    return dict(loss=loss, terms=terms, dy=dy, resp=resp, iou_resp=iou_resp)
+            if exchange is not None:
+                _lib.call("yh_v1_train_sharded", _ptr(y), n, s_h, s_w, a, c,
+                          float(img_hw[0]), float(img_hw[1]), _ptr(gt), _ptr(gt_off), m_local, m_glob,
+                          lam_h, _ptr(dy), _ptr(terms), _ptr(loss), _ptr(resp), _ptr(iou_resp),
+                          STEP_OVERLAPPED if input_ready else 0, _exchange_arg(exchange), _ptr(ws), ws.numel(), _stream())
+            else:
+                _lib.call("yh_v1_train_overlapped" if input_ready else "yh_v1_train", _ptr(y), n, s_h, s_w, a, c,
+                          float(img_hw[0]), float(img_hw[1]), _ptr(gt), _ptr(gt_off), m_local, m_glob,
+                          lam_h, _ptr(dy), _ptr(terms), _ptr(loss), _ptr(resp), _ptr(iou_resp),
+                          _ptr(ws), ws.numel(), _stream())
+    res = dict(loss=loss, terms=terms, dy=dy, resp=resp, iou_resp=iou_resp)
+    if input_ready:
+        res["_tws"] = ws
+    return res
+
+
+STEP_CLASS_AWARE, STEP_OVERLAPPED, STEP_NO_POST = 1, 2, 4
+
+
+def train_post(y, gt, gt_off, *, img_hw, lambdas, anchors, conf_thre, iou_thre, m_global=None, want_grad=True,
+               want_resp=False, class_aware=False, max_out=None, want_cls_spec=True, out=None, overlapped=False,
+               exchange=None, lists_only=False):
+    """The fused step of a YOLOv2 head -- yh_v2_train_post: train head (loss, terms, dL/dy) AND post-process
+    (threshold + per-image greedy NMS + class pick) of the same head tensor, which is read once: the train
+    head's dense pass lists the candidates, the post-process kernel works from those lists.  Bit-identical to
+    train_head(...) followed by postprocess(...).
+
+    Returns dict(train=<train_head dict>, post=<postprocess dict>, _ws=workspace).  Pass the returned dict as
+    `out` to reuse every buffer (pipelines, CUDA graphs).  `overlapped=True`: the overlap contract of
+    include/yolohead.h for ALL of this call's tensors including the workspace -- rotate complete `out` sets.
+    `exchange`: a dist.PeerExchange for a sharded batch (terms/loss of the whole batch on every rank).
+    """
+    y = _require_cuda_f32(y, "y")
+    n, s_h, s_w, a, c = head_shape(y, 2)
+    dev = y.device
+    if gt.device != dev or gt_off.device != dev:
+        raise ValueError("gt / gt_off must live on the same device as y")
+    if gt.dtype != torch.int32 or gt.dim() != 2 or gt.shape[1] != 12 or not gt.is_contiguous():
+        raise ValueError("gt must be a contiguous int32 [M,12] record tensor")
+    if gt_off.dtype != torch.int32 or gt_off.numel() != n + 1 or not gt_off.is_contiguous():
+        raise ValueError("gt_off must be a contiguous int32 [N+1] tensor")
+    if anchors is None or len(anchors) != a:
+        raise ValueError("anchors must list %d (w,h) pairs" % a)
+    m_local = int(gt.shape[0])
+    m_glob = m_local if m_global is None else int(m_global)
+    lam = [lambdas[k] for k in LAMBDA_KEYS] if isinstance(lambdas, dict) else list(lambdas)
+    p = s_h * s_w * a
+    max_out = p if max_out is None else int(max_out)
+    out = out if out is not None else {}
+    tr, po = out.get("train") or {}, out.get("post")
+    with torch.cuda.device(dev):
+        ws = out.get("_ws")
+        if ws is None:
+            nbytes = int(_lib.load().yh_train_post_workspace_bytes(n, s_h, s_w, a, c))
+            if nbytes == 0:
+                raise ValueError("unsupported head geometry for the fused step")
+            ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        dy = tr.get("dy") if want_grad else None
+        if want_grad and dy is None:
+            dy = torch.empty_like(y)
+        terms = tr.get("terms") if tr.get("terms") is not None else torch.empty(5, dtype=torch.float32, device=dev)
+        loss = tr.get("loss") if tr.get("loss") is not None else torch.empty((), dtype=torch.float32, device=dev)
+        resp = iou_resp = None
+        if want_resp:
+            resp = tr.get("resp") if tr.get("resp") is not None else torch.empty(m_local, dtype=torch.int32, device=dev)
+            iou_resp = tr.get("iou_resp") if tr.get("iou_resp") is not None else torch.empty(m_local, dtype=torch.float32, device=dev)
+        if po is not None:
+            if po["keep_idx"].shape != (n, max_out) or po["keep_idx"].device != dev:
+                raise ValueError("`out` does not match this call's shapes")
+        else:
+            po = dict(keep_idx=torch.empty(n, max_out, dtype=torch.int32, device=dev),
+                      keep_cnt=torch.empty(n, dtype=torch.int32, device=dev),
+                      bbox=torch.empty(n, max_out, 4, dtype=torch.float32, device=dev),
+                      conf=torch.empty(n, max_out, dtype=torch.float32, device=dev),
+                      cls_spec=torch.empty(n, max_out, c, dtype=torch.float32, device=dev) if want_cls_spec else None,
+                      label=torch.empty(n, max_out, dtype=torch.int32, device=dev),
+                      score=torch.empty(n, max_out, dtype=torch.float32, device=dev))
+        flags = ((STEP_CLASS_AWARE if class_aware else 0) | (STEP_OVERLAPPED if overlapped else 0) |
+                 (STEP_NO_POST if lists_only else 0))  # lists_only: the fused train kernel alone (timing aid)
+        _lib.call("yh_v2_train_post", _ptr(y), n, s_h, s_w, a, c, _anchors_host(anchors),
+                  float(img_hw[0]), float(img_hw[1]), _ptr(gt), _ptr(gt_off), m_local, m_glob,
+                  _host_floats(lam), _ptr(dy), _ptr(terms), _ptr(loss), _ptr(resp), _ptr(iou_resp),
+                  float(conf_thre), float(iou_thre), flags, max_out, _ptr(po["keep_idx"]), _ptr(po["keep_cnt"]),
+                  _ptr(po["bbox"]), _ptr(po["conf"]), _ptr(po["cls_spec"]), _ptr(po["label"]), _ptr(po["score"]),
+                  _exchange_arg(exchange), _ptr(ws), ws.numel(), _stream())
+    return dict(train=dict(loss=loss, terms=terms, dy=dy, resp=resp, iou_resp=iou_resp), post=po, _ws=ws)
 
 
 def decode(y, *, version, img_hw, anchors=None, boxes_per_cell=None):

@@ -14,6 +14,20 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
+def test_sharded_fused_step_with_peer_reduction_equals_the_whole_batch(cuda_device):
+    """Two ranks: the loss terms summed inside the kernel over NVLink peer memory equal the whole batch's, the
+    shards' gradients and kept boxes are the whole batch's slices (tests/multi_peer_check.py)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "tests", "multi_peer_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
+    assert res.returncode == 0 and lines, res.stdout[-2000:] + res.stderr[-3000:]
+    out = json.loads(lines[-1])
+    assert out["ok"] and out["world"] == 2
+
+
 def test_cfg4_sharded_training_step_equals_the_whole_batch(cuda_device):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
