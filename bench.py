@@ -55,7 +55,7 @@ def parse_args():
                          "boxes/image); cfg5: BASELINE config 5 (19x19, batch 512 unless --batch, 50..100 boxes/image)")
     ap.add_argument("--unfused", action="store_true",
                     help="a step = the two separate calls (yh_v2_train + yh_v2_postprocess: 3 launches, y read twice) "
-                         "instead of the fused step (yh_v2_train_post: 2 launches, y read once)")
+                         "instead of the fused step (yh_v2_train_post: one kernel per image batch + finalize, y read once)")
     ap.add_argument("--no-collective", action="store_true",
                     help="N > 1: leave the in-kernel peer-memory reduction of the loss terms out of the steps")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 400)")
@@ -101,8 +101,8 @@ def workload_config(workload, batch, sets=None, set_bytes=0, fused=True, collect
     if sets is not None:
         cfg["l2"] = "%d rotating buffer sets per GPU, inputs + outputs + workspace distinct per set (%.0f MB > 126 MB L2)" % (
             sets, sets * set_bytes / 1e6)
-        cfg["step"] = ("fused step: ONE call yh_v2_train_post = train kernel (lists the NMS candidates while it streams y) + "
-                       "candidates-only post-process kernel (also finishes the loss); y read once" if fused else
+        cfg["step"] = ("fused step: ONE call yh_v2_train_post = one kernel, one CTA per image (dense loss/gradient pass, the "
+                       "image's records, threshold, NMS, class pick) + the one-warp finalize kernel; y read once" if fused else
                        "two separate calls: yh_v2_train (+ finalize kernel) + yh_v2_postprocess; y read twice")
         cfg["streams"] = ("one stream, programmatic dependent launches; a graph replay is 4 passes over the %d buffer sets; "
                           "every call but the first of a pass is an overlapped call (include/yolohead.h, THE OVERLAP "
@@ -351,16 +351,16 @@ def main():
     gt = targets.records_to_tensor(case.rec, dev)
     off = torch.from_numpy(case.gt_off).to(dev)
     y0 = case.y.to(dev)
-    sets = [dict(y=y0.clone(), gt=gt.clone(), off=off.clone(), res=None, res_nc=None, lists=None, tr=None, tr_ov=None,
+    sets = [dict(y=y0.clone(), gt=gt.clone(), off=off.clone(), res=None, res_nc=None, tr=None, tr_ov=None,
                  post=None) for _ in range(R)]
     set_bytes = 2 * y0.numel() * 4
 
     stream = torch.cuda.Stream(dev)
 
     # One step = train head (decode + assignment + loss + dL/dy) + post-process (threshold + NMS + class pick) of
-    # the same head tensor.  Default: the fused step, ONE call (yh_v2_train_post): the train kernel lists the
-    # candidates while it streams y, the post-process kernel works from those lists and also finishes the loss --
-    # 2 launches, y read once.  --unfused: the two separate calls (3 launches, y read twice).
+    # the same head tensor.  Default: the fused step, ONE call (yh_v2_train_post): one kernel in which the CTA that
+    # holds an image in shared memory does all of it (+ the one-warp finalize kernel) -- 2 launches, y read once.
+    # --unfused: the two separate calls (3 launches, y read twice).
     # Overlap of consecutive kernels: every kernel of the path is a programmatic dependent launch.  A call may
     # additionally promise that none of its buffers is in use by any kernel launched since the last call without
     # that promise (rotating sets, include/yolohead.h "THE OVERLAP CONTRACT"); it then runs next to the tails of
@@ -384,11 +384,6 @@ def main():
         s[key] = ops.train_head(s["y"], s["gt"], s["off"], version=2, lambdas=lam, m_global=m_global, out=s[key],
                                 input_ready=overlapped, **kw)
 
-    def lists_only(s):  # the fused step's train kernel alone (candidate listing on, no post-process kernel)
-        s["lists"] = ops.train_post(s["y"], s["gt"], s["off"], lambdas=lam, conf_thre=conf_thre, iou_thre=iou_thre,
-                                    m_global=m_global, max_out=MAX_OUT, want_cls_spec=False, out=s["lists"],
-                                    lists_only=True, **kw)
-
     def post_only(s):
         s["post"] = ops.postprocess(s["y"], version=2, conf_thre=conf_thre, iou_thre=iou_thre, max_out=MAX_OUT,
                                     want_cls_spec=False, out=s["post"], **kw)
@@ -411,8 +406,6 @@ def main():
             train_only(s)
             train_only(s, True)
             post_only(s)
-            if fused:
-                lists_only(s)
         stream.synchronize()
         # one graph = ROUNDS passes over the R buffer sets
         ROUNDS = 4
@@ -428,7 +421,6 @@ def main():
         g_train_ov = capture(lambda: [train_only(s, i > 0) for i, s in enumerate(sets)])
         g_post = capture(lambda: [post_only(s) for s in sets])
         g_step_iso = capture(lambda: [step(s, True) for s in sets])
-        g_lists = capture(lambda: [lists_only(s) for s in sets]) if fused else None
         g_full_nc = None
         if xch is not None:  # the same chain without the exchange, to report what the collective costs
             g_full_nc = capture(lambda: [step(s, i == 0, exchange=None, key="res_nc") for _ in range(ROUNDS) for i, s in enumerate(sets)])
@@ -525,7 +517,6 @@ def main():
         post_ms = time_graph(g_post, reps)
         train_ov_ms = time_graph(g_train_ov, reps)
         step_iso_ms = time_graph(g_step_iso, reps)
-        lists_ms = time_graph(g_lists, reps) if g_lists is not None else None
 
     images = B * world
     value = images * K / (ms * 1e-3)
@@ -544,24 +535,32 @@ def main():
     def gbs(nbytes, ms_):
         return nbytes / (ms_ * 1e-3) / 1e9
 
-    # The dominant kernel is the train head: in the fused step the candidate-listing variant of yh_train_kernel.
-    # Its launch duration is the stream-ordered one (every launch starts after the one in front of it has
-    # completed: what a drop-in caller behind a conv gets, and what ncu's serialised per-launch time corresponds
-    # to).  The whole step of the timed region (overlapped launch chain) is reported under `step`.
-    dom_ms = lists_ms if lists_ms is not None else train_ms
-    achieved = gbs(train_bytes, dom_ms)
+    # Fused step: the dominant kernel IS the step -- yh_nms_kernel<.., TRAIN> does the train head's and the
+    # post-process's work on an image it reads once; its launch duration is the stream-ordered one (every launch
+    # starts after the one in front of it has completed: what ncu's serialised per-launch time corresponds to).
+    # Algorithmic bytes per SURVEY 8(d): 3P + 48k + 28K' per image for train head + post-process (the fused
+    # kernel's own minimum is 2P + 48k + 28K': it does not read y a second time -- both fractions are reported).
+    # --unfused: the dominant kernel is yh_train_kernel (2P + 48k).  The step of the timed region (overlapped
+    # launch chain) is reported under `step`.
     step_bytes = train_bytes + post_bytes
-    roofline = {"bound": "hbm",
-                "kernel": ("yh_train_kernel<CAND> (fused decode+assign+loss+dL/dy, listing the NMS candidates) + its one-warp "
-                           "finalize dependent" if fused else
-                           "yh_train_kernel (fused decode+assign+loss+dL/dy) + its one-warp finalize dependent"),
+    fused_min = train_bytes + 28 * kept
+    if fused:
+        dom_ms, dom_bytes = step_iso_ms, step_bytes
+        dom_name = ("yh_nms_kernel<IMG,TRAIN> = the fused step (one CTA per image: dense loss/gradient pass + records + "
+                    "threshold + NMS + class pick, y read once) + its one-warp finalize dependent")
+    else:
+        dom_ms, dom_bytes = train_ms, train_bytes
+        dom_name = "yh_train_kernel (fused decode+assign+loss+dL/dy) + its one-warp finalize dependent"
+    achieved = gbs(dom_bytes, dom_ms)
+    roofline = {"bound": "hbm", "kernel": dom_name,
                 "regime": "stream-ordered launches over the rotating buffer sets (each launch starts after the previous "
                           "one has completed; only launch latency hidden); duration = CUDA-event time of the graph / launches",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": train_bytes,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes,
                 "us_per_launch": dom_ms * 1e3,
                 "separate_kernels": {"what": "the kernels of the two separate calls, stream-ordered launches (the drop-in "
                                              "get_loss / detect path) and back-to-back train-head launches with the overlap promise",
+                                     "train_algorithmic_bytes": train_bytes,
                                      "train_us_per_launch": train_ms * 1e3, "train_frac": gbs(train_bytes, train_ms) / peak,
                                      "train_overlapped_us_per_launch": train_ov_ms * 1e3,
                                      "train_overlapped_frac": gbs(train_bytes, train_ov_ms) / peak,
@@ -573,11 +572,10 @@ def main():
                          "achieved": gbs(step_bytes, ms / K), "frac": gbs(step_bytes, ms / K) / peak,
                          "stream_ordered_us": step_iso_ms * 1e3, "stream_ordered_frac": gbs(step_bytes, step_iso_ms) / peak}}
     if fused:
-        # the fused step does not read y a second time: its own minimum traffic is 2P + 48k + 28K' per image
-        # (+ the candidate rows written and read back: ~1/15 of P each way, counted as overhead, not as algorithmic)
-        fb = train_bytes + 28 * kept
-        roofline["step"]["fused_minimum_bytes"] = fb
-        roofline["step"]["frac_of_fused_minimum"] = gbs(fb, ms / K) / peak
+        roofline["fused_minimum_bytes_per_launch"] = fused_min
+        roofline["frac_of_fused_minimum"] = gbs(fused_min, dom_ms) / peak
+        roofline["step"]["fused_minimum_bytes"] = fused_min
+        roofline["step"]["frac_of_fused_minimum"] = gbs(fused_min, ms / K) / peak
     roofline["traffic"], roofline["traffic_source"] = measured_traffic()
 
     # ---- e2e: host buffers in, host buffers out

@@ -197,26 +197,23 @@ YH_API int yh_v1_postprocess(const float* y, int n, int s_h, int s_w, int b, int
                       float* out_cls_spec, int32_t* out_label, float* out_score,
                       void* ws, size_t ws_bytes, void* stream);
 
-/* ---- the fused step: train head + post-process of the SAME head tensor, y read once -------------------
- * yh_v2_train followed by yh_v2_postprocess reads y twice; here the train head's dense pass (which already
- * takes the sigmoid of every objectness logit) also lists the predictors with conf >= conf_thre -- their
- * 5 + C logits go to a compact per-tile list in the workspace (~50 of 845 predictors per image at the
- * reference's thresholds) -- and the post-process kernel ranks, decodes, suppresses and emits from those
- * lists alone: ~1/15 of the head tensor instead of all of it, a small CTA per image.  It also turns the loss
- * sums into terms/loss (no separate finalize launch).  Results are bit-identical to the two separate calls;
- * images whose lists overflow (more than 64 candidates in a tile, more than 256 in an image) fall back to
- * reading y inside the same kernel.  Inputs the fused form does not cover (unaligned y, tiles spanning more
- * than two images) run the two kernels of the separate calls instead -- same results.
+/* ---- the fused step: train head + post-process of the SAME head tensor in ONE kernel, y read once ---------
+ * yh_v2_train followed by yh_v2_postprocess reads y twice, in two kernels.  Here one CTA per image stages the
+ * image in shared memory (as the post-process does) and does BOTH: the train head's dense pass as the pieces
+ * land (no-object term, dL/dy written from registers), then half of the CTA processes the image's ground-truth
+ * records while the other half resolves its NMS (rank, decode, pair tests, greedy order, class pick, emit); the
+ * one-warp finalize kernel follows.  Decisions, dL/dy and detections are bit-identical to the two separate
+ * calls; loss and terms agree to float rounding (the partial sums are grouped by image instead of by tile).
+ * Inputs the fused kernel does not cover (unaligned y or dy, images larger than the 200 KB shared-memory
+ * stage, fewer than 3 classes) run the kernels of the two separate calls instead -- same results.
  *   flags: YH_STEP_CLASS_AWARE (as YH_POST_CLASS_AWARE), YH_STEP_OVERLAPPED (THE OVERLAP CONTRACT above, for
  *   all buffers of this call including ws).
  *   xch_host: NULL on one GPU.  Sharded batches: see YhExchange -- the loss terms of all ranks are summed
- *   inside the kernel over peer memory; every rank's terms/loss then hold the values of the whole batch.
- *   ws: yh_train_post_workspace_bytes() bytes, zero-filled once when allocated (calls leave it reusable). */
+ *   inside the finalize kernel over peer memory; every rank's terms/loss then hold the values of the whole batch.
+ *   ws: yh_train_post_workspace_bytes() bytes, 256-byte aligned, zero-filled once when allocated (calls leave it
+ *   reusable). */
 #define YH_STEP_CLASS_AWARE 1
 #define YH_STEP_OVERLAPPED 2
-#define YH_STEP_NO_POST 4 /* train head with candidate listing only (the lists stay in ws, terms/loss by the
-                             finalize kernel, the post-process outputs are not touched): times the fused
-                             train kernel alone */
 
 /* Peer-memory exchange of the loss sums between the ranks of a sharded batch (one process per GPU).  Every
  * rank allocates yh_exchange_bytes() bytes of device memory, zero-filled once, and maps the buffers of all

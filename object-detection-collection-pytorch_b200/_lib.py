@@ -10,7 +10,7 @@ import os
 import threading
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libyolohead.so")
+LIB_PATH = os.environ.get("YH_LIB_PATH") or os.path.join(PKG_DIR, "libyolohead.so")  # (override: experimental builds)
 
 ABI_VERSION = 2
 MAX_RANKS = 16

@@ -46,11 +46,12 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False, extra=()):
-    if not force and not needs_build():
+def build(force=False, verbose=False, extra=(), out=None):
+    """`out`: build an experimental variant (extra -D flags) next to the product library."""
+    if out is None and not force and not needs_build():
         return LIB_PATH
     cmd = [find_nvcc(), "-shared", *NVCC_FLAGS, *extra, "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-           "-o", LIB_PATH, *sources()]
+           "-o", out or LIB_PATH, *sources()]
     if verbose:
         print(" ".join(cmd), flush=True)
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -58,7 +59,7 @@ def build(force=False, verbose=False, extra=()):
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose and (res.stdout or res.stderr):
         print(res.stdout + res.stderr)
-    return LIB_PATH
+    return out or LIB_PATH
 
 
 if __name__ == "__main__":

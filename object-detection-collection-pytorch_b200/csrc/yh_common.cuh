@@ -43,25 +43,12 @@ struct YhGeom {
 int yh_make_geom(YhGeom* g, int version, int n, int s_h, int s_w, int a, int c,
                  const float* anchors_wh_host, float img_h, float img_w);
 
-// How the train head cuts the flattened batch of cells into tiles (yh_train.cu); the fused step's
-// post-process needs the same numbers to find an image's candidate lists.
+// How the train head cuts the flattened batch of cells into tiles (yh_train.cu).
 int yh_train_tiling(long long total_cells, int cell_floats, int* tile_cells, int* num_tiles, int* grid);
 
 // sigmoid(t) >= conf_thre decided on the logit: below to_reject never, from to_accept on always, in between
 // the sigmoid is evaluated (yh_nms.cu; the fused train head applies the same rule, so both list the same set).
 void yh_conf_band(float conf_thre, float* to_reject, float* to_accept);
-
-// Candidates handed from the train head's dense pass to the post-process of the same step (yh_v2_train_post):
-// per tile two lists (the tile's first image, its second image), kYhCandCap entries each, an entry =
-// [the predictor's 5 + C logits | its index inside the image (int bits) | pad to a multiple of 4 floats].
-constexpr int kYhCandCap = 64;
-struct YhCandBuf {
-    float* rows;       // [num_tiles][2][kYhCandCap][stride]
-    int2* tile_cnt;    // [num_tiles]: TRUE counts of the two lists (a count above kYhCandCap: the list is incomplete)
-    int stride;        // floats per entry
-    int tile_cells, num_tiles;
-    float to_reject, to_accept, conf_thre;
-};
 
 // Totals of the six fixed-point loss sums -> terms and loss (yh_finalize.cuh); with world > 1 the sums of
 // all ranks are exchanged through peer memory first.
@@ -75,6 +62,13 @@ struct YhFinalParams {
     unsigned long long* peer[YH_MAX_RANKS];  // exchange buffers of all ranks mapped into this process
 };
 int yh_fill_exchange(YhFinalParams* f, const YhExchange* xch_host);
+int yh_launch_finalize(const YhFinalParams& f, cudaStream_t stream);  // the one-warp finalize kernel (yh_train.cu)
+
+// gradient coefficients of the five loss terms (yh_loss_coefs fills them and the finalize parameters' lam / inv_den)
+struct YhLossCoef {
+    float cxy, cwh, cconf, cno, ccls;
+};
+void yh_loss_coefs(const float* lambdas_host, int m_global, int preds, YhLossCoef* k, YhFinalParams* f);
 
 // The train head behind every train entry point (yh_train.cu), and the post-process behind every post-process
 // entry point (yh_nms.cu); the fused step (yh_v2_train_post) sequences the two.
@@ -82,8 +76,7 @@ int yh_train_impl(int version, const float* y, int n, int s_h, int s_w, int a, i
                   const float* anchors_wh_host, float img_h, float img_w, const YhGt* gt,
                   const int32_t* gt_off, int m_local, int m_global, const float* lambdas_host,
                   float* dy, float* terms, float* loss, int32_t* resp, float* iou_resp, void* ws,
-                  size_t ws_bytes, void* stream, int late_wait, const YhExchange* xch_host,
-                  const YhCandBuf* cand, YhFinalParams* fin_out);
+                  size_t ws_bytes, void* stream, int late_wait, const YhExchange* xch_host);
 
 // ------------------------------------------------------------------------------------------
 // device helpers

@@ -36,10 +36,12 @@
 // tiles of 256 candidates, through generic pointers (rest below, also the path of yh_nms and of
 // unaligned or oversized head tensors).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "yh_common.cuh"
 #include "yh_finalize.cuh"
+#include "yh_record.cuh"
 
 namespace {
 
@@ -47,10 +49,8 @@ namespace {
 #define YH_X_NMS_THREADS 512
 #endif
 constexpr int kThreadsFull = YH_X_NMS_THREADS;  // threads per CTA of the kernels that read the head tensor
-#ifndef YH_X_CAND_THREADS
-#define YH_X_CAND_THREADS 256
-#endif
-constexpr int kThreadsCand = YH_X_CAND_THREADS;  // ... of the candidates-only kernel of the fused step
+constexpr int kTeam = 256;    // fused step: threads of a CTA that resolve the image's NMS while the others process its records
+constexpr int kRecSmem = 32;  // fused step: records of the image staged in shared memory (more: read from global memory)
 constexpr int kTile = 256;             // ranked candidates per suppression tile
 constexpr int kTileWords = kTile / 32;
 constexpr int kSmemCand = 256;         // candidates held in shared memory
@@ -65,7 +65,7 @@ constexpr int kGroups = 4;             // whole-image mode: the image arrives in
 constexpr int kImgBytesMax = YH_X_NMS_IMG_BYTES;
 
 enum { SRC_HEAD = 0, SRC_DECODED = 2 };
-enum { MODE_GENERAL = 0, MODE_IMG = 1, MODE_CAND = 2 };
+enum { MODE_GENERAL = 0, MODE_IMG = 1 };
 
 #ifdef YH_X_TRACE
 __device__ unsigned long long g_ntrace[4096 * 16];
@@ -85,6 +85,10 @@ extern "C" YH_API int yh_x_ntrace_copy(unsigned long long* host, int n) {
 template <bool B>
 struct FastTag {
     static constexpr bool value = B;
+};
+template <int N>
+struct IntTag {
+    static constexpr int value = N;
 };
 
 struct NmsParams {
@@ -116,8 +120,15 @@ struct NmsParams {
     int stage_bytes;         // shared memory in front of the candidate arrays (staged rows, or the whole image)
     int slot_floats;         // floats per staged row slot (multiple of 4)
     unsigned magic_sw;       // ceil(2^32 / s_w): cell / s_w == umulhi(cell, magic_sw) for cell < 2^16
-    YhCandBuf cand;          // MODE_CAND: the candidate lists the train head of the same step wrote
-    YhFinalParams fin;       // MODE_CAND: the loss totals -> terms / loss, done by one extra CTA of this kernel
+    // ---- the fused step (TRAIN kernels): the train head's work on the image this CTA holds anyway
+    float* dy;               // [N, ...] gradient (NULL: loss only)
+    const YhGt* gt;          // records sorted by image
+    const int32_t* gt_off;   // [N+1]
+    int m_local;
+    unsigned long long* acc; // the six fixed-point loss sums (train workspace)
+    float cxy, cwh, cconf, cno, ccls;
+    int32_t* resp;
+    float* iou_resp;
 };
 
 struct Cand {
@@ -314,16 +325,25 @@ __device__ __forceinline__ bool suppresses_dense(const float4& bi, float ai, con
 // IMG: the image's whole slice of the head tensor is staged in shared memory by kGroups bulk copies
 // issued at the start (ONE global round trip, no per-candidate copies); otherwise the objectness
 // logits are read with strided loads and only the candidates' rows are staged.
-// MODE_CAND (the fused step): the candidates come from the lists the train head's dense pass wrote -- one bulk copy
-// per tile list, ~50 rows of 5 + C logits per image instead of the image -- and the lean path below runs on those rows;
-// an image whose lists overflowed is processed from the head tensor by the general path, in the same CTA.  One CTA
-// beyond the images turns the train head's loss totals into terms and loss.
-template <int TV, int TA, int TC, int MODE, int NTH>
+// TRAIN (the fused step, yh_v2_train_post; whole-image mode, v2): the CTA that holds an image in shared memory for
+// the post-process ALSO does the train head's work on it -- y is read once per step, by one kernel:
+//   * as each piece of the image lands, its warp group runs the dense pass over it: the no-object term and its
+//     gradient per objectness logit, dL/dy written with 16-byte stores straight from registers (zero elsewhere);
+//   * once the image is complete, the upper half of the CTA processes the image's ground-truth records (one warp
+//     per record, dealt by cell so that records sharing a cell accumulate in CSR order; yh_record.cuh -- the same
+//     arithmetic, the same bits as the train head) on top of the dense values, while the lower half resolves the
+//     image's NMS (rank, decode, pair tests, greedy order, class pick, emit: the lean path below on a 256-thread team);
+//   * the CTA's six loss sums go onto the 64-bit fixed-point accumulators; yh_train_finalize_kernel follows.
+template <int TV, int TA, int TC, int MODE, int NTH, bool TRAIN>
 __global__ void __launch_bounds__(NTH, NTH >= 512 ? 2 : 3) yh_nms_kernel(const NmsParams p) {
     constexpr int kThreads = NTH, kWarps = NTH / 32;
-    constexpr bool IMG = MODE == MODE_IMG, CANDM = MODE == MODE_CAND;
+    constexpr bool IMG = MODE == MODE_IMG;
+    static_assert(!TRAIN || (MODE == MODE_IMG && NTH > kTeam), "the fused step runs on the whole-image kernel");
+    __shared__ float red[TRAIN ? kWarps * 6 : 1];                       // TRAIN: the warps' six loss sums
+    __shared__ __align__(16) int4 s_rec[TRAIN ? 3 * kRecSmem : 1];      // TRAIN: the image's first records
+    __shared__ __align__(8) uint64_t bar_rec;                           // TRAIN: ... have landed
     extern __shared__ __align__(128) unsigned char smem_raw[];  // [staged rows or image | candidate arrays]
-    __shared__ unsigned int mask[kTile * kTileWords];
+    __shared__ __align__(16) unsigned int mask[kTile * kTileWords];  // (zeroed with 16-byte stores)
     __shared__ unsigned int rem0[kTileWords];
     __shared__ __align__(8) uint64_t bar;      // staged rows have landed (transaction bytes)
     __shared__ __align__(8) uint64_t bar_list; // every thread has listed its candidates
@@ -333,12 +353,6 @@ __global__ void __launch_bounds__(NTH, NTH >= 512 ? 2 : 3) yh_nms_kernel(const N
     const YhGeom& g = p.g;
     const int img = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (CANDM && img == p.n) {  // the extra CTA: the train head's totals -> terms and loss (it has completed after the wait)
-        yh_grid_launch_dependents();
-        yh_grid_dependency_wait();
-        if (warp == 0) yh_finalize_warp(p.fin, lane);
-        return;
-    }
     const int P = p.p;
     const bool head = p.src == SRC_HEAD;
     const int A = TA ? TA : g.a, C = TC ? TC : p.c;
@@ -352,7 +366,7 @@ __global__ void __launch_bounds__(NTH, NTH >= 512 ? 2 : 3) yh_nms_kernel(const N
     auto carve_ws = [&]() -> Cand { return p.ws ? carve(p.ws + (size_t)img * p.ws_per_image, P) : ca; };
 
     NT(0);
-    if (IMG || CANDM) {  // the single-tile path sets suppression bits with atomicOr
+    if (IMG) {  // the single-tile path sets suppression bits with atomicOr
         for (int q = tid; q < kTile * kTileWords / 4; q += kThreads) reinterpret_cast<uint4*>(mask)[q] = make_uint4(0u, 0u, 0u, 0u);
     }
     if (tid == 0) {
@@ -360,23 +374,17 @@ __global__ void __launch_bounds__(NTH, NTH >= 512 ? 2 : 3) yh_nms_kernel(const N
         s_kept = 0;
         yh_mbar_init(&bar, kThreads);
         yh_mbar_init(&bar_list, kThreads);
-        if (IMG || CANDM) {
+        if (IMG) {
 #pragma unroll
             for (int q = 0; q < kGroups; ++q) yh_mbar_init(&bar_img[q], 1);
         }
+        if (TRAIN) yh_mbar_init(&bar_rec, 1);
         yh_mbar_fence_init();
     }
     // (programmatic dependent launch: the prologue above overlaps the previous kernel's tail; global
     // memory is only touched once that kernel has completed)
-    if (CANDM) {
-        // the lists are the previous kernel's output: always wait for it -- but let the NEXT kernel of the stream go
-        // first (an overlapped train head of the next step streams next to this kernel's latency-bound phases)
-        yh_grid_launch_dependents();
-        yh_grid_dependency_wait();
-    } else {
-        if (!p.late_wait) yh_grid_dependency_wait();
-        yh_grid_launch_dependents();
-    }
+    if (!p.late_wait) yh_grid_dependency_wait();
+    yh_grid_launch_dependents();
     // IMG: the image's aligned window [image start - fsh, ...) goes to shared memory in kGroups pieces cut at
     // unit boundaries (v2: predictors, v1: cells) rounded down to 16 bytes; window float w is image float w - fsh
     const int img_units = (TV ? TV : p.g.version) == 2 ? p.p : p.g.cells;
@@ -398,7 +406,25 @@ __global__ void __launch_bounds__(NTH, NTH >= 512 ? 2 : 3) yh_nms_kernel(const N
             }
         }
     }
+    // TRAIN: the image's record range (every thread: the dense pass needs the box count), and its first records
+    // into shared memory with one bulk copy -- both round trips are hidden behind the arrival of the image
+    int o0 = 0, o1 = 0;
+    WarpSums sums = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (TRAIN) {
+        o0 = __ldg(p.gt_off + img);
+        o1 = min(__ldg(p.gt_off + img + 1), p.m_local);
+    }
     __syncthreads();
+    if (TRAIN && tid == kThreads - 32) {
+        const int nsm = min(o1 - o0, kRecSmem);
+        if (nsm > 0) {
+            yh_mbar_expect_tx(&bar_rec, (uint32_t)nsm * 48u);
+            yh_bulk_load(s_rec, p.gt + o0, (uint32_t)nsm * 48u, &bar_rec);
+        } else {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(yh_smem_u32(&bar_rec)) : "memory");
+        }
+    }
+    const float kn = (float)(o1 - o0);
 
     // float offsets, inside the image, of a predictor's 5 box logits and C class logits (32-bit: one
     // image of the head tensor is far below 2^31 floats); `fsh` is the image's own shift inside its
@@ -437,77 +463,6 @@ __global__ void __launch_bounds__(NTH, NTH >= 512 ? 2 : 3) yh_nms_kernel(const N
 
     NT(1);
     uint32_t tx = 0;
-    // ---------------- A (candidate lists of the fused step) ----------------
-    // The image's cells lie in tiles t_lo..t_hi of the train head; a tile holds one list for its first image and one
-    // for its second.  One warp reads the lists' lengths, and -- if no list overflowed and the image has at most
-    // kSmemCand candidates -- fetches each list with ONE bulk copy into consecutive row slots.
-    const int cstride = TC ? ((5 + TC + 1 + 3) & ~3) : p.cand.stride;  // floats per list entry
-    bool cand_lean = false;
-    if (CANDM) {
-        if (warp == 0) {
-            const int R = p.cand.tile_cells, cells = g.cells;
-            const int t_lo = (img * cells) / R, t_hi = ((img + 1) * cells - 1) / R;
-            int total = 0, cnt0 = 0, side0 = 0;
-            bool over = false;
-            for (int tb = t_lo; tb <= t_hi; tb += 32) {  // pass 1: lengths
-                const int t = tb + lane;
-                int cnt = 0, side = 0;
-                if (t <= t_hi) {
-                    const int2 c2 = __ldcg(p.cand.tile_cnt + t);
-                    side = ((t * R) / cells == img) ? 0 : 1;
-                    cnt = side ? c2.y : c2.x;
-                }
-                if (tb == t_lo) { cnt0 = cnt; side0 = side; }
-                over = over || cnt > kYhCandCap;
-                total += cnt;
-            }
-            for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-            over = __any_sync(0xffffffffu, over) || total > kSmemCand;
-            if (!over) {
-                int base = 0;
-                uint32_t mytx = 0;
-                for (int tb = t_lo; tb <= t_hi; tb += 32) {  // pass 2: one bulk copy per non-empty list
-                    const int t = tb + lane;
-                    int cnt = cnt0, side = side0;
-                    if (tb != t_lo) {
-                        cnt = 0;
-                        if (t <= t_hi) {
-                            const int2 c2 = __ldcg(p.cand.tile_cnt + t);
-                            side = ((t * R) / cells == img) ? 0 : 1;
-                            cnt = side ? c2.y : c2.x;
-                        }
-                    }
-                    int inc = cnt;
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int v = __shfl_up_sync(0xffffffffu, inc, o);
-                        if (lane >= o) inc += v;
-                    }
-                    if (cnt > 0) {
-                        const uint32_t bytes = (uint32_t)(cnt * cstride) * 4u;
-                        yh_bulk_load(stage + (size_t)(base + inc - cnt) * cstride,
-                                     p.cand.rows + ((size_t)t * 2 + side) * kYhCandCap * cstride, bytes, &bar_img[0]);
-                        mytx += bytes;
-                    }
-                    base += __shfl_sync(0xffffffffu, inc, 31);
-                }
-                for (int o = 16; o > 0; o >>= 1) mytx += __shfl_xor_sync(0xffffffffu, mytx, o);
-                if (lane == 0) {
-                    if (mytx) yh_mbar_expect_tx(&bar_img[0], mytx);
-                    else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(yh_smem_u32(&bar_img[0])) : "memory");
-                }
-            }
-            if (lane == 0) s_count = over ? -1 : total;
-        }
-        __syncthreads();
-        cand_lean = s_count >= 0;
-        if (cand_lean) {
-            yh_mbar_wait(&bar_img[0], 0);  // the rows have landed
-        } else {
-            __syncthreads();
-            if (tid == 0) s_count = 0;  // this image continues from the head tensor (general path below)
-            __syncthreads();
-        }
-    }
     if (IMG) {
         // ---------------- A (whole image): each warp group thresholds its piece as it lands ----------------
         const float* win = reinterpret_cast<const float*>(smem_raw);
@@ -525,6 +480,56 @@ __global__ void __launch_bounds__(NTH, NTH >= 512 ? 2 : 3) yh_nms_kernel(const N
         if (gtid < 32) yh_mbar_wait(&bar_img[grp], 0);
         asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kGroupThreads) : "memory");
         yh_mbar_wait(&bar_img[grp], 0);
+        if (TRAIN) {
+            // ---- dense pass over this group's piece (the train head's, yh_train.cu: same helpers, same bits): window
+            // floats 4*i4 .. 4*i4+3 are image floats f0 .. f0+3 and sit at positions m .. m+3 of a predictor row; the
+            // objectness logit (position 4) is among them iff 1 <= m <= 4.  dL/dy is zero but the objectness channel.
+            const float4* win4 = reinterpret_cast<const float4*>(smem_raw);
+            float4* dwin4 = p.dy ? reinterpret_cast<float4*>(p.dy + ((long long)img * p.img_floats - fsh)) : nullptr;
+            const int q4lo = grp == 0 ? 0 : (fsh + ((img_units * grp) / kGroups) * img_unit_floats) >> 2;
+            const int q4hi = grp == kGroups - 1 ? (fsh + p.img_floats + 3) >> 2
+                                                : (fsh + ((img_units * (grp + 1)) / kGroups) * img_unit_floats) >> 2;
+            const int mstep = (4 * kGroupThreads) % bs;
+            int f0 = 4 * (q4lo + gtid) - fsh;
+            int m = (f0 + bs) % bs;
+            for (int i4 = q4lo + gtid; i4 < q4hi; i4 += kGroupThreads, f0 += 4 * kGroupThreads) {
+                if (f0 >= 0 && f0 + 3 < p.img_floats) {
+                    const float4 v = win4[i4];
+                    const bool has = (unsigned)(m - 1) < 4u;
+                    float tl = v.w;
+                    tl = m == 2 ? v.z : tl;
+                    tl = m == 3 ? v.y : tl;
+                    tl = m == 4 ? v.x : tl;
+                    float conf;
+                    float w = noobj_term(tl, kn, &conf);
+                    w = has ? w : 0.f;
+                    sums.no += w;
+                    const float val = noobj_grad(w, conf, p.cno);
+                    float4 o;
+                    o.x = m == 4 ? val : 0.f;
+                    o.y = m == 3 ? val : 0.f;
+                    o.z = m == 2 ? val : 0.f;
+                    o.w = m == 1 ? val : 0.f;
+                    if (dwin4) dwin4[i4] = o;
+                } else {
+                    // the image's first / last 16 bytes shared with its neighbours (images are not multiples of 16 bytes)
+                    for (int j = 0; j < 4; ++j) {
+                        const int f = f0 + j;
+                        if (f < 0 || f >= p.img_floats) continue;
+                        float o = 0.f;
+                        if (f % bs == 4) {
+                            float conf;
+                            const float w = noobj_term(win[4 * i4 + j], kn, &conf);
+                            sums.no += w;
+                            o = noobj_grad(w, conf, p.cno);
+                        }
+                        if (p.dy) p.dy[(long long)img * p.img_floats + f] = o;
+                    }
+                }
+                m += mstep;
+                m = m >= bs ? m - bs : m;
+            }
+        }
         // conf >= conf_thre is decided on the logit wherever that is safe (to_reject / to_accept leave a
         // band around logit(conf_thre) in which the sigmoid is evaluated); survivors are listed with
         // their LOGIT -- the sigmoid of the ~50 survivors is taken later by as many threads, instead
@@ -556,7 +561,7 @@ __global__ void __launch_bounds__(NTH, NTH >= 512 ? 2 : 3) yh_nms_kernel(const N
                 }
             }
         }
-    } else if (!cand_lean)
+    } else
     // ---------------- A: threshold + stage the survivors' rows ----------------
     for (int base = 0; base < P; base += kThreads * kLoadUnroll) {
         float val[kLoadUnroll];
@@ -623,6 +628,85 @@ __global__ void __launch_bounds__(NTH, NTH >= 512 ? 2 : 3) yh_nms_kernel(const N
     const bool with_labels = head ? (p.class_aware != 0) : (p.labels != nullptr);
     int2* const pairs = reinterpret_cast<int2*>(ca.u_conf);  // IMG: (u_conf | u_idx) hold 64-bit entries instead
 
+    // ---- fused step: the image's ground-truth records, by the warps that do not resolve the NMS.  Records are dealt
+    // by cell (cell % team warps), so the records of one cell stay on one warp, in CSR order: collisions on a
+    // predictor accumulate deterministically.  The rows hold the dense pass' values (complete: every thread has
+    // passed the list barrier); a cell's first record overwrites without reading them back.
+    auto do_records = [&]() {
+        constexpr int kRecWarps = kWarps - kTeam / 32;
+        const int tw = warp - kTeam / 32;
+        const int nrec = o1 - o0;
+        if (nrec <= 0) return;
+        const int nsm = min(nrec, kRecSmem);
+        yh_mbar_wait(&bar_rec, 0);
+        const float* win = reinterpret_cast<const float*>(smem_raw);
+        float* dimg = p.dy ? p.dy + (long long)img * p.img_floats : nullptr;
+        const float my_pw = lane < 5 * A ? g.pw[lane / 5] : 0.f, my_ph = lane < 5 * A ? g.ph[lane / 5] : 0.f;
+        const bool track = g.cells <= 64 * kRecWarps;  // cells this warp has updated fit one 64-bit mask
+        unsigned long long seen = 0ull;
+        for (int base = 0; base < nrec; base += 32) {
+            int lc = -1;
+            const int r = base + lane;
+            if (r < nrec) {
+                const int4 h = r < nsm ? s_rec[3 * r] : __ldg(reinterpret_cast<const int4*>(p.gt + o0 + r));
+                const bool ok = h.x == img && h.y >= 0 && h.y < g.s_h && h.z >= 0 && h.z < g.s_w;
+                lc = ok ? h.y * g.s_w + h.z : -1;
+                if (lc >= 0 && lc % kRecWarps != tw) lc = -1;
+            }
+            unsigned bal = __ballot_sync(0xffffffffu, lc >= 0);
+            while (bal) {
+                const int b = __ffs(bal) - 1;
+                bal &= bal - 1u;
+                const int lcell = __shfl_sync(0xffffffffu, lc, b);
+                const int rj = base + b;
+                RecordRegs rr;
+                if (rj < nsm) {
+                    rr.hd = s_rec[3 * rj];
+                    rr.tt = *reinterpret_cast<const float4*>(s_rec + 3 * rj + 1);
+                    rr.bb = *reinterpret_cast<const float4*>(s_rec + 3 * rj + 2);
+                } else {
+                    const int4* rp = reinterpret_cast<const int4*>(p.gt + o0 + rj);
+                    rr.hd = __ldg(rp);
+                    rr.tt = __ldg(reinterpret_cast<const float4*>(rp + 1));
+                    rr.bb = __ldg(reinterpret_cast<const float4*>(rp + 2));
+                }
+                const unsigned long long bit = 1ull << ((lcell / kRecWarps) & 63);
+                const bool again = !track || (seen & bit) != 0ull;
+                seen |= bit;
+                if (dimg) process_record<1>(p, 2, A, C, rr, o0 + rj, win + fsh + lcell * cf, dimg + lcell * cf, again, nullptr, nullptr,
+                                            kn, lane, my_pw, my_ph, sums);
+                else process_record<0>(p, 2, A, C, rr, o0 + rj, win + fsh + lcell * cf, nullptr, false, nullptr, nullptr,
+                                       kn, lane, my_pw, my_ph, sums);
+            }
+        }
+    };
+    // ---- fused step: the CTA's six loss sums -> the 64-bit fixed-point accumulators (exact, order-independent;
+    // yh_train.cu has the full story); the finalize kernel behind this one turns the totals into terms and loss
+    auto publish_sums = [&]() {
+        const float s_no = yh_warp_sum(sums.no);
+        const float s_xy = yh_warp_sum(sums.xy), s_wh = yh_warp_sum(sums.wh), s_conf = yh_warp_sum(sums.conf);
+        const float s_nr = yh_warp_sum(sums.nr), s_cls = yh_warp_sum(sums.cls);
+        if (lane == 0) {
+            float* r = red + warp * 6;
+            r[0] = s_xy; r[1] = s_wh; r[2] = s_conf; r[3] = s_no; r[4] = s_nr; r[5] = s_cls;
+        }
+        __syncthreads();
+        if (tid == kThreads - 1) {
+            // (an overlapped call shares nothing with the calls in front of it but must not complete before them:
+            //  the wait at the end of the kernel covers that; the accumulators are this call's own)
+            constexpr double kFix = 4294967296.0;  // 2^32
+            unsigned flags = 0u;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                float a = 0.f;
+                for (int w = 0; w < kWarps; ++w) a += red[w * 6 + q];
+                if (a >= 0.f && a < 1073741824.f) atomicAdd(p.acc + q, (unsigned long long)((double)a * kFix + 0.5));
+                else flags |= 1u << q;  // NaN / inf / out of range: the term becomes NaN, like the reference's
+            }
+            if (flags) atomicOr(p.acc + 6, (unsigned long long)flags);
+        }
+    };
+
     // Whole-image mode with at most one tile of candidates, all in shared memory: the lean path.  The
     // kernel's tail is bound by instruction issue (two CTAs per SM, and the next kernel of the stream
     // streaming next to them), so every phase is laid out for few warp instructions:
@@ -633,16 +717,20 @@ __global__ void __launch_bounds__(NTH, NTH >= 512 ? 2 : 3) yh_nms_kernel(const N
     //      resolution of the greedy order by one warp, as in the general path -- while the other warps pick
     //      label and score of every candidate (four lanes per box, without the divisions that cannot matter);
     //   E  four lanes per kept box copy the record out.
-    auto rest_img = [&](auto lab_tag) {
+    // (fused step: run by the first kTeam threads of the CTA only -- `team_tag` carries the team size, the phases then
+    //  meet on a named barrier instead of the CTA barrier -- while the other warps process the image's records)
+    auto rest_img = [&](auto lab_tag, auto team_tag) {
         constexpr bool LAB = decltype(lab_tag)::value;
+        constexpr int kThreads = decltype(team_tag)::value, kWarps = kThreads / 32;
+        auto team_sync = [&]() {
+            if (kThreads == NTH) __syncthreads();
+            else asm volatile("bar.sync 6, %0;" ::"n"(kThreads) : "memory");
+        };
         const float* win = reinterpret_cast<const float*>(smem_raw);
         Cand ca = carve(smem_raw + p.stage_bytes, kSmemCand);
         const bool use_lab = LAB && p.class_aware != 0;
-        // where the logits of a candidate are: in the staged image, or (MODE_CAND) in its row slot
-        auto box_row = [&](int k, int ik) -> const float* { return CANDM ? win + k * cstride : win + (fsh + box_off(ik)); };
-        auto cls_row = [&](int ranked) -> const float* {
-            return CANDM ? win + ca.s_slot[ranked] * cstride + 5 : win + (fsh + cls_off(ca.s_idx[ranked]));
-        };
+        auto box_row = [&](int k, int ik) -> const float* { return win + (fsh + box_off(ik)); };
+        auto cls_row = [&](int ranked) -> const float* { return win + (fsh + cls_off(ca.s_idx[ranked])); };
 
         // ---------------- B: rank + decode ----------------
         for (int kb = 0; kb < K; kb += kThreads / 2) {
@@ -685,11 +773,10 @@ __global__ void __launch_bounds__(NTH, NTH >= 512 ? 2 : 3) yh_nms_kernel(const N
                     ca.s_area[rank] = __fmul_rn(__fsub_rn(hi, lo), __fsub_rn(ohi, olo));
                     ca.s_idx[rank] = ik;
                     ca.s_conf[rank] = ck;
-                    if (CANDM) ca.s_slot[rank] = k;
                 }
             }
         }
-        __syncthreads();
+        team_sync();
         NT(4);
 
         constexpr int kPick = 4;  // lanes per class pick
@@ -722,7 +809,7 @@ __global__ void __launch_bounds__(NTH, NTH >= 512 ? 2 : 3) yh_nms_kernel(const N
         const bool picked = !with_spec && (use_lab || want_ls);  // emit finds label and score in shared memory
         if (use_lab) {
             pick_all(0, kWarps);
-            __syncthreads();
+            team_sync();
         }
 
         // ---------------- D: greedy suppression (one tile) ----------------
@@ -748,7 +835,7 @@ __global__ void __launch_bounds__(NTH, NTH >= 512 ? 2 : 3) yh_nms_kernel(const N
                 }
             }
         }
-        __syncthreads();
+        team_sync();
         NT(7);
         if (warp != 0 && picked && !use_lab) pick_all(1, kWarps - 1);
         if (warp == 0) {
@@ -805,7 +892,7 @@ __global__ void __launch_bounds__(NTH, NTH >= 512 ? 2 : 3) yh_nms_kernel(const N
             }
             if (lane == 0) s_kept = kept_n;
         }
-        __syncthreads();
+        team_sync();
         NT(8);
 
         NT(12);
@@ -863,25 +950,31 @@ __global__ void __launch_bounds__(NTH, NTH >= 512 ? 2 : 3) yh_nms_kernel(const N
         NT(13);
     };
 
-    if ((IMG && !overflow) || cand_lean) {
+    if (IMG && !overflow) {
         // the common case first, and out of the way of everything below
         // (logit, predictor) -> sort key: confidence bits in the high word (positive floats order like
         // integers), complement of the predictor index in the low word (ties: lower index first)
         for (int k = tid; k < K; k += kThreads) {
-            if (CANDM) {
-                const float* row = reinterpret_cast<const float*>(smem_raw) + k * cstride;
-                pairs[k] = make_int2(~__float_as_int(row[bs]), __float_as_int(yh_sigmoid(row[4])));
-            } else {
-                const int2 e = pairs[k];
-                pairs[k] = make_int2(~e.y, __float_as_int(yh_sigmoid(__int_as_float(e.x))));
-            }
+            const int2 e = pairs[k];
+            pairs[k] = make_int2(~e.y, __float_as_int(yh_sigmoid(__int_as_float(e.x))));
         }
         __syncthreads();
-        if (!with_labels) rest_img(FastTag<false>{});
-        else rest_img(FastTag<true>{});
+        if (TRAIN) {
+            if (warp < kTeam / 32) {
+                if (!with_labels) rest_img(FastTag<false>{}, IntTag<kTeam>{});
+                else rest_img(FastTag<true>{}, IntTag<kTeam>{});
+            } else {
+                do_records();
+            }
+            publish_sums();
+        } else {
+            if (!with_labels) rest_img(FastTag<false>{}, IntTag<NTH>{});
+            else rest_img(FastTag<true>{}, IntTag<NTH>{});
+        }
         if (p.late_wait) yh_grid_dependency_wait();  // (see the end of the kernel)
         return;
     }
+    if (TRAIN && warp >= kTeam / 32) do_records();  // (an image with more candidates than shared memory holds: records first)
 
     Cand cw = ca;
     if (overflow) {  // continue in the workspace arrays
@@ -1156,30 +1249,38 @@ __global__ void __launch_bounds__(NTH, NTH >= 512 ? 2 : 3) yh_nms_kernel(const N
     if (fast && !with_labels) rest(FastTag<true>{}, FastTag<false>{});
     else if (fast) rest(FastTag<true>{}, FastTag<true>{});
     else rest(FastTag<false>{}, FastTag<true>{});
+    if (TRAIN) publish_sums();
     // (YH_POST_INPUT_READY) everything above ran next to the tail of the previous kernel of the stream;
     // this kernel must not complete before that one has, or work launched after it could overtake it
     if (p.late_wait) yh_grid_dependency_wait();
 }
 
-template <int TV, int TA, int TC, int MODE, int NTH>
+template <int TV, int TA, int TC, int MODE, int NTH, bool TRAIN = false>
 int launch_variant(const NmsParams& p, size_t smem, void* stream) {
     static size_t configured[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) dev = 0;
     if (smem > 32 * 1024 && smem > configured[dev]) {
-        int rc = yh_check_cuda(cudaFuncSetAttribute(yh_nms_kernel<TV, TA, TC, MODE, NTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+        int rc = yh_check_cuda(cudaFuncSetAttribute(yh_nms_kernel<TV, TA, TC, MODE, NTH, TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                                "cudaFuncSetAttribute(nms)");
         if (rc) return rc;
         configured[dev] = smem;
     }
-    // (MODE_CAND: one CTA beyond the images finishes the train head's loss)
-    return yh_check_cuda(yh_launch_pdl(yh_nms_kernel<TV, TA, TC, MODE, NTH>, dim3((unsigned)p.n + (MODE == MODE_CAND ? 1u : 0u)),
+    return yh_check_cuda(yh_launch_pdl(yh_nms_kernel<TV, TA, TC, MODE, NTH, TRAIN>, dim3((unsigned)p.n),
                                        dim3(NTH), smem, (cudaStream_t)stream, p),
                          "yh_nms launch");
 }
 
-int launch(NmsParams& p, void* ws, size_t ws_bytes, void* stream, bool cand_mode = false) {
+// whole-image staging applies: the image's aligned window (<= 3 floats of shift in front, padded to 16 bytes) fits in
+// shared memory (next to a second CTA's up to ~96 KB); needs bulk copies (aligned y) and C >= 3 (then the floats past
+// the last whole 16 bytes of the tensor, which arrive by plain loads, are never an objectness logit)
+bool img_mode_applies(const NmsParams& p) {
+    const int win_bytes = ((p.img_floats + 3 + 3) & ~3) * 4;
+    return p.src == SRC_HEAD && p.use_tma && p.c >= 3 && win_bytes <= kImgBytesMax;
+}
+
+int launch(NmsParams& p, void* ws, size_t ws_bytes, void* stream, bool train = false) {
     YH_REQUIRE(p.n > 0 && p.p > 0, YH_ERR_INVALID, "n and predictors per image must be positive");
     YH_REQUIRE(p.max_out >= 0, YH_ERR_INVALID, "max_out < 0");
     YH_REQUIRE(p.keep_cnt && (p.max_out == 0 || p.keep_idx), YH_ERR_INVALID, "keep_idx / keep_cnt is NULL");
@@ -1193,25 +1294,17 @@ int launch(NmsParams& p, void* ws, size_t ws_bytes, void* stream, bool cand_mode
         p.ws = reinterpret_cast<unsigned char*>(ws);
         p.ws_per_image = cand_bytes(p.p);
     }
-    if (cand_mode) {
-        // shared memory: kSmemCand row slots for the lists' entries, then the candidate arrays; an image that
-        // falls back to the head tensor stages nothing (its rows are read from global memory)
-        p.stage_slots = 0;
-        p.stage_bytes = kSmemCand * p.cand.stride * 4;
-        const size_t smem = (size_t)p.stage_bytes + cand_bytes(kSmemCand);
-        if (p.g.a == 5 && p.c == 20) return launch_variant<2, 5, 20, MODE_CAND, kThreadsCand>(p, smem, stream);
-        return launch_variant<2, 0, 0, MODE_CAND, kThreadsCand>(p, smem, stream);
-    }
-    // whole-image staging: the image's aligned window (<= 3 floats of shift in front, padded to 16 bytes)
-    // fits next to a second CTA's; needs bulk copies (aligned y) and C >= 3 (then the floats past the last
-    // whole 16 bytes of the tensor, which arrive by plain loads, are never an objectness logit)
     const int win_bytes = ((p.img_floats + 3 + 3) & ~3) * 4;
-    const bool img_mode = p.src == SRC_HEAD && p.use_tma && p.c >= 3 && win_bytes <= kImgBytesMax;
+    const bool img_mode = img_mode_applies(p);
     p.stage_bytes = img_mode ? win_bytes : p.stage_slots * p.slot_floats * 4;
     const size_t smem = (size_t)p.stage_bytes + cand_bytes(kSmemCand);
     // compile-time geometries for the shapes the reference uses (VOC: YOLOv2 5 anchors x 20 classes,
     // YOLOv1 B=2, C=20); anything else, and decoded-box input, runs the run-time-geometry variant
     constexpr int NTF = kThreadsFull;
+    if (train) {  // the fused step (the caller checked img_mode_applies and version 2)
+        if (p.g.a == 5 && p.c == 20) return launch_variant<2, 5, 20, MODE_IMG, NTF, true>(p, smem, stream);
+        return launch_variant<2, 0, 0, MODE_IMG, NTF, true>(p, smem, stream);
+    }
     if (img_mode) {
         if (p.g.version == 2 && p.g.a == 5 && p.c == 20) return launch_variant<2, 5, 20, MODE_IMG, NTF>(p, smem, stream);
         if (p.g.version == 1 && p.g.a == 2 && p.c == 20) return launch_variant<1, 2, 20, MODE_IMG, NTF>(p, smem, stream);
@@ -1269,30 +1362,6 @@ int postprocess_impl(int version, const float* y, int n, int s_h, int s_w, int a
     return launch(p, ws, ws_bytes, stream);
 }
 
-// layout of the fused step's workspace: [train sums 256 B | tile counts | candidate rows | general post-process workspace]
-struct StepLayout {
-    int tile_cells, num_tiles, grid, stride;
-    size_t off_cnt, off_rows, off_post, total;
-    bool fusable;  // the tiles touch at most two images (the candidate lists have two sides)
-};
-int step_layout(StepLayout* L, int n, int s_h, int s_w, int a, int c) {
-    const long long cells = (long long)s_h * s_w;
-    const int cf = a * (5 + c);
-    int rc = yh_train_tiling((long long)n * cells, cf, &L->tile_cells, &L->num_tiles, &L->grid);
-    if (rc) {
-        yh_set_error("cell too wide for the shared-memory stage (%d floats per cell)", cf);
-        return rc;
-    }
-    L->stride = (5 + c + 1 + 3) & ~3;
-    L->fusable = L->tile_cells <= cells;
-    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    L->off_cnt = up(yh_train_workspace_bytes());
-    L->off_rows = up(L->off_cnt + (size_t)L->num_tiles * sizeof(int2));
-    L->off_post = up(L->off_rows + (size_t)L->num_tiles * 2 * kYhCandCap * L->stride * 4);
-    L->total = up(L->off_post + yh_postprocess_workspace_bytes(n, (int)(cells * a)));
-    return YH_OK;
-}
-
 }  // namespace
 
 void yh_conf_band(float conf_thre, float* to_reject, float* to_accept) {
@@ -1316,9 +1385,8 @@ void yh_conf_band(float conf_thre, float* to_reject, float* to_accept) {
 extern "C" {
 
 size_t yh_train_post_workspace_bytes(int n, int s_h, int s_w, int a, int c) {
-    StepLayout L;
-    if (n <= 0 || s_h <= 0 || s_w <= 0 || a <= 0 || c <= 0 || step_layout(&L, n, s_h, s_w, a, c)) return 0;
-    return L.total;
+    if (n <= 0 || s_h <= 0 || s_w <= 0 || a <= 0 || c <= 0) return 0;
+    return 256 + yh_postprocess_workspace_bytes(n, s_h * s_w * a);  // [loss sums | post-process workspace]
 }
 
 int yh_v2_train_post(const float* y, int n, int s_h, int s_w, int a, int c, const float* anchors_wh_host,
@@ -1328,46 +1396,49 @@ int yh_v2_train_post(const float* y, int n, int s_h, int s_w, int a, int c, cons
                      float* out_bbox, float* out_conf, float* out_cls_spec, int32_t* out_label, float* out_score,
                      const YhExchange* xch_host, void* ws, size_t ws_bytes, void* stream) {
     YH_REQUIRE(n > 0 && s_h > 0 && s_w > 0 && a > 0 && c > 0, YH_ERR_INVALID, "n, grid, anchors and classes must be positive");
-    StepLayout L;
-    int rc = step_layout(&L, n, s_h, s_w, a, c);
-    if (rc) return rc;
-    YH_REQUIRE(ws && ws_bytes >= L.total, YH_ERR_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, L.total);
+    const size_t need = yh_train_post_workspace_bytes(n, s_h, s_w, a, c);
+    YH_REQUIRE(ws && ws_bytes >= need, YH_ERR_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, need);
     YH_REQUIRE(((uintptr_t)ws & 255) == 0, YH_ERR_INVALID, "workspace must be 256-byte aligned");
     unsigned char* base = reinterpret_cast<unsigned char*>(ws);
     const int overlapped = (flags & YH_STEP_OVERLAPPED) ? 1 : 0;
-    const int post_flags = (flags & YH_STEP_CLASS_AWARE) ? YH_POST_CLASS_AWARE : 0;
-    const bool aligned = ((uintptr_t)y & 15) == 0 && ((uintptr_t)dy & 15) == 0;
-    if (!(L.fusable && aligned)) {
-        // not covered by the fused form: the two kernels of the separate calls, same results
-        rc = yh_train_impl(2, y, n, s_h, s_w, a, c, anchors_wh_host, img_h, img_w, gt, gt_off, m_local, m_global,
-                           lambdas_host, dy, terms, loss, resp, iou_resp, base, yh_train_workspace_bytes(), stream,
-                           overlapped, xch_host, nullptr, nullptr);
-        if (rc) return rc;
-        return postprocess_impl(2, y, n, s_h, s_w, a, c, anchors_wh_host, img_h, img_w, conf_thre, iou_thre,
-                                post_flags | (overlapped ? YH_POST_INPUT_READY : 0), max_out, keep_idx, keep_cnt, out_bbox,
-                                out_conf, out_cls_spec, out_label, out_score, base + L.off_post, L.total - L.off_post, stream);
-    }
-    NmsParams p;  // (validated before anything is launched)
-    rc = fill_head_params(p, 2, y, n, s_h, s_w, a, c, anchors_wh_host, img_h, img_w, conf_thre, iou_thre, post_flags, max_out,
-                          keep_idx, keep_cnt, out_bbox, out_conf, out_cls_spec, out_label, out_score);
+    const int post_flags = ((flags & YH_STEP_CLASS_AWARE) ? YH_POST_CLASS_AWARE : 0) | (overlapped ? YH_POST_INPUT_READY : 0);
+    NmsParams p;
+    int rc = fill_head_params(p, 2, y, n, s_h, s_w, a, c, anchors_wh_host, img_h, img_w, conf_thre, iou_thre, post_flags, max_out,
+                              keep_idx, keep_cnt, out_bbox, out_conf, out_cls_spec, out_label, out_score);
     if (rc) return rc;
-    YH_REQUIRE(keep_cnt && (max_out == 0 || keep_idx) && max_out >= 0, YH_ERR_INVALID, "keep_idx / keep_cnt is NULL or max_out < 0");
-    YH_REQUIRE(((uintptr_t)out_bbox & 15) == 0, YH_ERR_INVALID, "out_bbox must be 16-byte aligned");
-    YhCandBuf cb;
-    cb.rows = reinterpret_cast<float*>(base + L.off_rows);
-    cb.tile_cnt = reinterpret_cast<int2*>(base + L.off_cnt);
-    cb.stride = L.stride;
-    cb.tile_cells = L.tile_cells;
-    cb.num_tiles = L.num_tiles;
-    cb.to_reject = p.to_reject; cb.to_accept = p.to_accept; cb.conf_thre = conf_thre;
-    const bool no_post = (flags & YH_STEP_NO_POST) != 0;
-    rc = yh_train_impl(2, y, n, s_h, s_w, a, c, anchors_wh_host, img_h, img_w, gt, gt_off, m_local, m_global,
-                       lambdas_host, dy, terms, loss, resp, iou_resp, base, yh_train_workspace_bytes(), stream,
-                       overlapped, xch_host, &cb, no_post ? nullptr : &p.fin);
-    if (rc || no_post) return rc;
-    p.cand = cb;
-    p.late_wait = 0;
-    return launch(p, base + L.off_post, L.total - L.off_post, stream, true);
+    const bool fusable = img_mode_applies(p) && ((uintptr_t)dy & 15) == 0 && 5 * a <= 32 && p.g.preds >= 2;
+    if (!fusable) {
+        // inputs the fused kernel does not cover (unaligned tensors, images beyond the shared-memory stage): the
+        // kernels of the two separate calls, same results
+        rc = yh_train_impl(2, y, n, s_h, s_w, a, c, anchors_wh_host, img_h, img_w, gt, gt_off, m_local, m_global,
+                           lambdas_host, dy, terms, loss, resp, iou_resp, base, 256, stream, overlapped, xch_host);
+        if (rc) return rc;
+        return launch(p, base + 256, ws_bytes - 256, stream);
+    }
+    YH_REQUIRE(gt_off && terms && loss && lambdas_host, YH_ERR_INVALID, "null pointer argument");
+    YH_REQUIRE(m_local >= 0 && (m_local == 0 || gt), YH_ERR_INVALID, "bad ground-truth arguments");
+    YH_REQUIRE(m_global > 0, YH_ERR_EMPTY, "no ground-truth boxes in the batch (m_global=%d)", m_global);
+    YH_REQUIRE(m_local <= m_global, YH_ERR_INVALID, "m_local > m_global");
+    YH_REQUIRE(((uintptr_t)gt & 15) == 0, YH_ERR_INVALID, "gt must be 16-byte aligned");
+    YhLossCoef kc;
+    YhFinalParams f;
+    yh_loss_coefs(lambdas_host, m_global, p.g.preds, &kc, &f);
+    f.acc = reinterpret_cast<unsigned long long*>(base);
+    f.terms = terms;
+    f.loss = loss;
+    rc = yh_fill_exchange(&f, xch_host);
+    if (rc) return rc;
+    p.dy = dy; p.gt = gt; p.gt_off = gt_off; p.m_local = m_local;
+    p.acc = f.acc;
+    p.cxy = kc.cxy; p.cwh = kc.cwh; p.cconf = kc.cconf; p.cno = kc.cno; p.ccls = kc.ccls;
+    p.resp = resp; p.iou_resp = iou_resp;
+    rc = launch(p, base + 256, ws_bytes - 256, stream, true);
+    if (rc) return rc;
+    if (getenv("YH_DEBUG_SYNC")) {  // (debugging aid: attribute a device fault to the fused kernel; never set under capture)
+        rc = yh_check_cuda(cudaStreamSynchronize((cudaStream_t)stream), "fused kernel (debug sync)");
+        if (rc) return rc;
+    }
+    return yh_launch_finalize(f, (cudaStream_t)stream);
 }
 
 size_t yh_postprocess_workspace_bytes(int n, int preds_per_image) {

@@ -43,6 +43,7 @@
 
 #include "yh_common.cuh"
 #include "yh_finalize.cuh"
+#include "yh_record.cuh"
 
 namespace {
 
@@ -67,7 +68,6 @@ constexpr int kChunks = YH_X_CHUNKS;      // TMA chunks (mbarriers) per tile
 constexpr int kAhead = YH_X_AHEAD;        // chunks in flight per CTA
 constexpr int kTileBytesMax = (kCtasPerSm >= 4 ? 40 : (kCtasPerSm == 3 ? 52 : 80)) * 1024;  // shared-memory stage of one tile
 constexpr int kMaxGrid = 2048;
-constexpr int kClsRegs = 4;               // class logits per lane kept in registers (C <= 128)
 constexpr int kWindow = 128;              // speculative record window (records) per tile
 constexpr int kWindowMax = 256;           // record window buffer: an exact window after a miss may be this long
 #ifndef YH_X_SLOTS
@@ -123,19 +123,7 @@ struct TrainParams {
     float lam[5];
     double inv_den[5];    // 1/(2M), 1/(2M), 1/M, 1/(M(P-1)), 1/M
     float cxy, cwh, cconf, cno, ccls;  // gradient coefficients (see train_impl)
-    YhCandBuf cand;       // fused step (CAND kernels): where the dense pass lists the predictors with conf >= conf_thre
 };
-
-struct WarpSums {
-    float no, xy, wh, conf, nr, cls;
-};
-
-// order-preserving float <-> int map (for redux.sync max on floats; NaNs are not ordered)
-__device__ __forceinline__ int yh_ordered(float f) {
-    const int i = __float_as_int(f);
-    return i ^ ((i >> 31) & 0x7fffffff);
-}
-__device__ __forceinline__ float yh_unordered(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
 
 template <bool VEC>
 __device__ __forceinline__ float4 load4(const float* base, int idx4) {
@@ -166,207 +154,10 @@ __device__ __forceinline__ void put4(float4& v, int j, float x) {
     if (j == 0) v.x = x; else if (j == 1) v.y = x; else if (j == 2) v.z = x; else v.w = x;
 }
 
-// No-object part of one objectness logit `t` in an image with `kn` boxes: the term kn * conf^2 and
-// its gradient cno * kn * conf^2 * (1 - conf).  Approximate sigmoid (no decision depends on it) and
-// explicitly rounded steps: the dense pass and the record warp must produce identical bits.
-__device__ __forceinline__ float noobj_term(float t, float kn, float* conf_out) {
-    // (two SFU operations: ex2.approx and rcp.approx handle +-inf, 0 and NaN the way the sigmoid needs them, and
-    // the range fix-ups __expf / __fdividef wrap around them were a quarter of the dense pass' instructions)
-    float e, conf;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__fmul_rn(t, -1.4426950408889634f)));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(conf) : "f"(__fadd_rn(1.0f, e)));
-    *conf_out = conf;
-    return __fmul_rn(__fmul_rn(kn, conf), conf);
-}
-__device__ __forceinline__ float noobj_grad(float w, float conf, float cno) {
-    return __fmul_rn(__fmul_rn(cno, w), __fsub_rn(1.0f, conf));
-}
-
-struct RecordRegs {
-    int4 hd;    // img, cy, cx, cls
-    float4 tt;  // stx, sty, tw, th
-    float4 bb;  // x1, y1, x2, y2
-};
-
-// One ground-truth record against its cell; all 32 lanes cooperate and the work is laid out for
-// LATENCY (records are the epilogue of a tile):
-//   * lane l < 5A owns ONE activation (anchor l/5, channel l%5), so the 5A exp/sigmoid chains run
-//     side by side; four shuffles hand every lane its anchor's box, the IoU is formed, and two
-//     redux.sync steps pick the responsible anchor (max IoU, then lowest index: torch's first max);
-//   * as soon as the anchor is known every lane issues its loads of the class logits and of the
-//     dL/dy values it will update, so their latency hides behind the channel arithmetic;
-//   * the five lanes of the responsible anchor each finish THEIR channel (x, y, w, h, conf:
-//     target transform, squared error, gradient) in parallel; their squared errors accumulate in
-//     per-lane registers by channel role;
-//   * class softmax: lanes stride the classes, max through redux.sync on an order-preserving
-//     integer image, then ONE butterfly for (sum e, sum e^2): with p = e / sum e,
-//       sum_c (p_c - 1[c=t])^2 = S2 - 2 p_t + 1   and   sum_c (p_c - 1[c=t]) p_c = S2 - p_t,
-//     S2 = sum p^2, so no third reduction is needed.
-// `ycell` points at the cell's floats of y (in the shared-memory tile), `dcell` at the cell's
-// floats of dy (global memory; holds the dense pass' values, visible after the CTA barrier);
-// `kn` is the box count of the cell's image; `my_pw/my_ph` are the anchor multipliers of this
-// lane's anchor (lane / 5).  Requires 5A <= 32.
-// MODE 0: loss only; 1: add the gradient onto dy in global memory (`again`: an earlier record
-// already updated this cell, so the row is read back; otherwise it holds the dense pass' values,
-// which are known without a load: zero but the objectness channel); 2: leave the gradient in the
-// shared-memory patch row `patch` (+ the dense objectness value of the row in *pdense), to be
-// applied after the dense pass.
-template <int MODE>
-__device__ __forceinline__ int process_record(const TrainParams& p, const int version, const int A, const int C,
-                                              const RecordRegs& rr, int jj, const float* ycell,
-                                              float* dcell, bool again, float* patch, float* pdense, float kn,
-                                              int lane, float my_pw, float my_ph, WarpSums& s) {
-    const YhGeom& g = p.g;
-    const int bs = version == 2 ? 5 + C : 5;
-    const int4 hd = rr.hd;
-    const float4 tt = rr.tt;
-    const float4 bb = rr.bb;
-
-    const int a = lane / 5, q = lane - 5 * a;
-    const bool mine = lane < 5 * A;
-    float act = 0.f, t_raw = 0.f;
-    if (mine) {
-        const float t = ycell[a * bs + q];
-        t_raw = t;
-        const bool is_exp = version == 2 && (q == 2 || q == 3);
-        const float e = expf(is_exp ? t : -t);
-        act = is_exp ? e : __fdiv_rn(1.0f, __fadd_rn(1.0f, e));
-    }
-    const int l0 = mine ? 5 * a : 0;
-    const float bx_s = __shfl_sync(0xffffffffu, act, l0);
-    const float by_s = __shfl_sync(0xffffffffu, act, l0 + 1);
-    const float bw_a = __shfl_sync(0xffffffffu, act, l0 + 2);
-    const float bh_a = __shfl_sync(0xffffffffu, act, l0 + 3);
-    int key = INT_MIN;  // order-preserving image of this lane's IoU; NaN (as torch) ranks highest
-    float iou = 0.f;
-    if (mine) {
-        const YhBox pb = yh_decode_box(bx_s, by_s, bw_a, bh_a, my_pw, my_ph, hd.z, hd.y, g.gw, g.gh);
-        const YhBox gb{bb.x, bb.y, bb.z, bb.w};
-        iou = yh_iou_xyxy(pb, gb);
-        key = iou != iou ? INT_MAX : yh_ordered(iou);
-    }
-    const int best = __reduce_max_sync(0xffffffffu, key);
-    const int r = __reduce_min_sync(0xffffffffu, (mine && key == best) ? a : 1 << 20);  // first max
-
-    // loads that depend on r go out now: class logits (and, MODE 1, the dL/dy values to be updated)
-    const int coff = version == 2 ? r * bs + 5 : 5 * A;
-    const float* cl = ycell + coff;
-    float* dcl = dcell + coff;
-    const bool resp_lane = mine && a == r;
-    float old_ch = 0.f;
-    if (MODE == 1 && resp_lane) {
-        if (again) {
-            old_ch = dcell[r * bs + q];
-        } else if (q == 4) {  // what the dense pass wrote for this logit (same helper, same bits)
-            float cf_;
-            const float w = noobj_term(t_raw, kn, &cf_);
-            old_ch = noobj_grad(w, cf_, p.cno);
-        }
-    }
-    float lg[kClsRegs], oldc[kClsRegs];
-#pragma unroll
-    for (int k = 0; k < kClsRegs; ++k) {
-        const int c = lane + 32 * k;
-        lg[k] = c < C ? cl[c] : -INFINITY;
-        oldc[k] = (MODE == 1 && again && c < C) ? dcl[c] : 0.f;
-    }
-    const float iou_r = __shfl_sync(0xffffffffu, iou, 5 * r);
-
-    // the five lanes of the responsible anchor finish one channel each
-    if (resp_lane) {
-        float d, grad;
-        if (q < 2) {            // x, y: (sigmoid(t) - target)^2, models/yolov2.py:1046-1050
-            d = act - (q == 0 ? tt.x : tt.y);
-            grad = p.cxy * d * act * (1.f - act);
-            s.xy += d * d;
-        } else if (q < 4) {     // w, h: (sqrt(act) - sqrt(target))^2, models/yolov2.py:946-947, 1063-1067
-            const float t = q == 2 ? tt.z : tt.w;
-            const float tgt = version == 2 ? __fsqrt_rn(__fdiv_rn(t, q == 2 ? my_pw : my_ph)) : __fsqrt_rn(t);
-            const float qv = __fsqrt_rn(act);
-            d = qv - tgt;
-            grad = p.cwh * d * qv;
-            if (version != 2) grad *= 1.f - act;  // v1: d sqrt(sigmoid(t)) / dt, models/yolov1.py:745-761
-            s.wh += d * d;
-        } else {                // objectness: (iou - conf)^2 and the no-object correction
-            d = act - iou_r;
-            grad = (p.cconf * d - p.cno * act) * act * (1.f - act);
-            s.conf += d * d;
-            s.nr += act * act;
-            if (p.resp) p.resp[jj] = r;
-            if (p.iou_resp) p.iou_resp[jj] = iou_r;
-            if (MODE == 2) {  // what the dense pass writes for this logit
-                float cf_;
-                const float w = noobj_term(t_raw, kn, &cf_);
-                *pdense = noobj_grad(w, cf_, p.cno);
-            }
-        }
-        if (MODE == 1) dcell[r * bs + q] = __fadd_rn(old_ch, grad);  // (explicit add: MODE 1 and 2 must round alike)
-        if (MODE == 2) patch[q] = grad;
-    }
-
-    // class term
-    float mx = -INFINITY;
-#pragma unroll
-    for (int k = 0; k < kClsRegs; ++k) mx = fmaxf(mx, lg[k]);
-    for (int c = lane + 32 * kClsRegs; c < C; c += 32) mx = fmaxf(mx, cl[c]);
-    mx = yh_unordered(__reduce_max_sync(0xffffffffu, yh_ordered(mx)));
-    float s1 = 0.f, s2 = 0.f, et = 0.f;  // sum e, sum e^2, e of the target class (owning lane only)
-#pragma unroll
-    for (int k = 0; k < kClsRegs; ++k) {
-        const int c = lane + 32 * k;
-        lg[k] = c < C ? expf(lg[k] - mx) : 0.f;
-        s1 += lg[k];
-        s2 += lg[k] * lg[k];
-        if (c == hd.w) et = lg[k];
-    }
-    for (int c = lane + 32 * kClsRegs; c < C; c += 32) {
-        const float e = expf(cl[c] - mx);
-        s1 += e;
-        s2 += e * e;
-        if (c == hd.w) et = e;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-    }
-    const bool has_t = hd.w >= 0 && hd.w < C;
-    et = __shfl_sync(0xffffffffu, et, has_t ? (hd.w & 31) : 0);
-    const float inv = __fdiv_rn(1.0f, s1);
-    const float S2 = s2 * inv * inv;
-    const float pt = has_t ? et * inv : 0.f;
-    const float dot = S2 - pt;
-    if (lane == 0) s.cls += S2 - 2.f * pt + (has_t ? 1.f : 0.f);
-    if (MODE == 1) {
-#pragma unroll
-        for (int k = 0; k < kClsRegs; ++k) {
-            const int c = lane + 32 * k;
-            if (c < C) {
-                const float pc = lg[k] * inv;
-                dcl[c] = __fadd_rn(oldc[k], p.ccls * pc * (pc - (c == hd.w ? 1.f : 0.f) - dot));
-            }
-        }
-        for (int c = lane + 32 * kClsRegs; c < C; c += 32) {
-            const float pc = expf(cl[c] - mx) * inv;
-            dcl[c] = __fadd_rn(again ? dcl[c] : 0.f, p.ccls * pc * (pc - (c == hd.w ? 1.f : 0.f) - dot));
-        }
-    }
-    if (MODE == 2 && lane < C) {  // 5 + C <= kPatchFloats: one class per lane
-        const float pc = lg[0] * inv;
-        patch[5 + lane] = p.ccls * pc * (pc - (lane == hd.w ? 1.f : 0.f) - dot);
-    }
-    __syncwarp();
-    return r;
-}
-
 // TV/TA/TC != 0 fix version / boxes per cell / classes at compile time (index arithmetic folds,
 // divisions become multiplies); 0 keeps them as run-time values from the geometry.
 // VEC: y and dy are 16-byte aligned (float4 accesses); otherwise the same code with scalar accesses.
-// CAND (fused step, yh_v2_train_post; v2, tiles of at most two images): the dense pass also lists the predictors
-// whose confidence reaches conf_thre -- decided on the logit it holds anyway, the sigmoid only inside a narrow band
-// around logit(conf_thre) -- and after the tile barrier their rows are copied from the shared-memory tile to the
-// tile's candidate lists in the workspace, which is all the post-process of the same step reads.
-template <bool WRITE_DY, bool VEC, int TV, int TA, int TC, bool CAND>
+template <bool WRITE_DY, bool VEC, int TV, int TA, int TC>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const TrainParams p) {
     extern __shared__ __align__(128) float s_tile[];  // the tile's slice of y
     __shared__ __align__(16) int4 s_win[3 * kWindowMax];  // window of ground-truth records (speculative, or exact after a miss)
@@ -383,8 +174,6 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
     __shared__ int s_ncell;           // records of the list with a private cell copy
     __shared__ int s_collide;         // bit i: patch i shares its cell with another patch (applied in order)
     __shared__ int s_ready;           // tile index + 1 once the record list of that tile is published
-    __shared__ int s_cand[CAND ? 2 * kYhCandCap : 2];  // CAND: tile-local float offsets of the candidates' rows, per image of the tile
-    __shared__ int s_ccnt[2];                          // ... and how many (may exceed kYhCandCap: the list is then incomplete)
 
     const YhGeom& g = p.g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -404,8 +193,6 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
         for (int c = 0; c <= kChunks + 2; ++c) yh_mbar_init(&s_bar[c], 1);
         yh_mbar_fence_init();
         s_ready = 0;
-        s_ccnt[0] = 0;
-        s_ccnt[1] = 0;
     }
     // everything above overlaps the tail of the previous kernel of the stream (programmatic dependent
     // launch); nothing below may run before that kernel has completed: it may have produced y, and it
@@ -530,10 +317,6 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
             // TMA producer: the window first (everything the record warp does hangs on it), then the
             // first chunks of the tile
             yh_fence_proxy_async();  // (multi-tile: the stage was read through the generic proxy)
-            if (CAND && t != (int)blockIdx.x) {  // (ordered before the streaming warps' first hit by chunk 0's mbarrier)
-                s_ccnt[0] = 0;
-                s_ccnt[1] = 0;
-            }
             if (wn > 0) {
                 yh_mbar_expect_tx(&s_bar[kChunks], (uint32_t)wn * 48u);
                 yh_bulk_load(s_win, p.gt + w0, (uint32_t)wn * 48u, &s_bar[kChunks]);
@@ -643,15 +426,6 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
             return true;
         };
 
-        // CAND: objectness logit `tl` of the predictor whose row starts at tile-local float `row0` reaches the threshold?
-        // (rare: ~6 % of the predictors at the reference's settings; same rule as the post-process kernel's phase A)
-        auto cand_hit = [&](float tl, int row0) {
-            if (tl >= p.cand.to_accept || yh_sigmoid(tl) >= p.cand.conf_thre) {
-                const int side = row0 < thr0 ? 0 : 1;
-                const int slot = atomicAdd(&s_ccnt[side], 1);
-                if (slot < kYhCandCap) s_cand[side * kYhCandCap + slot] = row0;
-            }
-        };
         if (!record_warp) {
             // ================= streaming warps: the dense pass =================
             const float4* tile4 = reinterpret_cast<const float4*>(s_tile);
@@ -674,7 +448,6 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
                         tl = m == 2 ? v.z : tl;
                         tl = m == 3 ? v.y : tl;
                         tl = m == 4 ? v.x : tl;
-                        if (CAND && has && tl >= p.cand.to_reject) cand_hit(tl, lf - m);
                         float conf;
                         float w = noobj_term(tl, (lf + 4 - m) < thr0 ? kn0 : kn1, &conf);
                         w = has ? w : 0.f;
@@ -702,7 +475,6 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
                         tl = m == 2 ? v.z : tl;
                         tl = m == 3 ? v.y : tl;
                         tl = m == 4 ? v.x : tl;
-                        if (CAND && has && tl >= p.cand.to_reject) cand_hit(tl, lf - m);
                         float conf;
                         float w = noobj_term(tl, kn_of(lf + 4 - m), &conf);
                         w = has ? w : 0.f;
@@ -738,7 +510,6 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
                 const bool is_to = version == 2 ? (pc % bs == 4) : (pc < 5 * A && pc % 5 == 4);
                 float o = 0.f;
                 if (is_to) {
-                    if (CAND && s_tile[lf] >= p.cand.to_reject) cand_hit(s_tile[lf], lf - 4);
                     float conf;
                     const float w = noobj_term(s_tile[lf], kn_of(lf), &conf);
                     sums.no += w;
@@ -851,26 +622,6 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
         XT(1);
         __syncthreads();  // the tile's dense dL/dy is written (and visible to the whole CTA); patches are ready
         XT(2);
-        if (CAND) {
-            // the tile's candidate rows -> its two lists in the workspace (the tile is still in shared memory);
-            // entry = [5 + C logits | predictor index inside its image]
-            const int cn0 = s_ccnt[0], cn1 = s_ccnt[1];
-            if (tid == 0) p.cand.tile_cnt[t] = make_int2(cn0, cn1);
-            const int k0 = min(cn0, kYhCandCap), k1 = min(cn1, kYhCandCap);
-            float* region = p.cand.rows + (size_t)t * (2 * kYhCandCap) * p.cand.stride;
-            for (int i = warp; i < k0 + k1; i += kWarps) {
-                const int side = i >= k0 ? 1 : 0, j = side ? i - k0 : i;
-                const int row0 = s_cand[side * kYhCandCap + j];
-                float* dst = region + (size_t)(side * kYhCandCap + j) * p.cand.stride;
-                for (int q = lane; q < bs; q += 32) dst[q] = s_tile[row0 + q];
-                if (lane == 0) {
-                    const int lcell = row0 / cf;
-                    const int an = (row0 - lcell * cf) / bs;
-                    const int gcell = c0 + lcell;
-                    dst[bs] = __int_as_float((gcell - (gcell / cells) * cells) * A + an);
-                }
-            }
-        }
         const int nrec = s_nrec, npatch = s_npatch;
         // (no records left over: the sums folded before the barrier are final and get published
         //  right after the patch stores, without another CTA barrier)
@@ -998,15 +749,8 @@ __global__ void __launch_bounds__(32) yh_train_finalize_kernel(const YhFinalPara
     yh_finalize_warp(f, (int)threadIdx.x);
 }
 
-int launch_finalize(const YhFinalParams& f, cudaStream_t stream) {
-#ifdef YH_X_ONE_KERNEL
-    return 0;
-#else
-    return yh_check_cuda(yh_launch_pdl(yh_train_finalize_kernel, dim3(1), dim3(32), 0, stream, f), "yh_train_finalize launch");
-#endif
-}
 
-template <bool WDY, bool VEC, int TV, int TA, int TC, bool CAND>
+template <bool WDY, bool VEC, int TV, int TA, int TC>
 int launch_variant(const TrainParams& p, int grid, cudaStream_t stream) {
     const size_t smem = (((size_t)p.tile_cells * p.g.cell_floats + 3) & ~(size_t)3) * 4 + 16 +
                         (size_t)p.cell_slots * p.cell_slot_floats * 4;
@@ -1015,13 +759,13 @@ int launch_variant(const TrainParams& p, int grid, cudaStream_t stream) {
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) dev = 0;
     if (smem > configured[dev]) {
-        int rc = yh_check_cuda(cudaFuncSetAttribute(yh_train_kernel<WDY, VEC, TV, TA, TC, CAND>,
+        int rc = yh_check_cuda(cudaFuncSetAttribute(yh_train_kernel<WDY, VEC, TV, TA, TC>,
                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                                "cudaFuncSetAttribute(train)");
         if (rc) return rc;
         configured[dev] = smem;
     }
-    return yh_check_cuda(yh_launch_pdl(yh_train_kernel<WDY, VEC, TV, TA, TC, CAND>, dim3(grid), dim3(kThreads), smem, stream, p),
+    return yh_check_cuda(yh_launch_pdl(yh_train_kernel<WDY, VEC, TV, TA, TC>, dim3(grid), dim3(kThreads), smem, stream, p),
                          "yh_train launch");
 }
 
@@ -1031,17 +775,9 @@ int launch_geometry(const TrainParams& p, int grid, cudaStream_t stream) {
     // compile-time geometries for the shapes the reference trains: YOLOv2 5 anchors x 20 classes
     // (VOC, models/yolov2.py:49-70) and YOLOv1 B=2, C=20 (config.py:7-11); anything else runs the
     // same kernel with run-time geometry
-    if (g.version == 2 && g.a == 5 && g.c == 20) return launch_variant<WDY, VEC, 2, 5, 20, false>(p, grid, stream);
-    if (g.version == 1 && g.a == 2 && g.c == 20) return launch_variant<WDY, VEC, 1, 2, 20, false>(p, grid, stream);
-    return launch_variant<WDY, VEC, 0, 0, 0, false>(p, grid, stream);
-}
-
-// the candidate-listing variants of the fused step (v2, aligned tensors only)
-template <bool WDY>
-int launch_geometry_cand(const TrainParams& p, int grid, cudaStream_t stream) {
-    const YhGeom& g = p.g;
-    if (g.a == 5 && g.c == 20) return launch_variant<WDY, true, 2, 5, 20, true>(p, grid, stream);
-    return launch_variant<WDY, true, 2, 0, 0, true>(p, grid, stream);
+    if (g.version == 2 && g.a == 5 && g.c == 20) return launch_variant<WDY, VEC, 2, 5, 20>(p, grid, stream);
+    if (g.version == 1 && g.a == 2 && g.c == 20) return launch_variant<WDY, VEC, 1, 2, 20>(p, grid, stream);
+    return launch_variant<WDY, VEC, 0, 0, 0>(p, grid, stream);
 }
 
 void tiling(long long total_cells, int cf, int* tile_cells, int* num_tiles, int* grid) {
@@ -1070,6 +806,33 @@ int yh_train_tiling(long long total_cells, int cell_floats, int* tile_cells, int
     return YH_OK;
 }
 
+int yh_launch_finalize(const YhFinalParams& f, cudaStream_t stream) {
+#ifdef YH_X_ONE_KERNEL
+    return 0;
+#else
+    return yh_check_cuda(yh_launch_pdl(yh_train_finalize_kernel, dim3(1), dim3(32), 0, stream, f), "yh_train_finalize launch");
+#endif
+}
+
+// Loss normalisation shared by the train head and the fused step: denominators of the five means and the
+// gradient coefficients.  d(mean)/d(activation):  xy: 2(s-t)/(2M);  wh: 2(q-T)/(2M) * dq/dt with dq/dt = q/2;
+// conf: 2(conf-iou)/M;  noobj: 2 conf /(M(P-1));  cls: 2/M
+void yh_loss_coefs(const float* lambdas_host, int m_global, int preds, YhLossCoef* k, YhFinalParams* f) {
+    const double M = (double)m_global;
+    const double P1 = (double)preds - 1.0;
+    k->cxy = (float)(lambdas_host[0] / M);
+    k->cwh = (float)(lambdas_host[1] / (2.0 * M));
+    k->cconf = (float)(lambdas_host[2] * 2.0 / M);
+    k->cno = (float)(lambdas_host[3] * 2.0 / (M * P1));
+    k->ccls = (float)(lambdas_host[4] * 2.0 / M);
+    for (int i = 0; i < 5; ++i) f->lam[i] = lambdas_host[i];
+    f->inv_den[0] = 1.0 / (2.0 * M);
+    f->inv_den[1] = 1.0 / (2.0 * M);
+    f->inv_den[2] = 1.0 / M;
+    f->inv_den[3] = 1.0 / (M * P1);
+    f->inv_den[4] = 1.0 / M;
+}
+
 int yh_fill_exchange(YhFinalParams* f, const YhExchange* xch_host) {
     f->rank = 0;
     f->world = 1;
@@ -1087,15 +850,12 @@ int yh_fill_exchange(YhFinalParams* f, const YhExchange* xch_host) {
     return YH_OK;
 }
 
-// The train head of every entry point.  `cand` != NULL (fused step): the CAND kernel, candidate lists into *cand;
-// the caller checked that the fused form applies.  `fin_out` != NULL: the finalize step is left to the caller
-// (its parameters go to *fin_out), otherwise the one-warp finalize kernel is launched behind the train kernel.
+// The train head of every train entry point: the train kernel and, right behind it, the one-warp finalize kernel.
 int yh_train_impl(int version, const float* y, int n, int s_h, int s_w, int a, int c,
                   const float* anchors_wh_host, float img_h, float img_w, const YhGt* gt,
                   const int32_t* gt_off, int m_local, int m_global, const float* lambdas_host,
                   float* dy, float* terms, float* loss, int32_t* resp, float* iou_resp, void* ws,
-                  size_t ws_bytes, void* stream, int late_wait, const YhExchange* xch_host,
-                  const YhCandBuf* cand, YhFinalParams* fin_out) {
+                  size_t ws_bytes, void* stream, int late_wait, const YhExchange* xch_host) {
     TrainParams p;
     int rc = yh_make_geom(&p.g, version, n, s_h, s_w, a, c, anchors_wh_host, img_h, img_w);
     if (rc) return rc;
@@ -1122,21 +882,11 @@ int yh_train_impl(int version, const float* y, int n, int s_h, int s_w, int a, i
     p.late_wait = late_wait;
     p.rec_per_cell = (float)((double)m_local / (double)total_cells);
 
-    const double M = (double)m_global;
-    const double P1 = (double)p.g.preds - 1.0;
-    for (int i = 0; i < 5; ++i) p.lam[i] = lambdas_host[i];
-    p.inv_den[0] = 1.0 / (2.0 * M);
-    p.inv_den[1] = 1.0 / (2.0 * M);
-    p.inv_den[2] = 1.0 / M;
-    p.inv_den[3] = 1.0 / (M * P1);
-    p.inv_den[4] = 1.0 / M;
-    // d(mean)/d(activation):  xy: 2(s-t)/(2M);  wh: 2(q-T)/(2M) * dq/dt with dq/dt = q/2;
-    // conf: 2(conf-iou)/M;  noobj: 2 conf /(M(P-1));  cls: 2/M
-    p.cxy = (float)(lambdas_host[0] / M);
-    p.cwh = (float)(lambdas_host[1] / (2.0 * M));
-    p.cconf = (float)(lambdas_host[2] * 2.0 / M);
-    p.cno = (float)(lambdas_host[3] * 2.0 / (M * P1));
-    p.ccls = (float)(lambdas_host[4] * 2.0 / M);
+    YhLossCoef kc;
+    YhFinalParams f;
+    yh_loss_coefs(lambdas_host, m_global, p.g.preds, &kc, &f);
+    p.cxy = kc.cxy; p.cwh = kc.cwh; p.cconf = kc.cconf; p.cno = kc.cno; p.ccls = kc.ccls;
+    for (int i = 0; i < 5; ++i) { p.lam[i] = f.lam[i]; p.inv_den[i] = f.inv_den[i]; }
 
     YH_REQUIRE(kTileBytesMax / (16ll * cf) >= 1, YH_ERR_UNSUPPORTED, "cell too wide for the shared-memory stage (%d floats per cell)", cf);
     int grid = 0;
@@ -1146,36 +896,24 @@ int yh_train_impl(int version, const float* y, int n, int s_h, int s_w, int a, i
     p.total_floats = total_cells * cf;
     p.cell_slot_floats = (cf + 6 + 3) & ~3;
     {
-        const long long per_cta = (227ll * 1024) / kCtasPerSm - 1024 - (cand ? 19 : 18) * 1024;  // minus reserve and static arrays
+        const long long per_cta = (227ll * 1024) / kCtasPerSm - 1024 - 18 * 1024;  // minus reserve and static arrays
         const long long left = per_cta - ((long long)p.tile_cells * cf * 4 + 32);
         long long slots = left > 0 ? left / (p.cell_slot_floats * 4ll) : 0;
         p.cell_slots = (int)(slots < kCellSlots ? slots : kCellSlots);
     }
-    memset(&p.cand, 0, sizeof(p.cand));
-    YhFinalParams f;
     f.acc = p.acc; f.terms = p.terms; f.loss = p.loss;
-    for (int i = 0; i < 5; ++i) { f.lam[i] = p.lam[i]; f.inv_den[i] = p.inv_den[i]; }
     rc = yh_fill_exchange(&f, xch_host);
     if (rc) return rc;
 
     const bool vec = ((uintptr_t)y & 15) == 0 && ((uintptr_t)dy & 15) == 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (cand) {
-        YH_REQUIRE(version == 2 && vec && p.tile_cells <= p.g.cells && cand->tile_cells == p.tile_cells &&
-                   cand->num_tiles == p.num_tiles, YH_ERR_INVALID, "internal: fused step on an input it does not cover");
-        p.cand = *cand;
-        rc = dy ? launch_geometry_cand<true>(p, grid, st) : launch_geometry_cand<false>(p, grid, st);
-    } else if (dy) {
+    if (dy) {
         rc = vec ? launch_geometry<true, true>(p, grid, st) : launch_geometry<true, false>(p, grid, st);
     } else {
         rc = vec ? launch_geometry<false, true>(p, grid, st) : launch_geometry<false, false>(p, grid, st);
     }
     if (rc) return rc;
-    if (fin_out) {
-        *fin_out = f;
-        return YH_OK;
-    }
-    return launch_finalize(f, st);
+    return yh_launch_finalize(f, st);
 }
 
 extern "C" {
@@ -1188,7 +926,7 @@ int yh_v2_train(const float* y, int n, int s_h, int s_w, int a, int c, const flo
                 int m_global, const float* lambdas_host, float* dy, float* terms, float* loss,
                 int32_t* resp, float* iou_resp, void* ws, size_t ws_bytes, void* stream) {
     return yh_train_impl(2, y, n, s_h, s_w, a, c, anchors_wh_host, img_h, img_w, gt, gt_off, m_local,
-                         m_global, lambdas_host, dy, terms, loss, resp, iou_resp, ws, ws_bytes, stream, 0, nullptr, nullptr, nullptr);
+                         m_global, lambdas_host, dy, terms, loss, resp, iou_resp, ws, ws_bytes, stream, 0, nullptr);
 }
 
 int yh_v1_train(const float* y, int n, int s_h, int s_w, int b, int c, float img_h, float img_w,
@@ -1196,7 +934,7 @@ int yh_v1_train(const float* y, int n, int s_h, int s_w, int b, int c, float img
                 const float* lambdas_host, float* dy, float* terms, float* loss, int32_t* resp,
                 float* iou_resp, void* ws, size_t ws_bytes, void* stream) {
     return yh_train_impl(1, y, n, s_h, s_w, b, c, nullptr, img_h, img_w, gt, gt_off, m_local, m_global,
-                         lambdas_host, dy, terms, loss, resp, iou_resp, ws, ws_bytes, stream, 0, nullptr, nullptr, nullptr);
+                         lambdas_host, dy, terms, loss, resp, iou_resp, ws, ws_bytes, stream, 0, nullptr);
 }
 
 int yh_v2_train_overlapped(const float* y, int n, int s_h, int s_w, int a, int c, const float* anchors_wh_host,
@@ -1204,7 +942,7 @@ int yh_v2_train_overlapped(const float* y, int n, int s_h, int s_w, int a, int c
                            int m_global, const float* lambdas_host, float* dy, float* terms, float* loss,
                            int32_t* resp, float* iou_resp, void* ws, size_t ws_bytes, void* stream) {
     return yh_train_impl(2, y, n, s_h, s_w, a, c, anchors_wh_host, img_h, img_w, gt, gt_off, m_local,
-                         m_global, lambdas_host, dy, terms, loss, resp, iou_resp, ws, ws_bytes, stream, 1, nullptr, nullptr, nullptr);
+                         m_global, lambdas_host, dy, terms, loss, resp, iou_resp, ws, ws_bytes, stream, 1, nullptr);
 }
 
 int yh_v1_train_overlapped(const float* y, int n, int s_h, int s_w, int b, int c, float img_h, float img_w,
@@ -1212,7 +950,7 @@ int yh_v1_train_overlapped(const float* y, int n, int s_h, int s_w, int b, int c
                            const float* lambdas_host, float* dy, float* terms, float* loss, int32_t* resp,
                            float* iou_resp, void* ws, size_t ws_bytes, void* stream) {
     return yh_train_impl(1, y, n, s_h, s_w, b, c, nullptr, img_h, img_w, gt, gt_off, m_local, m_global,
-                         lambdas_host, dy, terms, loss, resp, iou_resp, ws, ws_bytes, stream, 1, nullptr, nullptr, nullptr);
+                         lambdas_host, dy, terms, loss, resp, iou_resp, ws, ws_bytes, stream, 1, nullptr);
 }
 
 int yh_v2_train_sharded(const float* y, int n, int s_h, int s_w, int a, int c, const float* anchors_wh_host,
@@ -1222,7 +960,7 @@ int yh_v2_train_sharded(const float* y, int n, int s_h, int s_w, int a, int c, c
                         size_t ws_bytes, void* stream) {
     return yh_train_impl(2, y, n, s_h, s_w, a, c, anchors_wh_host, img_h, img_w, gt, gt_off, m_local,
                          m_global, lambdas_host, dy, terms, loss, resp, iou_resp, ws, ws_bytes, stream,
-                         (flags & YH_STEP_OVERLAPPED) ? 1 : 0, xch_host, nullptr, nullptr);
+                         (flags & YH_STEP_OVERLAPPED) ? 1 : 0, xch_host);
 }
 
 int yh_v1_train_sharded(const float* y, int n, int s_h, int s_w, int b, int c, float img_h, float img_w,
@@ -1232,7 +970,7 @@ int yh_v1_train_sharded(const float* y, int n, int s_h, int s_w, int b, int c, f
                         void* stream) {
     return yh_train_impl(1, y, n, s_h, s_w, b, c, nullptr, img_h, img_w, gt, gt_off, m_local, m_global,
                          lambdas_host, dy, terms, loss, resp, iou_resp, ws, ws_bytes, stream,
-                         (flags & YH_STEP_OVERLAPPED) ? 1 : 0, xch_host, nullptr, nullptr);
+                         (flags & YH_STEP_OVERLAPPED) ? 1 : 0, xch_host);
 }
 
 }  // extern "C"

@@ -159,16 +159,16 @@ def train_head(y, gt, gt_off, *, version, img_hw, lambdas, anchors=None, boxes_p
     return res
 
 
-STEP_CLASS_AWARE, STEP_OVERLAPPED, STEP_NO_POST = 1, 2, 4
+STEP_CLASS_AWARE, STEP_OVERLAPPED = 1, 2
 
 
 def train_post(y, gt, gt_off, *, img_hw, lambdas, anchors, conf_thre, iou_thre, m_global=None, want_grad=True,
                want_resp=False, class_aware=False, max_out=None, want_cls_spec=True, out=None, overlapped=False,
-               exchange=None, lists_only=False):
+               exchange=None):
     """The fused step of a YOLOv2 head -- yh_v2_train_post: train head (loss, terms, dL/dy) AND post-process
-    (threshold + per-image greedy NMS + class pick) of the same head tensor, which is read once: the train
-    head's dense pass lists the candidates, the post-process kernel works from those lists.  Bit-identical to
-    train_head(...) followed by postprocess(...).
+    (threshold + per-image greedy NMS + class pick) of the same head tensor in ONE kernel that reads it once
+    (one CTA per image holds the image in shared memory and does both).  Decisions, dL/dy and detections are
+    bit-identical to train_head(...) followed by postprocess(...); loss/terms agree to float rounding.
 
     Returns dict(train=<train_head dict>, post=<postprocess dict>, _ws=workspace).  Pass the returned dict as
     `out` to reuse every buffer (pipelines, CUDA graphs).  `overlapped=True`: the overlap contract of
@@ -220,8 +220,7 @@ def train_post(y, gt, gt_off, *, img_hw, lambdas, anchors, conf_thre, iou_thre, 
                       cls_spec=torch.empty(n, max_out, c, dtype=torch.float32, device=dev) if want_cls_spec else None,
                       label=torch.empty(n, max_out, dtype=torch.int32, device=dev),
                       score=torch.empty(n, max_out, dtype=torch.float32, device=dev))
-        flags = ((STEP_CLASS_AWARE if class_aware else 0) | (STEP_OVERLAPPED if overlapped else 0) |
-                 (STEP_NO_POST if lists_only else 0))  # lists_only: the fused train kernel alone (timing aid)
+        flags = (STEP_CLASS_AWARE if class_aware else 0) | (STEP_OVERLAPPED if overlapped else 0)
         _lib.call("yh_v2_train_post", _ptr(y), n, s_h, s_w, a, c, _anchors_host(anchors),
                   float(img_hw[0]), float(img_hw[1]), _ptr(gt), _ptr(gt_off), m_local, m_glob,
                   _host_floats(lam), _ptr(dy), _ptr(terms), _ptr(loss), _ptr(resp), _ptr(iou_resp),
