@@ -342,10 +342,18 @@ def main():
     # Sharded batch (N > 1): the six loss sums of all ranks are summed INSIDE the step's last kernel over NVLink
     # peer memory (odcp_b200.dist.PeerExchange, csrc/yh_finalize.cuh) -- the scalar-loss reduction of the
     # north star, in the timed region, every step, without an NCCL call.
-    xch = None
+    xch, xch_error = None, None
     if dist is not None and not args.no_collective:
         from odcp_b200.dist import PeerExchange
-        xch = PeerExchange(device=dev)
+        try:
+            xch = PeerExchange(device=dev)
+        except Exception as e:  # noqa: BLE001  (no peer access / IPC on this box: say so in the line, time without it)
+            xch_error = repr(e)
+        # all ranks or none: a rank that could not map its peers takes everyone to the plain path
+        ok = torch.tensor([0 if xch is None else 1], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            xch = None
 
     # rotating buffer sets: distinct addresses (inputs, outputs, workspace), > L2 in total
     gt = targets.records_to_tensor(case.rec, dev)
@@ -633,7 +641,8 @@ def main():
         collective = ("every step: the six loss sums of all %d ranks summed inside the step's last kernel over NVLink peer "
                       "memory (56-byte peer stores + sequence words, csrc/yh_finalize.cuh); terms/loss of the whole sharded "
                       "batch on every rank; no NCCL call in the timed region" % world) if xch is not None else \
-                     "none in the timed region (--no-collective): every rank reports the partial terms of its shard"
+                     ("none in the timed region (%s): every rank reports the partial terms of its shard"
+                      % ("--no-collective" if args.no_collective else "peer exchange unavailable: %s" % xch_error))
 
     # ---- CPU baseline (rank 0, N=1 only)
     cpu = None

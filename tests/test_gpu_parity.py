@@ -808,8 +808,8 @@ def test_postprocess_tail_and_unaligned_sources(cuda_device):
 # host-buffer pipeline
 # ------------------------------------------------------------------------------------------
 def test_host_pipeline_returns_what_the_direct_calls_return(cuda_device):
-    """HostHeadPipeline (pinned host buffers in, host buffers out, four streams, packed transfers)
-    against the same two calls made directly on device tensors, over more submits than slots."""
+    """HostHeadPipeline (pinned host buffers in, host buffers out, three streams, packed transfers, the fused
+    step) against the two separate calls made directly on device tensors, over more submits than slots."""
     from odcp_b200.host import HostHeadPipeline
     lam = synthetic.DEFAULT_LAMBDAS
     cases = [synthetic.make_case("p%d" % i, 2, 16, 13, 13, 5, 20, 416, 416, seed=900 + i, to_shift=-1.5) for i in range(5)]
@@ -833,9 +833,11 @@ def test_host_pipeline_returns_what_the_direct_calls_return(cuda_device):
                               lambdas=lam, **kw)
         post = ops.postprocess(y, conf_thre=0.5, iou_thre=0.45, max_out=64, want_cls_spec=False, **kw)
         torch.cuda.synchronize()
-        assert float(got["loss"]) == float(want["loss"].item())
+        # (the pipeline runs the fused step: gradients and detections bit for bit, the loss sums are grouped by
+        #  image instead of by tile -- equal to float rounding)
+        assert abs(float(got["loss"]) - float(want["loss"].item())) <= 2e-6 * abs(float(want["loss"].item()))
         assert torch.equal(got["dy"], want["dy"].cpu())
-        assert torch.equal(got["terms"], want["terms"].cpu())
+        assert torch.allclose(got["terms"], want["terms"].cpu(), rtol=2e-6, atol=0)
         cnt = post["keep_cnt"].cpu()
         assert torch.equal(got["keep_cnt"], cnt)
         mask = torch.arange(64)[None, :] < cnt.clamp(max=64)[:, None]
