@@ -86,7 +86,12 @@ class PeerExchange:
             if q == self.rank:
                 ptrs.append(self.local.data_ptr())
                 continue
-            st = torch.UntypedStorage._new_shared_cuda(*h)
+            # Open the peer's allocation with THIS rank's device current (first field: the device the handle is
+            # opened on): cudaIpcOpenMemHandle then maps it for kernels of this device and enables NVLink peer
+            # access lazily.  (Opened under the owner's device index -- what torch.multiprocessing does for
+            # tensors it hands to another process -- the pointer would only be valid for kernels on that GPU.)
+            with torch.cuda.device(dev):
+                st = torch.UntypedStorage._new_shared_cuda(dev.index, *h[1:])
             self._peers.append(st)
             ptrs.append(st.data_ptr())
         self.struct = _lib.YhExchange()
