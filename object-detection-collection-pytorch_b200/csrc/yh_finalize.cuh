@@ -3,19 +3,21 @@
 // workspace back to zero for the next call.
 //
 // Sharded batches (world > 1): the only data-path exchange of the whole path -- the six partial
-// sums of every rank -- happens HERE, inside the kernel, over NVLink peer memory: the warp stores its rank's
-// sums into its slot of every rank's exchange buffer (plain peer stores, 56 bytes per peer), publishes them
-// with a sequence word, waits for the sequence words of all ranks in its own buffer and adds the slots up in
-// rank order.  Integer sums: every rank obtains the same bits, and the same bits as one GPU over the whole
-// batch.  No NCCL call, no extra launch, no host round trip; the wait is hidden behind the next kernel of the
-// launch chain.  Exchange buffer layout (uint64 words): [parity 0/1][rank < YH_MAX_RANKS][8] = six sums, flags,
-// sequence; word 2*YH_MAX_RANKS*8: the local call counter.  Two parities: a rank can be at most one call ahead
-// of a peer that has not read the previous slot yet.
+// sums of every rank -- happens HERE, inside the kernel, over NVLink peer memory, with a low-latency protocol:
+// every 8-byte word a rank stores into a peer's buffer carries 32 bits of payload and the 32-bit sequence number
+// of the call (8-byte stores are single-copy atomic), so a word validates itself: no fence, no separate flag, one
+// NVLink store latency end to end.  The warp stores its rank's 7 values (six sums + flags) as 14 such words into
+// its slot of every rank's buffer, polls the 14 words of every rank's slot in its OWN buffer until they carry this
+// call's sequence number, and adds the slots up in rank order.  Integer sums: every rank obtains the same bits, and
+// the same bits as one GPU over the whole batch.  No NCCL call, no extra launch, no host round trip.
+// Exchange buffer layout (uint64 words): [parity 0/1][rank < YH_MAX_RANKS][16]; word 2*YH_MAX_RANKS*16: the local
+// call counter.  Two parities: a rank can be at most one call ahead of a peer that has not read its previous slot.
 #pragma once
 
 #include "yh_common.cuh"
 
-constexpr int kYhXchSeqWord = 2 * YH_MAX_RANKS * 8;
+constexpr int kYhXchSlotWords = 16;
+constexpr int kYhXchSeqWord = 2 * YH_MAX_RANKS * kYhXchSlotWords;
 constexpr size_t kYhXchBytes = (size_t)(kYhXchSeqWord + 8) * 8;
 
 __device__ __forceinline__ void yh_st_sys(unsigned long long* p, unsigned long long v) {
@@ -24,11 +26,6 @@ __device__ __forceinline__ void yh_st_sys(unsigned long long* p, unsigned long l
 __device__ __forceinline__ unsigned long long yh_ld_sys(const unsigned long long* p) {
     unsigned long long v;
     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long yh_ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ unsigned long long yh_globaltimer() {
@@ -45,36 +42,39 @@ __device__ __forceinline__ void yh_finalize_warp(const YhFinalParams& f, int lan
     if (f.world > 1) {
         unsigned long long* mine = f.peer[f.rank];
         const unsigned long long seq = yh_ld_sys(mine + kYhXchSeqWord) + 1ull;
+        const unsigned seq32 = (unsigned)seq | 0x80000000u;  // (never zero: a zero-filled buffer matches no call)
         const int par = (int)(seq & 1ull);
-        const int slot = (par * YH_MAX_RANKS + f.rank) * 8;
-        for (int q = 0; q < f.world; ++q)
-            if (lane < 7) yh_st_sys(f.peer[q] + slot + lane, a);
-        __threadfence_system();
-        __syncwarp();
-        if (lane < f.world) {  // publish: the slot of rank q is complete
-            __threadfence_system();
-            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f.peer[lane] + slot + 7), "l"(seq) : "memory");
-        }
-        // wait for every rank's slot in this rank's buffer (bounded: a rank that never arrives turns the
-        // loss into NaN after 4 s instead of hanging the device)
+        // lane l < 14: half (l & 1) of value (l >> 1), tagged with the sequence number
+        const unsigned long long val = __shfl_sync(0xffffffffu, a, lane >> 1);
+        const unsigned half = (lane & 1) ? (unsigned)(val >> 32) : (unsigned)val;
+        const unsigned long long word = ((unsigned long long)seq32 << 32) | half;
+        const int slot = (par * YH_MAX_RANKS + f.rank) * kYhXchSlotWords;
+        if (lane < 14)
+            for (int q = 0; q < f.world; ++q) yh_st_sys(f.peer[q] + slot + lane, word);
+        // every rank's slot in this rank's buffer (bounded: a rank that never arrives turns the loss into NaN
+        // after 4 s instead of hanging the device)
         bool ok = true;
-        if (lane < f.world) {
-            const unsigned long long* flag = mine + (par * YH_MAX_RANKS + lane) * 8 + 7;
-            const unsigned long long t0 = yh_globaltimer();
-            while (yh_ld_acquire_sys(flag) != seq) {
-                if (yh_globaltimer() - t0 > 4000000000ull) { ok = false; break; }
-                __nanosleep(64);
+        unsigned long long tot = 0ull;
+        const unsigned long long t0 = yh_globaltimer();
+        for (int r = 0; r < f.world; ++r) {
+            unsigned payload = 0u;
+            if (lane < 14) {
+                const unsigned long long* src = mine + (par * YH_MAX_RANKS + r) * kYhXchSlotWords + lane;
+                unsigned long long w = yh_ld_sys(src);
+                while ((unsigned)(w >> 32) != seq32) {
+                    if (yh_globaltimer() - t0 > 4000000000ull) { ok = false; break; }
+                    w = yh_ld_sys(src);
+                }
+                payload = (unsigned)w;
             }
+            // rank r's value (lane >> 1) = hi:lo, assembled on the even lane of each pair; summed in rank order
+            const unsigned hi = __shfl_down_sync(0xffffffffu, payload, 1);
+            const unsigned long long v = ((unsigned long long)hi << 32) | payload;
+            tot = (lane >> 1) == 6 ? (tot | v) : tot + v;
         }
         lost = !__all_sync(0xffffffffu, ok);
-        __threadfence_system();
-        unsigned long long tot = 0ull;
-        if (lane < 7)
-            for (int r = 0; r < f.world; ++r) {
-                const unsigned long long v = yh_ld_sys(mine + (par * YH_MAX_RANKS + r) * 8 + lane);
-                tot = lane == 6 ? (tot | v) : tot + v;
-            }
-        a = tot;
+        // value q sits on lane 2q: bring it to lane q
+        a = __shfl_sync(0xffffffffu, tot, (2 * lane) & 31);
         if (lane == 0) yh_st_sys(mine + kYhXchSeqWord, seq);
     }
     unsigned long long v[7];

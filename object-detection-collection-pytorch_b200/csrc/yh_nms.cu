@@ -971,7 +971,7 @@ __global__ void __launch_bounds__(NTH, NTH >= 512 ? 2 : 3) yh_nms_kernel(const N
             if (!with_labels) rest_img(FastTag<false>{}, IntTag<NTH>{});
             else rest_img(FastTag<true>{}, IntTag<NTH>{});
         }
-        if (p.late_wait) yh_grid_dependency_wait();  // (see the end of the kernel)
+        if (p.late_wait && img == 0 && tid == 0) yh_grid_dependency_wait();  // (see the end of the kernel)
         return;
     }
     if (TRAIN && warp >= kTeam / 32) do_records();  // (an image with more candidates than shared memory holds: records first)
@@ -1250,9 +1250,11 @@ __global__ void __launch_bounds__(NTH, NTH >= 512 ? 2 : 3) yh_nms_kernel(const N
     else if (fast) rest(FastTag<true>{}, FastTag<true>{});
     else rest(FastTag<false>{}, FastTag<true>{});
     if (TRAIN) publish_sums();
-    // (YH_POST_INPUT_READY) everything above ran next to the tail of the previous kernel of the stream;
-    // this kernel must not complete before that one has, or work launched after it could overtake it
-    if (p.late_wait) yh_grid_dependency_wait();
+    // (overlapped call) everything above ran next to the tails of the kernels in front of it on the stream; this
+    // grid must not complete before they have, or work launched after it could overtake them.  ONE thread of the
+    // grid waits: the grid is not complete until it exits, while every other CTA leaves and frees its SM for the
+    // kernels behind (all CTAs waiting here held their shared memory idle until the slowest predecessor was done)
+    if (p.late_wait && img == 0 && tid == 0) yh_grid_dependency_wait();
 }
 
 template <int TV, int TA, int TC, int MODE, int NTH, bool TRAIN = false>

@@ -722,11 +722,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
         __syncthreads();
     }
     if (tid == kPublisher) {
-        // (*_overlapped) this kernel ran next to the tails of the kernels in front of it; the workspace
-        // is shared with the previous launch of this kernel, and this launch must not complete before
-        // they have: wait for them now
-        if (p.late_wait) yh_grid_dependency_wait();
         publish();
+        // (*_overlapped) this kernel ran next to the tails of the kernels in front of it and must not complete
+        // before they have (work launched after it could overtake them): ONE thread of the grid waits for them --
+        // the grid is not complete until it exits, every other CTA leaves and frees its SM.  The workspace is this
+        // call's own (THE OVERLAP CONTRACT, include/yolohead.h), so the sums need not wait.
+        if (p.late_wait && blockIdx.x == 0) yh_grid_dependency_wait();
     }
     XT_FLUSH;
 }
