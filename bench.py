@@ -47,7 +47,8 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (0: the workload's own: 256 / 512)")
     ap.add_argument("--sets", type=int, default=8, help="rotating buffer sets (total must exceed L2)")
-    ap.add_argument("--cpu-sample", type=int, default=32, help="images in the CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="images per step of the CPU legs (0: the full batch for the headline workload, 8 for cfg5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS),
@@ -90,68 +91,98 @@ WORKLOADS = {
 }
 
 
-def workload_config(workload, batch, sets=None, set_bytes=0, fused=True, collective=None):
+def workload_config(workload, batch):
+    """`config` of the JSON line: the workload, identical in both arms (ours and --impl reference)."""
     w = WORKLOADS[workload]
-    cfg = {
+    return {
         "workload": "%s_b%d_train(decode+assign+loss+bwd)+postprocess(conf%.2f,nms_iou%.2f)"
                     % (w["name"], batch, CONF_THRE, IOU_THRE),
         "batch_per_gpu": batch, "grid": w["grid"], "anchors": 5, "classes": 20, "image": w["image"],
         "gt_boxes_per_image": w["boxes"], "candidates_per_image": w["cands"],
     }
-    if sets is not None:
-        cfg["l2"] = "%d rotating buffer sets per GPU, inputs + outputs + workspace distinct per set (%.0f MB > 126 MB L2)" % (
-            sets, sets * set_bytes / 1e6)
-        cfg["step"] = ("fused step: ONE call yh_v2_train_post = one kernel, one CTA per image (dense loss/gradient pass, the "
-                       "image's records, threshold, NMS, class pick) + the one-warp finalize kernel; y read once" if fused else
-                       "two separate calls: yh_v2_train (+ finalize kernel) + yh_v2_postprocess; y read twice")
-        cfg["streams"] = ("one stream, programmatic dependent launches; a graph replay is 4 passes over the %d buffer sets; "
-                          "every call but the first of a pass is an overlapped call (include/yolohead.h, THE OVERLAP "
-                          "CONTRACT) and runs next to the tails of the kernels in front of it; the first call of every "
-                          "pass waits for everything before it" % sets)
-        cfg["timing"] = ("the timed K-step region is rehearsed twice (its own graphs), starts behind a device-side gate "
-                         "kernel and is repeated; value = the median region, max over ranks per region")
-        if collective is not None:
-            cfg["collective"] = collective
-    return cfg
+
+
+def run_description(sets, set_bytes, fused, collective):
+    """How our arm ran the workload (top-level `run` of the line; not part of `config`)."""
+    run = {
+        "l2": "%d rotating buffer sets per GPU, inputs + outputs + workspace distinct per set (%.0f MB > 126 MB L2)" % (
+            sets, sets * set_bytes / 1e6),
+        "step": ("fused step: ONE call yh_v2_train_post = one kernel, one CTA per image (dense loss/gradient pass, the "
+                 "image's records, threshold, NMS, class pick) + the one-warp finalize kernel; y read once" if fused else
+                 "two separate calls: yh_v2_train (+ finalize kernel) + yh_v2_postprocess; y read twice"),
+        "streams": ("one stream, programmatic dependent launches; a graph replay is 4 passes over the %d buffer sets; "
+                    "every call but the first of a pass is an overlapped call (include/yolohead.h, THE OVERLAP "
+                    "CONTRACT) and runs next to the tails of the kernels in front of it; the first call of every "
+                    "pass waits for everything before it" % sets),
+        "timing": ("the timed K-step region is rehearsed twice (its own graphs), starts behind a device-side gate "
+                   "kernel and is repeated; value = the median region, max over ranks per region"),
+    }
+    if collective is not None:
+        run["collective"] = collective
+    return run
 
 
 # ------------------------------------------------------------------------------------------
 # CPU port of the reference path (oracle/) -- the baseline arm
 # ------------------------------------------------------------------------------------------
-def cpu_port_step(case, lambdas):
-    """One pass of the reference's torch-CPU algorithm over `case`: get_loss + backward
-    (dense per-box replication, autograd) and the per-image detect/NMS loop."""
-    from oracle import yolo_head_oracle as O
-    O.train_head_dense(case, lambdas)
-    O.postprocess_torch(case.y, case.height, case.width, case.version, case.anchors, CONF_THRE, IOU_THRE)
-
-
-def time_cpu_port(sample, reps, warm, workload="headline"):
-    from odcp_b200 import synthetic
+def make_cpu_step(workload, sample):
+    """The reference's CPU implementation of the path over a `sample`-image batch of the workload, as a callable.
+    With the staged reference (oracle/_ref, or /root/reference in the build container) it is the UNMODIFIED
+    reference: HeadOnly.get_loss + loss.backward() + predict + the per-image nms loop of detect
+    (oracle/refharness.py) -- kind "reference"; otherwise the oracle's port of the same op sequence (pinned
+    bit-exact against the reference's outputs, tests/golden/) -- kind "port"."""
+    from odcp_b200 import synthetic, targets
+    from oracle import refharness as RH
     torch.set_num_threads(os.cpu_count() or 1)
     case = WORKLOADS[workload]["case"](sample)
+    lam = synthetic.DEFAULT_LAMBDAS
+    if RH.available():
+        ref = RH.load_reference("cpu")
+        dense = targets.records_to_dense(case.rec, case.n, case.s_h, case.s_w, case.c, case.version)
+        import warnings
+        warnings.filterwarnings("ignore", message="Using a target size")  # the reference's own broadcasting mse_loss
+        return (lambda: RH.reference_step(ref, case, dense, lam, CONF_THRE, IOU_THRE)), "reference", \
+            "the unmodified reference (staged copy, %s): get_loss + backward + predict + per-image nms" % ref.location
+    from oracle import yolo_head_oracle as O
+
+    def port():
+        O.train_head_dense(case, lam)
+        O.postprocess_torch(case.y, case.height, case.width, case.version, case.anchors, CONF_THRE, IOU_THRE)
+    return port, "port", "oracle/ torch-CPU port of get_loss + backward and the per-image nms loop (reference not staged)"
+
+
+def cpu_sample_size(workload, batch, requested):
+    """Images per CPU step: the full batch where the reference can hold it (its per-box replication needs
+    49*S*S*A floats per box, several times over: headline batch 256 ~3 GB), a bounded sample otherwise."""
+    if requested:
+        return min(requested, batch)
+    return batch if workload == "headline" else 8
+
+
+def time_cpu(workload, sample, reps, warm):
+    fn, kind, what = make_cpu_step(workload, sample)
     for _ in range(warm):
-        cpu_port_step(case, synthetic.DEFAULT_LAMBDAS)
+        fn()
     ts = []
     for _ in range(reps):
         t0 = time.perf_counter()
-        cpu_port_step(case, synthetic.DEFAULT_LAMBDAS)
+        fn()
         ts.append(time.perf_counter() - t0)
-    return case, ts
+    return ts, kind, what
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path.  /root/reference does
-    not exist on the GPU box and the reference is torch-eager Python (nothing to compile), so this
-    arm times the oracle's torch-CPU port of it (same ops in the same order, pinned bit-exact
-    against the reference's outputs in tests/golden/) with all host threads."""
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores, all threads,
+    on our arm's workload (the full batch for the headline; for cfg5 the reference cannot hold the full batch --
+    SURVEY 8(a-4): 18 GB of replicated predictions -- and an 8-image sample is timed)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = args.cpu_sample
-    steps = max(1, min(args.steps, 20))
-    warm = max(1, min(args.warmup, 2))
-    case, ts = time_cpu_port(sample, steps, warm, args.workload)
+    batch = args.batch or WORKLOADS[args.workload]["batch"]
+    sample = cpu_sample_size(args.workload, batch, args.cpu_sample)
+    steps = max(1, min(args.steps, 40))
+    warm = max(0, min(args.warmup, 10))
+    ts, kind, what = time_cpu(args.workload, sample, steps, warm)
     total = float(np.sum(ts))
     value = sample * len(ts) / total
     cores = torch.get_num_threads()
@@ -159,12 +190,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": len(ts), "warmup": warm, "ms_per_step": 1e3 * total / len(ts), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.workload, args.batch or WORKLOADS[args.workload]["batch"]),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d-image sample of the batch-%d workload per step (the reference's per-box "
-                                   "replication grows as M*S*S*A); torch %s CPU, %d threads, os.cpu_count()=%s"
-                                   % (sample, args.batch or WORKLOADS[args.workload]["batch"], torch.__version__, cores,
-                                      os.cpu_count())},
+        "config": workload_config(args.workload, batch),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": "%d images per step (%s); %s; torch %s CPU, %d threads, os.cpu_count()=%s"
+                                   % (sample, "the full batch" if sample == batch else "a sample of the batch-%d workload" % batch,
+                                      what, torch.__version__, cores, os.cpu_count())},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -644,15 +674,15 @@ def main():
                      ("none in the timed region (%s): every rank reports the partial terms of its shard"
                       % ("--no-collective" if args.no_collective else "peer exchange unavailable: %s" % xch_error))
 
-    # ---- CPU baseline (rank 0, N=1 only)
+    # ---- CPU baseline (rank 0, N=1 only): a bounded amount of the same CPU work as --impl reference
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample = args.cpu_sample
-        _, ts = time_cpu_port(sample, reps=5, warm=1, workload=args.workload)
-        cpu = {"value": sample / float(np.min(ts)), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-               "sample": "%d-image sample of the same workload, best of 5 after 1 warm-up (%.2f s of CPU work); "
-                         "oracle/ torch-CPU port of get_loss+backward and the per-image nms loop; "
-                         "os.cpu_count()=%s" % (sample, float(np.sum(ts)), os.cpu_count())}
+        sample = cpu_sample_size(args.workload, B, args.cpu_sample)
+        ts, kind, what = time_cpu(args.workload, sample, reps=3, warm=1)
+        cpu = {"value": sample / float(np.min(ts)), "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+               "sample": "%d images per step (%s), best of 3 after 1 warm-up (%.1f s of CPU work); %s; os.cpu_count()=%s"
+                         % (sample, "the full batch" if sample == B else "a sample of the batch-%d workload" % B,
+                            float(np.sum(ts)), what, os.cpu_count())}
 
     if rank == 0:
         line = {
@@ -662,8 +692,8 @@ def main():
                           "what": "device time of the K-step region, max over ranks, per repetition"},
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.workload, B, R, set_bytes + (sets[0]["res"].get("_ws").numel() if fused else 0),
-                                      fused, collective),
+            "config": workload_config(args.workload, B),
+            "run": run_description(R, set_bytes + (sets[0]["res"].get("_ws").numel() if fused else 0), fused, collective),
             "clocks": sampler.summary(window), "e2e": e2e, "gpu_launches": (2 if fused else 3) * K,
             "roofline": roofline, "cpu_baseline": cpu, "loss": loss_value, "terms": terms_value,
         }
