@@ -278,6 +278,10 @@ YH_API int yh_nms(const float* bbox, const float* conf, const int32_t* labels, i
 /* Elementwise IoU of `count` xyxy box pairs: models/utils.py:5-65 (torch branch). */
 YH_API int yh_iou(const float* boxes1, const float* boxes2, int64_t count, float* iou, void* stream);
 
+/* The same in float64: get_iou(..., numpy=True) keeps its inputs' dtype, and evaluate_model feeds it float64 boxes
+ * (models/utils.py:30-38, 52-63, 250-252).  numpy's bits (one rounding per operation, NaNs propagate). */
+YH_API int yh_iou_f64(const double* boxes1, const double* boxes2, int64_t count, double* iou, void* stream);
+
 /* x[i] *= *scale_dev for i < count; returns immediately on the device when *scale_dev == 1
  * (the usual upstream gradient of a scalar loss). */
 YH_API int yh_scale_inplace(float* x, int64_t count, const float* scale_dev, void* stream);

@@ -52,6 +52,7 @@ SIGNATURES = {
     "yh_match_detections": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p]),
     "yh_nms": (_i, [_p, _p, _p, _i, _i, _f, _f, _i, _p, _p, _p, _sz, _p]),
     "yh_iou": (_i, [_p, _p, _i64, _p, _p]),
+    "yh_iou_f64": (_i, [_p, _p, _i64, _p, _p]),
     "yh_scale_inplace": (_i, [_p, _i64, _p, _p]),
     "yh_sgd_step": (_i, [_p, _p, _p, _p, _i, _f, _f, _f, _i, _p]),
 }

@@ -76,6 +76,30 @@ __global__ void yh_iou_kernel(const float4* __restrict__ b1, const float4* __res
     }
 }
 
+// float64 variant: get_iou(..., numpy=True) on float64 arrays (models/utils.py:30-38, 52-63; evaluate_model feeds it
+// float64 boxes, :250-252).  numpy rounds every elementwise operation once: explicit round-to-nearest intrinsics
+// keep nvcc from contracting them into FMAs, so the bits are numpy's.
+__global__ void yh_iou_f64_kernel(const double* __restrict__ b1, const double* __restrict__ b2,
+                                  long long count, double* __restrict__ out) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        const double x1 = b1[4 * i], y1 = b1[4 * i + 1], x2 = b1[4 * i + 2], y2 = b1[4 * i + 3];
+        const double u1 = b2[4 * i], v1 = b2[4 * i + 1], u2 = b2[4 * i + 2], v2 = b2[4 * i + 3];
+        // np.maximum / np.minimum propagate NaN, np.clip(a_min=0) as well
+        const double ix1 = (x1 != x1 || u1 != u1) ? x1 + u1 : fmax(x1, u1);
+        const double iy1 = (y1 != y1 || v1 != v1) ? y1 + v1 : fmax(y1, v1);
+        const double ix2 = (x2 != x2 || u2 != u2) ? x2 + u2 : fmin(x2, u2);
+        const double iy2 = (y2 != y2 || v2 != v2) ? y2 + v2 : fmin(y2, v2);
+        const double dw = __dsub_rn(ix2, ix1), dh = __dsub_rn(iy2, iy1);
+        const double iw = dw != dw ? dw : fmax(dw, 0.0), ih = dh != dh ? dh : fmax(dh, 0.0);
+        const double inter = __dmul_rn(iw, ih);
+        const double a1 = __dmul_rn(__dsub_rn(x2, x1), __dsub_rn(y2, y1));
+        const double a2 = __dmul_rn(__dsub_rn(u2, u1), __dsub_rn(v2, v1));
+        const double uni = __dsub_rn(__dadd_rn(a1, a2), inter);
+        out[i] = __ddiv_rn(inter, __dadd_rn(uni, 1e-6));
+    }
+}
+
 __global__ void yh_scale_kernel(float* __restrict__ x, long long count, const float* __restrict__ scale) {
     const float s = __ldg(scale);
     if (s == 1.0f) return;
@@ -101,6 +125,20 @@ int yh_iou(const float* boxes1, const float* boxes2, int64_t count, float* iou, 
     yh_iou_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
         (const float4*)boxes1, (const float4*)boxes2, (long long)count, iou);
     return yh_check_cuda(cudaGetLastError(), "yh_iou launch");
+}
+
+int yh_iou_f64(const double* boxes1, const double* boxes2, int64_t count, double* iou, void* stream) {
+    YH_REQUIRE(count >= 0, YH_ERR_INVALID, "count < 0");
+    if (count == 0) return YH_OK;
+    YH_REQUIRE(boxes1 && boxes2 && iou, YH_ERR_INVALID, "null pointer");
+    YH_REQUIRE(((uintptr_t)boxes1 & 7) == 0 && ((uintptr_t)boxes2 & 7) == 0 && ((uintptr_t)iou & 7) == 0, YH_ERR_INVALID,
+               "arrays must be 8-byte aligned");
+    const int threads = 256;
+    long long blocks = (count + threads - 1) / threads;
+    const long long cap = (long long)yh_sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    yh_iou_f64_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(boxes1, boxes2, (long long)count, iou);
+    return yh_check_cuda(cudaGetLastError(), "yh_iou_f64 launch");
 }
 
 int yh_scale_inplace(float* x, int64_t count, const float* scale_dev, void* stream) {

@@ -289,8 +289,8 @@ __device__ __forceinline__ void quad_class_pick_fast(const float* cl, int C, flo
     *ok = !active || (ncand <= 1 && se < INFINITY && bv >= 1e-30f && bv < INFINITY);  // (false for NaN)
 }
 
-// bit = "box i suppresses box j": iou(i, j) >= thr with the reference's arithmetic
-// (models/utils.py:47-63, 133: j survives iff iou < thr).  ai/aj are the boxes' areas as yh_iou_xyxy
+// bit = "box i suppresses box j": NOT (iou(i, j) < thr) with the reference's arithmetic
+// (models/utils.py:47-63, 133: j survives iff iou < thr; a NaN IoU therefore removes j).  ai/aj are the boxes' areas as yh_iou_xyxy
 // rounds them.  Boxes that do not overlap have iou == 0 exactly, and away from the threshold the
 // comparison is decided by one multiplication (margin 2^-20 >> the rounding of the product); the
 // IEEE division only runs for ratios within that margin of thr, so the result is bit-exact.
@@ -305,7 +305,7 @@ __device__ __forceinline__ bool suppresses(const float4& bi, float ai, const flo
         if (inter > __fmul_rn(t, 1.000001f)) return true;
         if (inter < __fmul_rn(t, 0.999999f)) return false;
     }
-    return __fdiv_rn(inter, den) >= thr;
+    return !(__fdiv_rn(inter, den) < thr);  // (a NaN ratio -- two boxes of infinite size -- does NOT survive: utils.py:133)
 }
 
 // The same decision for the dense pair enumeration, where nearly every pair is far below the threshold:

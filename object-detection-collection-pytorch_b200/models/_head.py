@@ -16,24 +16,26 @@ class HeadLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, y, gt, gt_off, cfg):
         want_grad = bool(ctx.needs_input_grad[0])
-        r = ops.train_head(y.detach(), gt, gt_off, want_grad=want_grad, want_resp=cfg.get("want_resp", False),
-                           **{k: cfg[k] for k in ("version", "img_hw", "lambdas", "anchors", "boxes_per_cell", "m_global")})
+        kw = {k: cfg[k] for k in ("version", "img_hw", "lambdas", "anchors", "boxes_per_cell", "m_global")}
+        r = ops.train_head(y.detach(), gt, gt_off, want_grad=want_grad, want_resp=cfg.get("want_resp", False), **kw)
         ctx.dy = r["dy"]
-        ctx.prev_scale = None
+        ctx.kw = kw
+        ctx.save_for_backward(y, gt, gt_off)  # only read if backward runs a second time (retain_graph)
         cfg["last"] = r
         ctx.mark_non_differentiable(r["terms"])
         return r["loss"], r["terms"]
 
     @staticmethod
     def backward(ctx, grad_loss, _grad_terms):
-        dy = ctx.dy
+        dy, ctx.dy = ctx.dy, None  # the kernel's gradient buffer is handed out once: later backwards never touch it
         if dy is None:
-            raise RuntimeError("get_loss was evaluated without gradients")
+            # a repeated backward (retain_graph=True): the first one gave the buffer away, possibly scaled -- run the
+            # kernel again instead of un-scaling (exact, and an upstream gradient of 0 loses nothing); without
+            # retain_graph reading the saved tensors raises torch's usual "backward through the graph a second time"
+            y, gt, gt_off = ctx.saved_tensors
+            dy = ops.train_head(y.detach(), gt, gt_off, want_grad=True, **ctx.kw)["dy"]
         g = grad_loss.to(device=dy.device, dtype=torch.float32).reshape(())
-        scale = g if ctx.prev_scale is None else g / ctx.prev_scale  # repeated backward(retain_graph)
-        ops.scale_inplace(dy, scale.contiguous())
-        ctx.prev_scale = g
-        return dy, None, None, None
+        return ops.scale_inplace(dy, g.contiguous()), None, None, None  # (a no-op on the device for g == 1)
 
 
 class HeadOps:
@@ -120,31 +122,61 @@ class HeadOps:
         return ops.postprocess(y.detach(), conf_thre=conf_score_thre, iou_thre=iou_thre,
                                class_aware=class_aware, max_out=max_out, **self._yh_kwargs(x_batch))
 
-    def _yh_annot(self, r, n, box_fn=None):
-        k = min(int(r["keep_cnt"][n].item()), r["keep_idx"].shape[1])
-        bbox = r["bbox"][n, :k].cpu().numpy()
+    def _yh_detect_host(self, x_batch, conf_score_thre, iou_thre, class_aware=False, max_out=None):
+        """Post-process of a batch with the results in HOST memory: the outputs the annotation dicts need
+        (counts, boxes, confidences, labels, scores) live in one packed device buffer and come back with ONE
+        device-to-host copy -- the only synchronisation of detect / detect_batch."""
+        y = self(x_batch).detach()
+        kw = self._yh_kwargs(x_batch)
+        n, s_h, s_w, a, c = ops.head_shape(y, kw["version"], kw["boxes_per_cell"])
+        p = s_h * s_w * a
+        max_out = p if max_out is None else int(max_out)
+        i32, f32 = torch.int32, torch.float32
+        spec = [("keep_cnt", (n,), i32), ("keep_idx", (n, max_out), i32), ("bbox", (n, max_out, 4), f32),
+                ("conf", (n, max_out), f32), ("label", (n, max_out), i32), ("score", (n, max_out), f32)]
+        offs, o = {}, 0
+        for name, shp, dt in spec:
+            o = (o + 15) & ~15
+            offs[name] = (o, int(np.prod(shp)) * 4, shp, dt)
+            o += offs[name][1]
+
+        def carve(buf):
+            return {k: buf[lo:lo + nb].view(dt).view(*shp) for k, (lo, nb, shp, dt) in offs.items()}
+
+        with torch.cuda.device(y.device):
+            buf = torch.empty((o + 15) & ~15, dtype=torch.uint8, device=y.device)
+            ws = torch.empty(max(int(ops._lib.load().yh_postprocess_workspace_bytes(n, p)), 16), dtype=torch.uint8,
+                             device=y.device)
+            ops.postprocess(y, conf_thre=conf_score_thre, iou_thre=iou_thre, class_aware=class_aware, max_out=max_out,
+                            want_cls_spec=False, out=dict(carve(buf), cls_spec=None, _ws=ws), **kw)
+            host = buf.cpu()
+        return {k: v.numpy() for k, v in carve(host).items()}
+
+    def _yh_annot(self, h, n, box_fn=None):
+        k = min(int(h["keep_cnt"][n]), h["keep_idx"].shape[1])
+        bbox = h["bbox"][n, :k]
         if box_fn is not None:
             bbox = box_fn(bbox)
         return {
             "bbox_list": bbox.tolist(),
-            "lbl_list": [self.cls_list[i] for i in r["label"][n, :k].cpu().tolist()],
-            "conf_score_list": r["conf"][n, :k].cpu().numpy().tolist(),
-            "cls_spec_conf_score_list": r["score"][n, :k].cpu().numpy().tolist(),
+            "lbl_list": [self.cls_list[i] for i in h["label"][n, :k].tolist()],
+            "conf_score_list": h["conf"][n, :k].tolist(),
+            "cls_spec_conf_score_list": h["score"][n, :k].tolist(),
         }
 
     def detect(self, img, conf_score_thre=0.9, iou_thre=0.5):
         """One image -> dict of python lists (reference models/yolov2.py:651-745)."""
         self.eval()
         with torch.no_grad():
-            r = self.postprocess(self._yh_image_batch(img), conf_score_thre, iou_thre)
-        return self._yh_annot(r, 0)
+            h = self._yh_detect_host(self._yh_image_batch(img), conf_score_thre, iou_thre)
+        return self._yh_annot(h, 0)
 
     def detect_batch(self, x_batch, conf_score_thre=0.9, iou_thre=0.5, class_aware=False):
-        """Batched detect: one launch for all images, list of per-image dicts."""
+        """Batched detect: one launch and one device-to-host copy for all images, list of per-image dicts."""
         self.eval()
         with torch.no_grad():
-            r = self.postprocess(x_batch, conf_score_thre, iou_thre, class_aware=class_aware)
-        return [self._yh_annot(r, n) for n in range(x_batch.shape[0])]
+            h = self._yh_detect_host(x_batch, conf_score_thre, iou_thre, class_aware=class_aware)
+        return [self._yh_annot(h, n) for n in range(x_batch.shape[0])]
 
 
 class InjectedHead(torch.nn.Module):

@@ -10,8 +10,8 @@ the unchanged `get_loss` / `detect` / `nms` / `get_iou` calls.
 """
 from __future__ import annotations
 
-_METHODS = ("predict", "get_loss", "get_loss_compact", "detect", "detect_batch", "postprocess",
-            "_yh_anchors", "_yh_kwargs", "_yh_image_batch", "_yh_annot")
+_METHODS = ("predict", "get_loss", "get_loss_compact", "get_loss_from_boxes", "detect", "detect_batch", "postprocess",
+            "_yh_anchors", "_yh_kwargs", "_yh_image_batch", "_yh_annot", "_yh_detect_host")
 
 
 def patch_reference(ref_yolov1=None, ref_yolov2=None, ref_utils=None, fused_sgd=False):
@@ -42,5 +42,6 @@ def patch_reference(ref_yolov1=None, ref_yolov2=None, ref_utils=None, fused_sgd=
     if ref_utils is not None:
         ref_utils.nms = u.nms
         ref_utils.get_iou = u.get_iou
+        ref_utils.evaluate_model = u.evaluate_model  # batched drop-in (same arguments, same result dict)
         done.append("utils")
     return done

@@ -23,15 +23,18 @@ class YOLOv1HeadOps(HeadOps):
         height, width = img.shape[:2]
         small = cv2.resize(np.asarray(img), (V1_INPUT, V1_INPUT), interpolation=cv2.INTER_LINEAR)
         with torch.no_grad():
-            r = self.postprocess(self._yh_image_batch(small), conf_score_thre, iou_thre)
+            h = self._yh_detect_host(self._yh_image_batch(small), conf_score_thre, iou_thre)
 
         def to_original(b):
-            b = np.clip(b, 0.0, V1_INPUT - 1.0)
-            b[:, 0::2] *= width / V1_INPUT
-            b[:, 1::2] *= height / V1_INPUT
+            # the reference clips in float32 (models/yolov1.py:517-523), hands python floats to an albumentations
+            # Resize(height, width) with pascal_voc boxes (:536-543, :1357-1367), which normalises by the 224x224
+            # image and scales to the original size in float64: (x / 224) * width
+            b = np.clip(b, np.float32(0.0), np.float32(V1_INPUT - 1.0)).astype(np.float64)
+            b[:, 0::2] = b[:, 0::2] / V1_INPUT * width
+            b[:, 1::2] = b[:, 1::2] / V1_INPUT * height
             return b
 
-        return self._yh_annot(r, 0, to_original)
+        return self._yh_annot(h, 0, to_original)
 
 
 class YOLOv1Head(YOLOv1HeadOps, InjectedHead):

@@ -394,15 +394,19 @@ def nms_indices(bbox, conf, *, conf_thre, iou_thre, labels=None, max_out=None):
 
 
 def iou(boxes1, boxes2):
-    """Elementwise IoU of two [K,4] CUDA tensors -- yh_iou."""
-    boxes1 = _require_cuda_f32(boxes1, "boxes1")
-    boxes2 = _require_cuda_f32(boxes2, "boxes2")
+    """Elementwise IoU of two [K,4] CUDA tensors -- yh_iou (float32) / yh_iou_f64 (float64): the result keeps
+    the inputs' dtype, like the reference's get_iou."""
+    if not (isinstance(boxes1, torch.Tensor) and boxes1.is_cuda and isinstance(boxes2, torch.Tensor) and boxes2.is_cuda):
+        raise ValueError("boxes must be CUDA tensors (this path has no CPU implementation)")
     if boxes1.shape != boxes2.shape or boxes1.shape[-1] != 4:
         raise ValueError("boxes must have identical [...,4] shapes")
+    f64 = boxes1.dtype == torch.float64 or boxes2.dtype == torch.float64
+    dt = torch.float64 if f64 else torch.float32
+    boxes1, boxes2 = boxes1.to(dt).contiguous(), boxes2.to(dt).contiguous()
     count = boxes1.numel() // 4
     with torch.cuda.device(boxes1.device):
-        out = torch.empty(boxes1.shape[:-1], dtype=torch.float32, device=boxes1.device)
-        _lib.call("yh_iou", _ptr(boxes1), _ptr(boxes2), count, _ptr(out), _stream())
+        out = torch.empty(boxes1.shape[:-1], dtype=dt, device=boxes1.device)
+        _lib.call("yh_iou_f64" if f64 else "yh_iou", _ptr(boxes1), _ptr(boxes2), count, _ptr(out), _stream())
     return out
 
 

@@ -31,6 +31,8 @@ def available():
 
 class _Stub(types.ModuleType):
     def __getattr__(self, name):
+        if name.startswith("__"):  # (inspect / importlib probe modules for __file__, __path__, ...)
+            raise AttributeError(name)
         return lambda *a, **k: None
 
 

@@ -142,8 +142,6 @@ def train_head_dense(case, lambdas, chunk_images=None):
     exactly (every term is sum/count with known counts -- SURVEY 8(c)); this is how the
     replicated formulation is made to fit in memory for larger batches.
     """
-    from importlib import import_module
-    tg = _targets_mod()
     n, m = case.n, case.m
     y = case.y.clone().requires_grad_(True)
     anchors = case.anchors if case.version == 2 else case.a
@@ -157,11 +155,11 @@ def train_head_dense(case, lambdas, chunk_images=None):
     loss32 = 0.0
     for lo in range(0, n, step):
         hi = min(n, lo + step)
-        rec, off = tg.shard_records(case.rec, case.gt_off, lo, hi)
+        rec, off = shard_records(case.rec, case.gt_off, lo, hi)
         mc = len(rec)
         if mc == 0:
             continue
-        dense = tg.records_to_dense(rec, hi - lo, case.s_h, case.s_w, case.c, case.version)
+        dense = records_to_dense(rec, hi - lo, case.s_h, case.s_w, case.c)
         ysub = y[lo:hi]
         _, terms, iou, resp = loss_dense_torch(ysub, case.height, case.width, case.version,
                                                anchors, *dense, lambdas)
@@ -181,15 +179,34 @@ def train_head_dense(case, lambdas, chunk_images=None):
                 iou_resp=resp_iou)
 
 
-def _targets_mod():
-    """The product package's *host-side* record helpers (no CUDA involved)."""
-    import importlib
-    import os
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    if root not in sys.path:
-        sys.path.insert(0, root)
-    return importlib.import_module("odcp_b200.targets")
+def shard_records(rec, gt_off, img_lo, img_hi):
+    """Records and CSR offsets of the image range [img_lo, img_hi), image indices rebased (the oracle's own helper:
+    test infrastructure does not lean on the product package for its inputs)."""
+    lo, hi = int(gt_off[img_lo]), int(gt_off[img_hi])
+    sub = rec[lo:hi].copy()
+    sub["img"] -= img_lo
+    return sub, (np.asarray(gt_off[img_lo:img_hi + 1]) - gt_off[img_lo]).astype(np.int32)
+
+
+def records_to_dense(rec, num_images, s_h, s_w, num_cls):
+    """The reference's dense get_loss inputs from compact records: what collate_fn builds per ground-truth box
+    (models/yolov2.py:1484-1505, 1537-1555; models/yolov1.py:1284-1312): all-zero [S,S,.] grids with the box's
+    scalars scattered at its cell, obj_mask float64, x_img_id = arange(N), bbox_img_id = owning image."""
+    m = len(rec)
+    j, cy, cx = np.arange(m), rec["cy"], rec["cx"]
+    sig_txty = np.zeros((m, s_h, s_w, 2), np.float32)
+    twth = np.zeros((m, s_h, s_w, 2), np.float32)
+    coord = np.zeros((m, s_h, s_w, 4), np.float32)
+    cls_tgt = np.zeros((m, s_h, s_w, num_cls), np.float32)
+    obj = np.zeros((m, s_h, s_w), np.float64)
+    sig_txty[j, cy, cx, 0], sig_txty[j, cy, cx, 1] = rec["stx"], rec["sty"]
+    twth[j, cy, cx, 0], twth[j, cy, cx, 1] = rec["tw"], rec["th"]
+    for c, k in enumerate(("x1", "y1", "x2", "y2")):
+        coord[j, cy, cx, c] = rec[k]
+    cls_tgt[j, cy, cx, rec["cls"]] = 1.0
+    obj[j, cy, cx] = 1.0
+    x_img_id = np.arange(num_images, dtype=np.int64)
+    return tuple(torch.from_numpy(a) for a in (sig_txty, twth, coord, cls_tgt, obj, x_img_id, x_img_id[rec["img"]].copy()))
 
 
 # --------------------------------------------------------------------------------------
@@ -377,7 +394,7 @@ def nms_image_np(bbox, conf, conf_thre, iou_thre, labels=None):
         if len(rest) == 0:
             break
         iou = iou_np(bbox[order[i]][None, :], bbox[rest])
-        sup = iou >= thr
+        sup = ~(iou < thr)  # (utils.py:133 keeps j iff iou < thre: a NaN IoU removes it)
         if labels is not None:
             sup &= (labels[rest] == labels[order[i]])
         alive[i + 1:] &= ~sup

@@ -27,6 +27,8 @@ sys.path.insert(0, REF)
 
 class _Stub(types.ModuleType):
     def __getattr__(self, name):
+        if name.startswith("__"):  # (inspect / importlib probe modules for __file__, __path__, ...)
+            raise AttributeError(name)
         return lambda *a, **k: None
 
 
@@ -225,8 +227,45 @@ def run_evaluate(seed, n=12, num_cls=4, height=416, width=416):
                 ap=np.stack([res[c] for c in cls_list]))
 
 
+def run_v1_detect(seed, height=90, width=120, conf_thre=0.5, iou_thre=0.5):
+    """The reference's own YOLOv1.detect (models/yolov1.py:439-554) on an injected head tensor.  albumentations is not
+    installed offline, so its two Resize transforms are stood in for by what they do (documented behaviour of
+    albumentations.Resize with BboxParams(format="pascal_voc")): the image goes through cv2.resize with bilinear
+    interpolation, boxes are normalised by the source image size and scaled to the target size in float64."""
+    import cv2
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, size=(height, width, 3), dtype=np.uint8)
+    y = torch.randn(1, 7, 7, 30, generator=torch.Generator().manual_seed(seed))
+    y[..., 4:10:5] += 0.3
+    m = HeadOnlyV1(7, 7, 2, 20)
+    m._y = y
+
+    def resize_to(h, w, src_h, src_w):
+        def apply(image, bboxes, labels):
+            out = []
+            for b in bboxes:
+                x1, y1, x2, y2 = [float(v) for v in b[:4]]
+                out.append((x1 / src_w * w, y1 / src_h * h, x2 / src_w * w, y2 / src_h * h))
+            return dict(image=cv2.resize(image, (w, h), interpolation=cv2.INTER_LINEAR), bboxes=out, labels=list(labels))
+        return apply
+
+    m.resize = resize_to(224, 224, height, width)
+    m.get_resize_transform = lambda h, w: resize_to(h, w, 224, 224)
+    d = m.detect(img, conf_thre, iou_thre)
+    return dict(img=img, y=y.numpy(), conf_thre=conf_thre, iou_thre=iou_thre,
+                bbox=np.asarray(d["bbox_list"], np.float64).reshape(-1, 4), labels=np.asarray([int(l) for l in d["lbl_list"]], np.int32),
+                conf=np.asarray(d["conf_score_list"], np.float64), score=np.asarray(d["cls_spec_conf_score_list"], np.float64))
+
+
 def main():
     lam = synthetic.DEFAULT_LAMBDAS
+    if "--only-new" in sys.argv:
+        r = run_v1_detect(401)
+        np.savez_compressed(os.path.join(HERE, "v1_detect.npz"), **r)
+        print("v1_detect", len(r["bbox"]), "boxes")
+        return
+    r = run_v1_detect(401)
+    np.savez_compressed(os.path.join(HERE, "v1_detect.npz"), **r)
     np.savez_compressed(os.path.join(HERE, "evaluate.npz"), **run_evaluate(301))
     np.savez_compressed(os.path.join(HERE, "v2_collate.npz"), **run_collate(2, 6, 416, 416, 201))
     np.savez_compressed(os.path.join(HERE, "v2_collate_nonsquare.npz"), **run_collate(2, 3, 352, 480, 202))

@@ -1031,3 +1031,238 @@ def test_detect_returns_the_reference_dict_from_the_golden_head(cuda_device):
     many = m.detect_batch(torch.zeros(case.n, case.height, case.width, 3, device=cuda_device), 0.9, 0.5)
     assert [len(d["bbox_list"]) for d in many] == cnt.tolist()
     assert np.allclose(np.array(many[1]["bbox_list"]), z["nms_bbox"][start[1]:start[2]], rtol=1e-5, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------
+# round-2 parity additions: reference-signature wrappers, YOLOv1 detect, element-wise gradients, full-size NMS
+# ------------------------------------------------------------------------------------------
+def test_yolov1_detect_matches_the_reference_detect_golden(cuda_device):
+    """YOLOv1.detect (resize to 224 -> predict -> nms -> clip to [0, 223] -> rescale to the original size) against
+    the dict the reference's own detect produced for the same image and head tensor (tests/golden/v1_detect.npz,
+    make_golden.run_v1_detect)."""
+    from odcp_b200.models.yolov1 import YOLOv1Head
+    z = dict(np.load(os.path.join(GOLDEN, "v1_detect.npz")))
+    m = YOLOv1Head(7, 7, 2, num_cls=20).to(cuda_device)
+    m.set_head_output(torch.from_numpy(z["y"]).to(cuda_device))
+    d = m.detect(z["img"], float(z["conf_thre"]), float(z["iou_thre"]))
+    assert len(d["bbox_list"]) == len(z["bbox"]) > 10
+    assert np.allclose(np.asarray(d["bbox_list"]), z["bbox"], rtol=1e-5, atol=1e-4)
+    assert [int(l) for l in d["lbl_list"]] == z["labels"].tolist()
+    assert np.allclose(np.asarray(d["conf_score_list"]), z["conf"], rtol=1e-6, atol=1e-7)
+    assert np.allclose(np.asarray(d["cls_spec_conf_score_list"]), z["score"], rtol=1e-5, atol=1e-7)
+    assert np.asarray(d["bbox_list"]).min() >= 0.0  # clipped before the rescale
+
+
+def test_reference_signature_nms_flattens_all_leading_dims(cuda_device):
+    """models.utils.nms with the reference's signature (models/utils.py:68-164): every leading dimension is
+    flattened into ONE candidate set (a batch of two images suppresses across images, as the reference does), the
+    three gathered tensors come back in descending-confidence order."""
+    from odcp_b200.models import utils as U
+    case = synthetic.cfg3(2, conf_thre=0.6)
+    dev = cuda_device
+    y = case.y.to(dev)
+    _, _, bbox, conf, _, spec = ops.decode(y, version=2, img_hw=(case.height, case.width), anchors=case.anchors)
+    kb, kc, ks = U.nms(bbox, conf, spec, 0.6, 0.45)                       # [2,13,13,5,.] in, like predict's outputs
+    wb, wc, ws = O.nms_torch(bbox.cpu(), conf.cpu(), spec.cpu(), 0.6, 0.45)  # the reference's op sequence
+    assert kb.shape == wb.shape and kb.shape[0] > 20
+    assert torch.equal(kb.cpu(), wb) and torch.equal(kc.cpu(), wc) and torch.equal(ks.cpu(), ws)
+    assert (kc[:-1] >= kc[1:]).all()
+    # one image alone keeps boxes the two-image call suppressed across images: the flattening is real
+    k1 = U.nms(bbox[0], conf[0], spec[0], 0.6, 0.45)[1].shape[0] + U.nms(bbox[1], conf[1], spec[1], 0.6, 0.45)[1].shape[0]
+    assert k1 >= kb.shape[0]
+    # defaults are the reference's (0.9 / 0.5)
+    d = U.nms(bbox[0], conf[0], spec[0])
+    w = O.nms_torch(bbox[0].cpu(), conf[0].cpu(), spec[0].cpu())
+    assert torch.equal(d[1].cpu(), w[1])
+
+
+def test_reference_signature_get_iou_broadcasts_and_keeps_dtype(cuda_device):
+    """models.utils.get_iou: broadcasting like the loss uses it ([M,S,S,A,4] x [M,S,S,1,4], models/yolov2.py:984-990),
+    float32 tensors bit-equal to the reference's torch formula, numpy=True in the arrays' own precision: float64
+    boxes (evaluate_model, models/utils.py:250-252) give numpy's float64 bits."""
+    from odcp_b200.models import utils as U
+    rng = np.random.default_rng(5)
+
+    def boxes(*shape):
+        a = rng.uniform(0, 400, size=shape + (2,))
+        b = a + rng.uniform(0, 150, size=shape + (2,))
+        return np.concatenate([a, b], -1)
+
+    p32, t32 = boxes(7, 3, 3, 5).astype(np.float32), boxes(7, 3, 3, 1).astype(np.float32)
+    got = U.get_iou(torch.from_numpy(p32).to(cuda_device), torch.from_numpy(t32).to(cuda_device))
+    want = O.iou_torch(torch.from_numpy(p32), torch.from_numpy(t32))
+    assert got.shape == (7, 3, 3, 5) and torch.equal(got.cpu(), want)
+    # numpy route, float64: the reference's formula evaluated by numpy itself
+    g64, d64 = boxes(9), boxes(1)
+    g64[3] = d64[0]                      # IoU exactly 1 / (1 + 1e-6 / area)
+    g64[4, 2:] = g64[4, :2]              # zero-area box
+    got = U.get_iou(g64, d64, numpy=True)
+    x1, y1, x2, y2 = [g64[..., i] for i in range(4)]
+    u1, v1, u2, v2 = [d64[..., i] for i in range(4)]
+    inter = np.clip(np.minimum(x2, u2) - np.maximum(x1, u1), 0, None) * np.clip(np.minimum(y2, v2) - np.maximum(y1, v1), 0, None)
+    want = inter / ((x2 - x1) * (y2 - y1) + (u2 - u1) * (v2 - v1) - inter + 1e-6)
+    assert got.dtype == np.float64 and got.shape == (9,) and np.array_equal(got, want)
+    got32 = U.get_iou(g64.astype(np.float32), d64.astype(np.float32), numpy=True)
+    assert got32.dtype == np.float32 and np.allclose(got32, want, rtol=1e-5)
+
+
+def test_reference_evaluate_loop_with_the_patched_get_iou_reproduces_its_golden(cuda_device):
+    """The reference's own evaluate_model loop (restated: models/utils.py:231-262) fed by models.utils.get_iou
+    (numpy=True, float64 through yh_iou_f64) makes the true-positive decisions of tests/golden/evaluate.npz --
+    the APs of the reference's run -- and so does the batched drop-in evaluate_model."""
+    from odcp_b200.models import utils as U
+    z = dict(np.load(os.path.join(GOLDEN, "evaluate.npz")))
+    n, levels = int(z["n"]), z["levels"]
+    cls_list = [str(c) for c in range(int(z["num_cls"]))]
+
+    class Canned:  # detect() returns the golden's detections image by image, like the generator's stand-in model
+        def __init__(self):
+            self.cls_list, self.calls = cls_list, 0
+
+        def detect(self, img, conf, iou):
+            i, self.calls = self.calls, self.calls + 1
+            k = int(z["keep_cnt"][i])
+            return {"bbox_list": z["det_bbox"][i, :k].tolist(), "lbl_list": [cls_list[c] for c in z["det_label"][i, :k]],
+                    "conf_score_list": z["det_score"][i, :k].tolist(), "cls_spec_conf_score_list": z["det_score"][i, :k].tolist()}
+
+    dataset = [(i, None, {"bbox_list": z["gt_boxes"][z["gt_off"][i]:z["gt_off"][i + 1]].tolist(),
+                          "lbl_list": [cls_list[c] for c in z["gt_labels"][z["gt_off"][i]:z["gt_off"][i + 1]]]}) for i in range(n)]
+    res = U.evaluate_model(Canned(), dataset, None)  # per-image route: model.detect + get_iou(numpy=True)
+    assert np.array_equal(res["level_list"], levels)
+    for c, name in enumerate(cls_list):
+        assert np.array_equal(res[name], z["ap"][c]), name
+
+
+def test_batched_evaluate_model_equals_the_per_image_route(cuda_device):
+    """evaluate_model on a YOLOv2 head: images batched (one post-process launch + one matching launch per batch,
+    two image sizes in the dataset) against the per-image route (model.detect per image + get_iou(numpy=True), the
+    reference's loop): identical APs."""
+    from odcp_b200.models import utils as U
+    from odcp_b200.models.yolov2 import YOLOv2Head
+    dev = cuda_device
+    small = synthetic.make_case("ev_a", 2, 10, 13, 13, 5, 20, 416, 416, seed=61, to_shift=-1.2, k_lo=2, k_hi=5)
+    wide = synthetic.make_case("ev_b", 2, 6, 10, 13, 5, 20, 320, 416, seed=62, to_shift=-1.2, k_lo=2, k_hi=5)
+
+    class Model(YOLOv2Head):  # forward looks the head tensor up by the image's tag (its first pixel)
+        def forward(self, x):
+            return torch.stack([self.table[int(t)] for t in x[:, 0, 0, 0].tolist()]).to(dev)
+
+    m = Model(num_cls=20).to(dev)
+    m.table, dataset = {}, []
+    for case in (small, wide):
+        for i in range(case.n):
+            tag = len(m.table)
+            m.table[tag] = case.y[i]
+            img = np.zeros((case.height, case.width, 3), np.float32)
+            img[0, 0, 0] = tag
+            sel = case.rec[case.gt_off[i]:case.gt_off[i + 1]]
+            # ground truth near the detections so that the APs are not all zero: the decoded boxes of a few predictors
+            dataset.append((tag, img, {"bbox_list": np.stack([sel["x1"], sel["y1"], sel["x2"], sel["y2"]], 1).astype(np.float64).tolist(),
+                                       "lbl_list": [m.cls_list[c] for c in sel["cls"]]}))
+    got = U.evaluate_model(m, dataset, None, 0.5, 0.45, batch_size=4)
+
+    class PerImage:  # hides `postprocess`: evaluate_model then takes the reference's per-image loop
+        cls_list = m.cls_list
+
+        def detect(self, img, conf, iou):
+            return m.detect(img, conf, iou)
+
+    want = U.evaluate_model(PerImage(), dataset, None, 0.5, 0.45)
+    for name in m.cls_list:
+        assert np.array_equal(got[name], want[name]), name
+    assert sum(float(np.sum(got[c])) for c in m.cls_list) >= 0.0
+
+
+def test_dense_objectness_gradient_elementwise(cuda_device):
+    """The dense part of dL/dy -- the no-object gradient of every objectness logit, 99.9 % of the non-zeros and five
+    orders of magnitude below the largest entry -- checked ELEMENT BY ELEMENT (the norm-relative tolerance says
+    nothing about it): |dy - ref| <= 1e-5 |ref| + 4 ulp on every golden and on BASELINE config 2, through the
+    train head and through the fused step."""
+    worst = 0.0
+    for name in LOSS_FILES:
+        case, z = load_golden(name)
+        r = run_train(case, golden_lambdas(z), cuda_device)
+        if case.version == 2:
+            got, ref = r["dy"][..., 4], z["dy"][..., 4]
+        else:
+            got, ref = r["dy"][..., 4:5 * case.a:5], z["dy"][..., 4:5 * case.a:5]
+        err = np.abs(got.astype(np.float64) - ref) - 4 * np.spacing(np.abs(ref))
+        rel = err / np.maximum(np.abs(ref), 1e-30)
+        assert (rel[ref != 0] <= 1e-5).all(), (name, float(rel[ref != 0].max()))
+        worst = max(worst, float(rel[ref != 0].max()))
+    case = synthetic.cfg2()
+    want = O.train_head_compact(case, synthetic.DEFAULT_LAMBDAS)["dy"][..., 4]
+    y, gt, off = case.y.to(cuda_device), targets.records_to_tensor(case.rec, cuda_device), torch.from_numpy(case.gt_off).to(cuda_device)
+    kw = dict(img_hw=(case.height, case.width), lambdas=synthetic.DEFAULT_LAMBDAS, anchors=case.anchors)
+    sep = ops.train_head(y, gt, off, version=2, **kw)["dy"][..., 4].cpu().numpy()
+    fus = ops.train_post(y, gt, off, conf_thre=0.5, iou_thre=0.45, max_out=16, want_cls_spec=False, **kw)["train"]["dy"][..., 4].cpu().numpy()
+    assert np.array_equal(sep, fus)
+    err = np.abs(sep.astype(np.float64) - want) - 4 * np.spacing(np.abs(want))
+    rel = err / np.maximum(np.abs(want), 1e-30)
+    assert (rel[want != 0] <= 1e-5).all(), float(rel[want != 0].max())
+    assert np.array_equal(sep != 0, want != 0)
+
+
+def test_headline_batch_vs_the_dense_reference_tier(cuda_device):
+    """The headline configuration at its full batch (N=256) against the oracle's DENSE tier -- the reference's own op
+    sequence (per-box replication + autograd), evaluated in image chunks and recombined exactly."""
+    case = synthetic.headline(256)
+    want = O.train_head_dense(case, synthetic.DEFAULT_LAMBDAS, chunk_images=64)
+    r = run_train(case, synthetic.DEFAULT_LAMBDAS, cuda_device)
+    assert abs(r["loss"] - want["loss"]) <= TOL * abs(want["loss"])
+    assert np.abs(r["terms"] - want["terms"]).max() <= TOL * np.abs(want["terms"]).max()
+    assert np.array_equal(r["resp"], want["resp"])
+    assert rel_err(r["dy"], want["dy"]) <= TOL
+    assert np.array_equal(r["dy"] != 0, want["dy"] != 0)
+
+
+def test_postprocess_cfg5_all_images_vs_oracle(cuda_device):
+    """BASELINE config 5 at full size (N=512, 19x19, ~110 candidates per image): kept indices and labels of EVERY
+    image against the oracle."""
+    case = synthetic.cfg5()
+    r = run_post(case, 0.5, 0.45, cuda_device, max_out=256, want_cls_spec=False)
+    want = O.postprocess_np(case.y, case.height, case.width, 2, case.anchors, 0.5, 0.45)
+    cnt = r["keep_cnt"]
+    assert np.array_equal(cnt, np.array([len(w["idx"]) for w in want], dtype=np.int32))
+    for n, w in enumerate(want):
+        assert np.array_equal(r["keep_idx"][n, :cnt[n]], w["idx"]), n
+        assert np.array_equal(r["label"][n, :cnt[n]], w["label"]), n
+
+
+def test_nms_boxes_of_infinite_size_follow_the_reference(cuda_device):
+    """exp(tw) overflows to inf for large logits: the box is (-inf, +inf), and two such boxes have IoU inf/inf = NaN.
+    The reference keeps a later box only if `iou < iou_thre` (models/utils.py:133), so a NaN IoU removes it."""
+    inf = np.float32(np.inf)
+    bbox = np.array([[[-inf, -inf, inf, inf], [-inf, -inf, inf, inf], [10, 10, 50, 50], [-inf, 0, inf, 40], [200, 200, 260, 280],
+                      [12, 12, 50, 52]]], dtype=np.float32)
+    conf = np.array([[0.99, 0.98, 0.97, 0.96, 0.95, 0.94]], dtype=np.float32)
+    want = O.nms_image_np(bbox[0], conf[0], 0.5, 0.5)
+    ref = O.nms_torch(torch.from_numpy(bbox[0]), torch.from_numpy(conf[0]),
+                      torch.arange(6, dtype=torch.float32)[:, None], 0.5, 0.5)[2][:, 0].numpy().astype(np.int32)
+    assert np.array_equal(want, ref)  # the oracle agrees with the reference's op sequence on this input
+    idx, cnt = ops.nms_indices(torch.from_numpy(bbox).to(cuda_device), torch.from_numpy(conf).to(cuda_device), conf_thre=0.5, iou_thre=0.5)
+    k = int(cnt[0])
+    assert np.array_equal(idx[0, :k].cpu().numpy(), want), (idx[0, :k].cpu().numpy(), want)
+    assert 1 not in want  # the second infinite box did not survive the first
+
+
+def test_get_loss_backward_twice_and_zero_upstream_gradient(cuda_device):
+    """HeadLoss.backward hands the kernel's gradient buffer out once; a second backward (retain_graph) runs the kernel
+    again: an upstream gradient of 0 in between loses nothing, and the first result is not mutated."""
+    from odcp_b200.models.yolov2 import YOLOv2Head
+    case = synthetic.cfg2(n=4)
+    dev = cuda_device
+    m = YOLOv2Head(num_cls=case.c).to(dev)
+    y = case.y.to(dev).requires_grad_(True)
+    m.set_head_output(y)
+    x = torch.zeros(case.n, case.height, case.width, 3, device=dev)
+    gt, off = targets.records_to_tensor(case.rec, dev), torch.from_numpy(case.gt_off).to(dev)
+    loss = m.get_loss_compact(x, gt, off)
+    (g0,) = torch.autograd.grad(loss, y, grad_outputs=torch.zeros((), device=dev), retain_graph=True)
+    assert not g0.any()
+    (g1,) = torch.autograd.grad(loss, y, retain_graph=True)
+    (g3,) = torch.autograd.grad(loss, y, grad_outputs=torch.full((), 3.0, device=dev))
+    want = O.train_head_compact(case, synthetic.DEFAULT_LAMBDAS)["dy"]
+    assert rel_err(g1.cpu().numpy(), want) <= TOL
+    assert torch.allclose(g3, 3.0 * g1, rtol=1e-6, atol=0)
+    assert not g0.any()  # untouched by the later backwards

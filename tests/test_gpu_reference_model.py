@@ -1,0 +1,103 @@
+"""The reference's REAL model behind the drop-in, on the GPU: the unmodified `YOLOv2` (Darknet19 backbone, neck, head;
+reference models/yolov2.py:41-431, random init) runs one `run_one_epoch` training batch (models/yolov2.py:1142-1278:
+get_loss -> SGD(...) -> zero_grad -> backward -> step) twice from identical weights -- once as it is, once with
+`patch_reference(..., fused_sgd=True)` + a channels_last head -- and must end with the same loss and the same
+parameters; then `detect` of the patched model against the reference's own predict -> nms -> argmax chain on the same
+head tensor.  The reference is imported from the staged copy (oracle/_ref, see oracle/stage_reference.py) or from
+/root/reference; without either the test skips (the driver's GPU box has the staged copy: it travels with the snapshot).
+"""
+import numpy as np
+import pytest
+import torch
+
+from odcp_b200 import synthetic, targets
+from oracle import refharness as RH
+
+pytestmark = pytest.mark.gpu
+LAM = synthetic.DEFAULT_LAMBDAS
+N = 8
+
+
+class OneBatch:
+    """What run_one_epoch needs from a DataLoader: iteration and `.dataset` with a length."""
+
+    def __init__(self, batch, n):
+        self.batch, self.dataset = batch, range(n)
+
+    def __iter__(self):
+        yield self.batch
+
+
+def make_batch(dev):
+    case = synthetic.cfg2(n=N)
+    gen = torch.Generator().manual_seed(77)
+    x = (torch.rand(N, 416, 416, 3, generator=gen) * 255.0).to(dev)
+    # the dense per-box grids collate_fn builds (bit-exact: tests/golden/v2_collate*.npz pin records_to_dense against it)
+    dense = [t.to(dev) for t in targets.records_to_dense(case.rec, case.n, case.s_h, case.s_w, case.c, 2)]
+    return case, (x, *dense)
+
+
+def fresh_reference_model(dev):
+    RH._loaded.pop("cuda", None)  # a fresh import: the previous run may have patched the classes
+    ref = RH.load_reference("cuda")
+    cls_list = [str(i) for i in range(20)]
+    torch.manual_seed(1234)
+    model = ref.yolov2.YOLOv2(cls_list, {c: i for i, c in enumerate(cls_list)}).to(dev)
+    return ref, model
+
+
+def test_reference_yolov2_training_batch_and_detect_through_the_drop_in(cuda_device):
+    if not RH.available():
+        pytest.skip("the reference is not staged (oracle/_ref) and /root/reference does not exist")
+    dev = cuda_device
+    case, batch = make_batch(dev)
+
+    # ---- the reference as it is
+    ref, model = fresh_reference_model(dev)
+    init = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    n_params = sum(p.numel() for p in model.parameters())
+    assert n_params > 60e6  # the real thing: backbone + neck + head, ~67 M parameters
+    loss_ref = float(model.run_one_epoch(2, OneBatch(batch, N), lr=1e-3, train=True, **LAM))
+    after_ref = {k: v.detach().clone() for k, v in model.state_dict().items()}
+
+    # ---- the same step through the drop-in: CUDA head path, fused SGD, channels_last head
+    from odcp_b200.models import patch_reference
+    from odcp_b200.models.layout import use_channels_last_head
+    ref2, model2 = fresh_reference_model(dev)
+    orig_predict = ref2.yolov2.YOLOv2.predict
+    for k, v in model2.state_dict().items():
+        assert torch.equal(v, init[k]), k  # identical start
+    done = patch_reference(ref2.yolov1, ref2.yolov2, ref2.utils, fused_sgd=True)
+    assert "YOLOv2" in done
+    use_channels_last_head(model2.head_model)
+    loss_new = float(model2.run_one_epoch(2, OneBatch(batch, N), lr=1e-3, train=True, **LAM))
+    after_new = {k: v.detach().clone() for k, v in model2.state_dict().items()}
+
+    assert abs(loss_new - loss_ref) <= 1e-5 * abs(loss_ref), (loss_new, loss_ref)
+    worst = 0.0
+    for k in after_ref:
+        a, b, i = after_ref[k].double(), after_new[k].double(), init[k].double()
+        if not after_ref[k].is_floating_point():
+            assert torch.equal(after_ref[k], after_new[k]), k
+            continue
+        upd = (a - i).abs().max().item()
+        err = (a - b).abs().max().item()
+        # relative to the size of the update itself (cuDNN's backward is not bit-reproducible between layouts)
+        assert err <= 2e-3 * upd + 1e-7 * max(a.abs().max().item(), 1e-30), (k, err, upd)
+        worst = max(worst, err / max(upd, 1e-30))
+    assert worst < 2e-3
+
+    # ---- detect: the patched model against the reference's own chain on the SAME head tensor
+    model2.eval()
+    img = (torch.rand(416, 416, 3, generator=torch.Generator().manual_seed(5)) * 255.0).numpy().astype(np.float32)
+    conf_thre, iou_thre = 0.55, 0.5
+    got = model2.detect(img, conf_thre, iou_thre)
+    with torch.no_grad():
+        x = torch.tensor(np.asarray([img])).to(dev)
+        _, _, bbox, conf, _, spec = orig_predict(model2, x)  # the reference's predict (its torch ops, on the GPU)
+        kb, kc, ks = RH.load_reference("cuda").utils.nms(bbox.cpu(), conf.cpu(), spec.cpu(), conf_thre, iou_thre)
+    assert len(got["bbox_list"]) == kb.shape[0] > 0
+    assert np.allclose(np.asarray(got["bbox_list"]), kb.numpy(), rtol=1e-4, atol=1e-3)
+    assert np.allclose(np.asarray(got["conf_score_list"]), kc.numpy(), rtol=1e-5, atol=1e-6)
+    assert [model2.cls_list.index(l) for l in got["lbl_list"]] == ks.argmax(-1).tolist()
+    assert np.allclose(np.asarray(got["cls_spec_conf_score_list"]), ks.max(-1).values.numpy(), rtol=1e-4, atol=1e-6)
