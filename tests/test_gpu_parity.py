@@ -1173,23 +1173,35 @@ def test_batched_evaluate_model_equals_the_per_image_route(cuda_device):
     assert sum(float(np.sum(got[c])) for c in m.cls_list) >= 0.0
 
 
+def elementwise_bound(ref, to_logit):
+    """Element-wise tolerance for the no-object gradient g = K conf^2 (1 - conf) of an objectness logit: 1e-5
+    relative, plus what 4 ulp of the fp32 confidence do to it through dg/dconf -- the reference's own sigmoid is
+    rounded to fp32 before autograd forms (1 - conf), so for saturated logits (conf -> 1) neither side knows the
+    value better than eps32 * (2 - 3 conf) / (1 - conf) relative."""
+    c = 1.0 / (1.0 + np.exp(-to_logit.astype(np.float64)))
+    cond = np.abs(2.0 - 3.0 * c) / np.maximum(1.0 - c, 1e-12)
+    return np.abs(ref) * (1e-5 + 4 * 2.0 ** -24 * cond)
+
+
 def test_dense_objectness_gradient_elementwise(cuda_device):
     """The dense part of dL/dy -- the no-object gradient of every objectness logit, 99.9 % of the non-zeros and five
     orders of magnitude below the largest entry -- checked ELEMENT BY ELEMENT (the norm-relative tolerance says
-    nothing about it): |dy - ref| <= 1e-5 |ref| + 4 ulp on every golden and on BASELINE config 2, through the
-    train head and through the fused step."""
+    nothing about it) on every golden and on BASELINE config 2, through the train head and through the fused step;
+    the worst element relative to its bound is reported."""
     worst = 0.0
     for name in LOSS_FILES:
         case, z = load_golden(name)
         r = run_train(case, golden_lambdas(z), cuda_device)
-        if case.version == 2:
-            got, ref = r["dy"][..., 4], z["dy"][..., 4]
-        else:
-            got, ref = r["dy"][..., 4:5 * case.a:5], z["dy"][..., 4:5 * case.a:5]
-        err = np.abs(got.astype(np.float64) - ref) - 4 * np.spacing(np.abs(ref))
-        rel = err / np.maximum(np.abs(ref), 1e-30)
-        assert (rel[ref != 0] <= 1e-5).all(), (name, float(rel[ref != 0].max()))
-        worst = max(worst, float(rel[ref != 0].max()))
+        sl = (Ellipsis, 4) if case.version == 2 else (Ellipsis, slice(4, 5 * case.a, 5))
+        got, ref, to = r["dy"][sl], z["dy"][sl], case.y.numpy()[sl]
+        # (cells that carry a record hold the record's objectness gradient as well: those are covered by the
+        #  norm-relative checks; here only logits whose gradient is purely the no-object term)
+        pure = np.ones(ref.shape, bool)
+        rec = case.rec
+        pure[rec["img"], rec["cy"], rec["cx"]] = False
+        ratio = np.abs(got.astype(np.float64) - ref)[pure] / np.maximum(elementwise_bound(ref, to)[pure], 1e-300)
+        assert (ratio[ref[pure] != 0] <= 1.0).all(), (name, float(ratio.max()))
+        worst = max(worst, float(ratio[ref[pure] != 0].max()))
     case = synthetic.cfg2()
     want = O.train_head_compact(case, synthetic.DEFAULT_LAMBDAS)["dy"][..., 4]
     y, gt, off = case.y.to(cuda_device), targets.records_to_tensor(case.rec, cuda_device), torch.from_numpy(case.gt_off).to(cuda_device)
@@ -1197,10 +1209,15 @@ def test_dense_objectness_gradient_elementwise(cuda_device):
     sep = ops.train_head(y, gt, off, version=2, **kw)["dy"][..., 4].cpu().numpy()
     fus = ops.train_post(y, gt, off, conf_thre=0.5, iou_thre=0.45, max_out=16, want_cls_spec=False, **kw)["train"]["dy"][..., 4].cpu().numpy()
     assert np.array_equal(sep, fus)
-    err = np.abs(sep.astype(np.float64) - want) - 4 * np.spacing(np.abs(want))
-    rel = err / np.maximum(np.abs(want), 1e-30)
-    assert (rel[want != 0] <= 1e-5).all(), float(rel[want != 0].max())
+    pure = np.ones(want.shape, bool)
+    pure[case.rec["img"], case.rec["cy"], case.rec["cx"]] = False
+    ratio = np.abs(sep.astype(np.float64) - want)[pure] / np.maximum(elementwise_bound(want, case.y.numpy()[..., 4])[pure], 1e-300)
+    assert (ratio[want[pure] != 0] <= 1.0).all(), float(ratio.max())
     assert np.array_equal(sep != 0, want != 0)
+    # and the plain statement for everything that is not saturated (conf <= 0.9): 2e-6 relative, element by element
+    mid = pure & (case.y.numpy()[..., 4] < 2.0) & (want != 0)
+    assert (np.abs(sep.astype(np.float64) - want)[mid] <= 2e-6 * np.abs(want[mid])).all()
+    print("worst element / bound: %.3f" % max(worst, float(ratio.max())))
 
 
 def test_headline_batch_vs_the_dense_reference_tier(cuda_device):
