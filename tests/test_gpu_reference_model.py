@@ -46,6 +46,17 @@ def fresh_reference_model(dev):
     return ref, model
 
 
+def widest_gap_midpoint(values, q=None, lo=None, hi=None):
+    """Middle of the widest gap between consecutive sorted `values` inside [lo, hi] (or between two quantiles)."""
+    v = np.sort(np.asarray(values, dtype=np.float64))
+    if q is not None:
+        lo, hi = np.quantile(v, q[0]), np.quantile(v, q[1])
+    v = np.concatenate([[lo], v[(v > lo) & (v < hi)], [hi]])
+    i = int(np.argmax(np.diff(v)))
+    assert v[i + 1] - v[i] > 1e-5, "no usable gap"
+    return float(0.5 * (v[i] + v[i + 1]))
+
+
 def test_reference_yolov2_training_batch_and_detect_through_the_drop_in(cuda_device):
     if not RH.available():
         pytest.skip("the reference is not staged (oracle/_ref) and /root/reference does not exist")
@@ -90,13 +101,22 @@ def test_reference_yolov2_training_batch_and_detect_through_the_drop_in(cuda_dev
     # ---- detect: the patched model against the reference's own chain on the SAME head tensor
     model2.eval()
     img = (torch.rand(416, 416, 3, generator=torch.Generator().manual_seed(5)) * 255.0).numpy().astype(np.float32)
-    conf_thre, iou_thre = 0.5, 0.5
-    got = model2.detect(img, conf_thre, iou_thre)
     with torch.no_grad():
         x = torch.tensor(np.asarray([img])).to(dev)
         _, _, bbox, conf, _, spec = orig_predict(model2, x)  # the reference's predict (its torch ops, on the GPU)
         RH._loaded.pop("cpu", None)  # a fresh, unpatched import of the reference's utils: ITS nms (CPU only)
-        kb, kc, ks = RH.load_reference("cpu").utils.nms(bbox.cpu(), conf.cpu(), spec.cpu(), conf_thre, iou_thre)
+        ref_utils = RH.load_reference("cpu").utils
+    # Thresholds the comparison is well-posed for: torch's CUDA sigmoid/exp and the kernel's differ in the last ulp, and
+    # a random-init head puts every objectness next to 0.5, so a threshold ON a confidence (or on a pair's IoU) would
+    # test rounding, not the path (north_star: ties within 1 ulp of a threshold are excluded).  Both thresholds are put
+    # in the middle of the widest gap of the values they are compared with.
+    conf_thre = widest_gap_midpoint(conf.flatten().cpu().numpy().astype(np.float64), q=(0.85, 0.95))
+    cand = bbox.reshape(-1, 4)[conf.flatten() >= conf_thre].cpu().numpy().astype(np.float64)
+    assert 20 <= cand.shape[0] <= 200, cand.shape
+    pair_iou = ref_utils.get_iou(cand[:, None, :], cand[None, :, :], numpy=True)[np.triu_indices(cand.shape[0], 1)]
+    iou_thre = widest_gap_midpoint(pair_iou, lo=0.35, hi=0.65)
+    got = model2.detect(img, conf_thre, iou_thre)
+    kb, kc, ks = ref_utils.nms(bbox.cpu(), conf.cpu(), spec.cpu(), conf_thre, iou_thre)
     assert len(got["bbox_list"]) == kb.shape[0] > 0
     assert np.allclose(np.asarray(got["bbox_list"]), kb.numpy(), rtol=1e-4, atol=1e-3)
     assert np.allclose(np.asarray(got["conf_score_list"]), kc.numpy(), rtol=1e-5, atol=1e-6)
