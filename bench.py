@@ -115,7 +115,8 @@ def run_description(sets, set_bytes, fused, collective):
                     "CONTRACT) and runs next to the tails of the kernels in front of it; the first call of every "
                     "pass waits for everything before it" % sets),
         "timing": ("the timed K-step region is rehearsed twice (its own graphs), starts behind a device-side gate "
-                   "kernel and is repeated; value = the median region, max over ranks per region"),
+                   "kernel (N > 1: and a one-float all-reduce that lines the ranks' streams up, both before the start "
+                   "event) and is repeated; value = the median region, max over ranks per region"),
     }
     if collective is not None:
         run["collective"] = collective
@@ -480,12 +481,19 @@ def main():
         sm_hz = 1e6 * float(torch.cuda.get_device_properties(dev).clock_rate) / 1e3  # clock_rate is in kHz
         gate_cycles = int(args.gate_us * 1e-6 * sm_hz)
 
+        align = torch.zeros(1, device=dev)
+
         def timed_region(ev0, ev1, full=g_full):
             """Exactly K steps between two events.  A gate kernel keeps the GPU busy while the host
             enqueues ev0, the graph launches and ev1: the region then starts with its first kernel already
             queued behind the event (no idle-GPU launch latency inside it)."""
             if gate_cycles > 0:
                 torch.cuda._sleep(gate_cycles)
+            if dist is not None:
+                # the ranks leave the host barrier tens of microseconds apart; a tiny all-reduce on the stream (outside
+                # the region) lines their streams up to a few microseconds, so a short region measures the steps and
+                # not the wait of the early ranks' exchange for the late ones
+                dist.all_reduce(align)
             ev0.record(stream)
             run_steps(K, full)
             ev1.record(stream)
