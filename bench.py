@@ -42,8 +42,8 @@ FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, only if MEASU
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4000)
-    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=0, help="0: 4000 (headline, cfg5) / 30 (cfg4)")
+    ap.add_argument("--warmup", type=int, default=-1, help="-1: 50 (headline, cfg5) / 5 (cfg4)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (0: the workload's own: 256 / 512)")
     ap.add_argument("--sets", type=int, default=8, help="rotating buffer sets (total must exceed L2)")
@@ -70,7 +70,15 @@ def parse_args():
     ap.add_argument("--gate-us", type=float, default=150.0,
                     help="device-side gate in front of every timed region: the GPU spins this long while the host "
                          "enqueues the start event, the K steps and the stop event, so the region holds no launch gap")
-    return ap.parse_args()
+    ap.add_argument("--torch-sgd", action="store_true", help="cfg4: torch.optim.SGD instead of the fused SGD step")
+    ap.add_argument("--bucket-mb", type=int, default=0, help="cfg4: DDP bucket size (0: DDP's default, 25 MB)")
+    args = ap.parse_args()
+    heavy = args.workload == "cfg4"
+    if args.steps <= 0:
+        args.steps = 30 if heavy else 4000
+    if args.warmup < 0:
+        args.warmup = 5 if heavy else 50
+    return args
 
 
 def _headline_case(n):
@@ -88,6 +96,9 @@ WORKLOADS = {
                      cands="~50 of 845", name="yolov2_head_13x13x5_c20"),
     "cfg5": dict(case=_cfg5_case, batch=512, grid=[19, 19], image=[608, 608], boxes="U{50..100}",
                  cands="~100 of 1805", name="yolov2_head_19x19x5_c20_dense_gt"),
+    # BASELINE config 4: the full training step (run_cfg4 below; its own metric)
+    "cfg4": dict(case=None, batch=64, grid=[13, 13], image=[416, 416], boxes="U{1..5}", cands="-",
+                 name="yolov2_full_training_step"),
 }
 
 
@@ -201,6 +212,192 @@ def run_reference(args):
     }
     emit(line)
 
+
+
+# ------------------------------------------------------------------------------------------
+# BASELINE config 4: the full YOLOv2 training step, batch-sharded under DDP
+# ------------------------------------------------------------------------------------------
+CFG4_METRIC = "yolov2_train_step_images_per_sec"
+
+
+def cfg4_config(batch):
+    return {"workload": "yolov2_darknet19_416_b%d_full_training_step(cudnn_convs+fused_head+backward+ddp_allreduce+sgd)" % batch,
+            "batch_per_gpu": batch, "grid": [13, 13], "anchors": 5, "classes": 20, "image": [416, 416],
+            "gt_boxes_per_image": "U{1..5}", "parameters": 67147837}
+
+
+def run_cfg4_reference(args):
+    """The unmodified reference's run_one_epoch over ONE batch on the host cores (a bounded sample: 4 images)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from odcp_b200 import synthetic, targets
+    from oracle import refharness as RH
+    batch = args.batch or WORKLOADS["cfg4"]["batch"]
+    sample = min(args.cpu_sample or 4, batch)
+    torch.set_num_threads(os.cpu_count() or 1)
+    if not RH.available():
+        emit({"impl": "reference", "unavailable": "the reference is not staged (oracle/_ref) on this box"})
+        return
+    ref = RH.load_reference("cpu")
+    cls_list = [str(i) for i in range(20)]
+    torch.manual_seed(1234)
+    model = ref.yolov2.YOLOv2(cls_list, {c: i for i, c in enumerate(cls_list)})
+    case = synthetic.make_case("cfg4", 2, sample, 13, 13, 5, 20, 416, 416, seed=104)
+    x = torch.rand(sample, 416, 416, 3, generator=torch.Generator().manual_seed(7)) * 255.0
+    dense = targets.records_to_dense(case.rec, case.n, case.s_h, case.s_w, case.c, 2)
+
+    class OneBatch:
+        dataset = range(sample)
+
+        def __iter__(self):
+            yield (x, *dense)
+
+    import warnings
+    warnings.filterwarnings("ignore", message="Using a target size")
+    steps, warm = max(1, min(args.steps, 5)), max(0, min(args.warmup, 1))
+    ts = []
+    for i in range(warm + steps):
+        t0 = time.perf_counter()
+        model.run_one_epoch(1, OneBatch(), lr=1e-3, train=True, **synthetic.DEFAULT_LAMBDAS)
+        if i >= warm:
+            ts.append(time.perf_counter() - t0)
+    total = float(np.sum(ts))
+    value = sample * len(ts) / total
+    cores = torch.get_num_threads()
+    emit({"impl": "reference", "metric": CFG4_METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(ts),
+          "warmup": warm, "ms_per_step": 1e3 * total / len(ts), "higher_is_better": True, "scaling": "weak",
+          "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg4_config(batch),
+          "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                           "sample": "%d images per step (a sample of the batch-%d workload); the unmodified reference's "
+                                     "run_one_epoch over one batch (get_loss, SGD, backward, step) on torch CPU, %d threads"
+                                     % (sample, batch, cores)},
+          "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
+
+
+def run_cfg4(args):
+    """One step = what the reference's run_one_epoch does per batch (models/yolov2.py:1237-1272) on this rank's shard
+    of the batch: forward through the convolutions (stock cuDNN, channels_last, TF32 as torch defaults), the fused
+    train head, backward (DDP's bucketed NCCL all-reduce of the 67.15 M parameter gradients overlapped with it), and
+    the fused SGD step.  odcp_b200.train_step has the step; this function times it."""
+    if args.impl == "reference":
+        run_cfg4_reference(args)
+        return
+    from odcp_b200 import ops, synthetic, targets
+    from odcp_b200.models.layout import use_channels_last_head
+    from odcp_b200.optim import SGD
+    from odcp_b200.train_step import ShardedTrainStep, YOLOv2Net
+
+    world, rank, local_rank = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", 1), ("RANK", 0), ("LOCAL_RANK", 0)))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    B, K, W = args.batch or WORKLOADS["cfg4"]["batch"], args.steps, max(args.warmup, 3)
+    case = synthetic.make_case("cfg4", 2, B, 13, 13, 5, 20, 416, 416, seed=104 + rank)
+    torch.manual_seed(11)
+    model = use_channels_last_head(YOLOv2Net()).to(dev)
+    n_par = sum(p.numel() for p in model.parameters())
+    gt, off = targets.records_to_tensor(case.rec, dev), torch.from_numpy(case.gt_off).to(dev)
+    from odcp_b200 import dist as yh_dist
+    m_global = yh_dist.global_box_count(case.m, device=dev)
+    trainer = ShardedTrainStep(model, optimizer_cls=torch.optim.SGD if args.torch_sgd else SGD,
+                               bucket_cap_mb=args.bucket_mb or None, static_box_count=m_global)
+    x_host = (torch.rand(B, 416, 416, 3, generator=torch.Generator().manual_seed(7 + rank)) * 255.0).pin_memory()
+    x = x_host.to(dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def timed(n, from_host):
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        a.record()
+        last = None
+        for _ in range(n):
+            if from_host:
+                x.copy_(x_host, non_blocking=True)
+            last = trainer.step(x, gt, off, case.m)
+            if from_host:
+                last = float(last.item())  # the step's result on the host, every step
+        e.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        barrier()
+        t = torch.tensor([a.elapsed_time(e), wall * 1e3], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0].item()), float(t[1].item()), last
+
+    timed(W, False)
+    sampler = ClockSampler(nvml_index(local_rank))
+    sampler.start()
+    ms, _, last = timed(K, False)
+    sampler.stop()
+    loss_share = float(last.item())
+    ke = max(3, min(K, 20))
+    timed(2, True)
+    _, e2e_ms, _ = timed(ke, True)
+
+    # the head call inside the step, alone (stream-ordered, this rank's head tensor)
+    with torch.no_grad():
+        y = model(x).contiguous()
+    kw = dict(version=2, img_hw=(416, 416), anchors=synthetic.YOLOV2_ANCHORS, lambdas=synthetic.DEFAULT_LAMBDAS, m_global=m_global)
+    out = ops.train_head(y, gt, off, **kw)
+    g = torch.cuda.CUDAGraph()
+    st = torch.cuda.Stream(dev)
+    with torch.cuda.stream(st):
+        ops.train_head(y, gt, off, out=out, **kw)
+        st.synchronize()
+        with torch.cuda.graph(g, stream=st):
+            for _ in range(8):
+                ops.train_head(y, gt, off, out=out, **kw)
+        g.replay()
+        st.synchronize()
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        for _ in range(20):
+            g.replay()
+        e.record(st)
+        st.synchronize()
+    head_ms = a.elapsed_time(e) / 160
+    head_bytes = 2 * y.numel() * 4 + 48 * case.m
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else FALLBACK_HBM_GBS
+    if rank == 0:
+        emit({
+            "metric": CFG4_METRIC, "value": B * world * K / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (convolutions: TF32 tensor cores, torch's cuDNN default; head, loss, gradient, SGD: fp32)",
+            "data": "synthetic", "config": cfg4_config(B),
+            "run": {"optimizer": "torch.optim.SGD re-created per step (the reference)" if args.torch_sgd else
+                                 "odcp_b200.optim.SGD (yh_sgd_step, one launch) re-created per step",
+                    "ddp": None if world == 1 else "DistributedDataParallel, gradient_as_bucket_view, bucket %s MB; "
+                           "all-reduce of %d bytes per step overlapped with the backward" % (args.bucket_mb or 25, 4 * n_par),
+                    "l2": "activations of one step (GBs) far exceed the 126 MB L2",
+                    "box_count": "the all-rank box count is known up front (static shards): no per-step all-reduce for it"},
+            "allreduce_bytes_per_step": 0 if world == 1 else 4 * n_par, "parameters": n_par,
+            "clocks": sampler.summary("the %d timed steps" % K),
+            "e2e": {"value": B * world * ke / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
+                    "d2h_bytes_per_step": 4, "steps": ke, "ms_per_step": e2e_ms / ke,
+                    "path": "ShardedTrainStep.step with the image batch copied from pinned host memory and the loss read "
+                            "back every step (wall clock, max over ranks)"},
+            "gpu_launches": 3 * K,  # ours per step: yh_train_kernel, yh_train_finalize_kernel, yh_sgd_kernel (+ cuDNN/NCCL/aten)
+            "roofline": {"bound": "hbm", "kernel": "yh_train_kernel + finalize inside the step (the convolutions are cuDNN's: out of scope)",
+                         "achieved": head_bytes / (head_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": head_bytes / (head_ms * 1e-3) / 1e9 / peak, "traffic": None,
+                         "algorithmic_bytes_per_launch": head_bytes, "us_per_launch": head_ms * 1e3,
+                         "share_of_step": head_ms / (ms / K)},
+            "cpu_baseline": None, "loss_share_of_rank0": loss_share,
+        })
+    if dist is not None:
+        dist.destroy_process_group()
 
 # ------------------------------------------------------------------------------------------
 # clocks
@@ -338,6 +535,9 @@ def emit(line):
 def main():
     args = parse_args()
     quiet_stdout()
+    if args.workload == "cfg4":
+        run_cfg4(args)
+        return
     if args.impl == "reference":
         run_reference(args)
         return

@@ -14,10 +14,30 @@ _METHODS = ("predict", "get_loss", "get_loss_compact", "get_loss_from_boxes", "d
             "_yh_anchors", "_yh_kwargs", "_yh_image_batch", "_yh_annot", "_yh_detect_host")
 
 
-def patch_reference(ref_yolov1=None, ref_yolov2=None, ref_utils=None, fused_sgd=False):
+def _channels_last_init(cls):
+    """Wrap `cls.__init__` so that every Conv2d of a new model is put into channels_last memory format (values and
+    state_dict keys unchanged): the head conv then writes NHWC and the reference's `permute(0, 2, 3, 1)` + `reshape`
+    in head() (models/yolov2.py:338-362) is a view instead of a copy of the head tensor -- and of its gradient."""
+    from .layout import use_channels_last_head
+    orig = cls.__init__
+    if getattr(orig, "_yh_channels_last", False):
+        return
+
+    def __init__(self, *args, **kwargs):
+        orig(self, *args, **kwargs)
+        use_channels_last_head(self)
+
+    __init__._yh_channels_last = True
+    __init__.__doc__ = orig.__doc__
+    cls.__init__ = __init__
+
+
+def patch_reference(ref_yolov1=None, ref_yolov2=None, ref_utils=None, fused_sgd=False, channels_last=False):
     """`fused_sgd=True` also replaces the `SGD` name the reference's run_one_epoch resolves
     (models/yolov2.py:7, :1253-1268) with odcp_b200.optim.SGD: the same update (a new optimizer per
-    iteration, so every step is a first step) in one kernel launch."""
+    iteration, so every step is a first step) in one kernel launch.
+    `channels_last=True` makes YOLOv2 models constructed afterwards run their convolutions in channels_last, which
+    turns the layout change in front of the head path into a view (models/layout.py)."""
     from . import utils as u
     from .yolov1 import YOLOv1HeadOps
     from .yolov2 import YOLOv2HeadOps
@@ -38,6 +58,8 @@ def patch_reference(ref_yolov1=None, ref_yolov2=None, ref_utils=None, fused_sgd=
         if fused_sgd:
             from ..optim import SGD
             mod.SGD = SGD
+        if channels_last and cls_name == "YOLOv2":  # (YOLOv1's head is a Linear layer: nothing to lay out)
+            _channels_last_init(cls)
         done.append(cls_name)
     if ref_utils is not None:
         ref_utils.nms = u.nms

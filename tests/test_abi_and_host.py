@@ -265,3 +265,24 @@ def test_threshold_band_of_the_postprocess_is_safe():
         ulp = np.spacing(f32(thr))
         assert sig(hi) - f32(thr) > 40 * ulp, thr
         assert f32(thr) - sig(lo) > 40 * ulp, thr
+
+
+def test_yolov2_net_is_the_reference_network():
+    """odcp_b200.train_step.YOLOv2Net (the stock-cuDNN network of BASELINE config 4) against the reference's YOLOv2:
+    same parameter count, same state_dict keys, and -- with the reference's weights loaded -- the same head tensor."""
+    from oracle import refharness as RH
+    if not RH.available():
+        pytest.skip("the reference is not staged (oracle/_ref) and /root/reference does not exist")
+    import torch
+    from odcp_b200 import train_step as T
+    ref = RH.load_reference("cpu")
+    cls_list = [str(i) for i in range(20)]
+    torch.manual_seed(0)
+    theirs = ref.yolov2.YOLOv2(cls_list, {c: i for i, c in enumerate(cls_list)}).eval()
+    ours = T.YOLOv2Net(cls_list).eval()
+    assert sum(p.numel() for p in ours.parameters()) == T.YOLOV2_PARAMETERS == sum(p.numel() for p in theirs.parameters())
+    assert list(ours.state_dict().keys()) == list(theirs.state_dict().keys())
+    ours.load_state_dict(theirs.state_dict())
+    x = torch.rand(1, 416, 416, 3, generator=torch.Generator().manual_seed(3)) * 255.0
+    with torch.no_grad():
+        assert torch.equal(ours(x), theirs(x))

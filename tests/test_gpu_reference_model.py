@@ -57,11 +57,14 @@ def widest_gap_midpoint(values, q=None, lo=None, hi=None):
     return float(0.5 * (v[i] + v[i + 1]))
 
 
-def test_reference_yolov2_training_batch_and_detect_through_the_drop_in(cuda_device):
+def test_reference_yolov2_training_batch_and_detect_through_the_drop_in(cuda_device, monkeypatch):
     if not RH.available():
         pytest.skip("the reference is not staged (oracle/_ref) and /root/reference does not exist")
     dev = cuda_device
     case, batch = make_batch(dev)
+    # fp32 convolutions in both runs: the comparison is between memory layouts / kernels, not TF32 roundings
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
+    monkeypatch.setattr(torch.backends.cuda.matmul, "allow_tf32", False)
 
     # ---- the reference as it is
     ref, model = fresh_reference_model(dev)
@@ -73,14 +76,26 @@ def test_reference_yolov2_training_batch_and_detect_through_the_drop_in(cuda_dev
 
     # ---- the same step through the drop-in: CUDA head path, fused SGD, channels_last head
     from odcp_b200.models import patch_reference
-    from odcp_b200.models.layout import use_channels_last_head
+    from odcp_b200.models.layout import is_free_view
     ref2, model2 = fresh_reference_model(dev)
     orig_predict = ref2.yolov2.YOLOv2.predict
     for k, v in model2.state_dict().items():
         assert torch.equal(v, init[k]), k  # identical start
-    done = patch_reference(ref2.yolov1, ref2.yolov2, ref2.utils, fused_sgd=True)
+    done = patch_reference(ref2.yolov1, ref2.yolov2, ref2.utils, fused_sgd=True, channels_last=True)
     assert "YOLOv2" in done
-    use_channels_last_head(model2.head_model)
+    torch.manual_seed(1234)  # constructed AFTER the patch: its convolutions are channels_last from the start
+    model2 = ref2.yolov2.YOLOv2(model2.cls_list, model2.cls2idx).to(dev)
+    for k, v in model2.state_dict().items():
+        assert torch.equal(v, init[k]), k  # same keys, same values
+    # the reference's own head() (permute + reshape, models/yolov2.py:338-362) is now a view of the conv's output
+    seen = {}
+    hook = model2.head_model[-1].register_forward_hook(lambda m, i, o: seen.update(out=o))
+    model2.eval()  # (no BatchNorm statistics are touched by this probe)
+    with torch.no_grad():
+        y_view = model2(batch[0][:2])
+    model2.train()
+    hook.remove()
+    assert is_free_view(seen["out"], y_view)
     loss_new = float(model2.run_one_epoch(2, OneBatch(batch, N), lr=1e-3, train=True, **LAM))
     after_new = {k: v.detach().clone() for k, v in model2.state_dict().items()}
 
