@@ -109,8 +109,9 @@ def test_reference_yolov2_training_batch_and_detect_through_the_drop_in(cuda_dev
         upd = (a - i).abs().max().item()
         err = (a - b).abs().max().item()
         # relative to the size of the update itself (cuDNN's backward is not bit-reproducible between layouts)
-        assert err <= 2e-3 * upd + 1e-7 * max(a.abs().max().item(), 1e-30), (k, err, upd)
-        worst = max(worst, err / max(upd, 1e-30))
+        ulp = 1e-7 * max(a.abs().max().item(), 1e-30)  # (a parameter that only sees weight decay moves by a few ulps)
+        assert err <= 2e-3 * upd + ulp, (k, err, upd)
+        worst = max(worst, max(err - ulp, 0.0) / max(upd, 1e-30))
     assert worst < 2e-3
 
     # ---- detect: the patched model against the reference's own chain on the SAME head tensor
