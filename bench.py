@@ -871,7 +871,7 @@ def main():
         e2e = {"value": images * ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes(m_local),
                "d2h_bytes_per_step": pipe.d2h_bytes(), "steps": ke, "ms_per_step": 1e3 * e2e_s / ke,
                "path": "HostHeadPipeline: pinned host y+GT -> H2D -> yh_v2_train_post (loss + dL/dy + kept boxes) -> "
-                       "D2H of loss, terms and kept boxes%s; 3 slots, copy/compute streams overlapped"
+                       "D2H of loss, terms and kept boxes%s; 3 slots; the head tensor goes up in two halves on two H2D streams, kernels and D2H on their own streams"
                        % (" and dL/dy" if args.e2e_return_dy else " (dL/dy is computed every step and stays on the device)")}
 
     collective = None

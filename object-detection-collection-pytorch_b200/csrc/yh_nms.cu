@@ -51,6 +51,10 @@ namespace {
 constexpr int kThreadsFull = YH_X_NMS_THREADS;  // threads per CTA of the kernels that read the head tensor
 constexpr int kTeam = 256;    // fused step: threads of a CTA that resolve the image's NMS while the others process its records
 constexpr int kRecSmem = 32;  // fused step: records of the image staged in shared memory (more: read from global memory)
+#ifndef YH_X_REC4_MIN
+#define YH_X_REC4_MIN 8
+#endif
+constexpr int kRec4Min = YH_X_REC4_MIN;  // fused step: images with more records than this process four per warp at a time (yh_record.cuh)
 constexpr int kTile = 256;             // ranked candidates per suppression tile
 constexpr int kTileWords = kTile / 32;
 constexpr int kSmemCand = 256;         // candidates held in shared memory
@@ -325,7 +329,7 @@ __device__ __forceinline__ bool suppresses_dense(const float4& bi, float ai, con
 // IMG: the image's whole slice of the head tensor is staged in shared memory by kGroups bulk copies
 // issued at the start (ONE global round trip, no per-candidate copies); otherwise the objectness
 // logits are read with strided loads and only the candidates' rows are staged.
-// TRAIN (the fused step, yh_v2_train_post; whole-image mode, v2): the CTA that holds an image in shared memory for
+// TRAIN != 0 (the fused step, yh_v2_train_post; whole-image mode, v2; TRAIN == 2: with the four-records-per-warp form): the CTA that holds an image in shared memory for
 // the post-process ALSO does the train head's work on it -- y is read once per step, by one kernel:
 //   * as each piece of the image lands, its warp group runs the dense pass over it: the no-object term and its
 //     gradient per objectness logit, dL/dy written with 16-byte stores straight from registers (zero elsewhere);
@@ -334,7 +338,7 @@ __device__ __forceinline__ bool suppresses_dense(const float4& bi, float ai, con
 //     arithmetic, the same bits as the train head) on top of the dense values, while the lower half resolves the
 //     image's NMS (rank, decode, pair tests, greedy order, class pick, emit: the lean path below on a 256-thread team);
 //   * the CTA's six loss sums go onto the 64-bit fixed-point accumulators; yh_train_finalize_kernel follows.
-template <int TV, int TA, int TC, int MODE, int NTH, bool TRAIN>
+template <int TV, int TA, int TC, int MODE, int NTH, int TRAIN>
 __global__ void __launch_bounds__(NTH, NTH >= 512 ? 2 : 3) yh_nms_kernel(const NmsParams p) {
     constexpr int kThreads = NTH, kWarps = NTH / 32;
     constexpr bool IMG = MODE == MODE_IMG;
@@ -654,11 +658,7 @@ __global__ void __launch_bounds__(NTH, NTH >= 512 ? 2 : 3) yh_nms_kernel(const N
                 if (lc >= 0 && lc % kRecWarps != tw) lc = -1;
             }
             unsigned bal = __ballot_sync(0xffffffffu, lc >= 0);
-            while (bal) {
-                const int b = __ffs(bal) - 1;
-                bal &= bal - 1u;
-                const int lcell = __shfl_sync(0xffffffffu, lc, b);
-                const int rj = base + b;
+            auto load_record = [&](int rj) -> RecordRegs {
                 RecordRegs rr;
                 if (rj < nsm) {
                     rr.hd = s_rec[3 * rj];
@@ -670,6 +670,36 @@ __global__ void __launch_bounds__(NTH, NTH >= 512 ? 2 : 3) yh_nms_kernel(const N
                     rr.tt = __ldg(reinterpret_cast<const float4*>(rp + 1));
                     rr.bb = __ldg(reinterpret_cast<const float4*>(rp + 2));
                 }
+                return rr;
+            };
+            if (TRAIN == 2 && nrec > kRec4Min) {
+                // an image dense with ground truth: four records per warp at a time, eight lanes each (yh_record.cuh)
+                while (bal) {
+                    const int b = yh_batch4(bal, lc, lane);
+                    const bool on = b >= 0;
+                    const int lcell_ = __shfl_sync(0xffffffffu, lc, on ? b : 0);  // (every lane takes part)
+                    const int lcell = on ? lcell_ : 0;
+                    const int rj = base + (on ? b : 0);
+                    RecordRegs rr;
+                    rr.hd = make_int4(0, 0, 0, 0);
+                    rr.tt = rr.bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (on) rr = load_record(rj);
+                    const unsigned long long bit = 1ull << ((lcell / kRecWarps) & 63);
+                    const bool again = !track || (seen & bit) != 0ull;
+                    const unsigned lo = __reduce_or_sync(0xffffffffu, on ? (unsigned)bit : 0u);
+                    const unsigned hi = __reduce_or_sync(0xffffffffu, on ? (unsigned)(bit >> 32) : 0u);
+                    seen |= ((unsigned long long)hi << 32) | lo;
+                    if (dimg) process_records4<1>(p, 2, A, C, on, rr, o0 + rj, win + fsh + lcell * cf, dimg + lcell * cf, again, kn, lane, sums);
+                    else process_records4<0>(p, 2, A, C, on, rr, o0 + rj, win + fsh + lcell * cf, nullptr, false, kn, lane, sums);
+                }
+                continue;
+            }
+            while (bal) {
+                const int b = __ffs(bal) - 1;
+                bal &= bal - 1u;
+                const int lcell = __shfl_sync(0xffffffffu, lc, b);
+                const int rj = base + b;
+                const RecordRegs rr = load_record(rj);
                 const unsigned long long bit = 1ull << ((lcell / kRecWarps) & 63);
                 const bool again = !track || (seen & bit) != 0ull;
                 seen |= bit;
@@ -1257,7 +1287,7 @@ __global__ void __launch_bounds__(NTH, NTH >= 512 ? 2 : 3) yh_nms_kernel(const N
     if (p.late_wait && img == 0 && tid == 0) yh_grid_dependency_wait();
 }
 
-template <int TV, int TA, int TC, int MODE, int NTH, bool TRAIN = false>
+template <int TV, int TA, int TC, int MODE, int NTH, int TRAIN = 0>
 int launch_variant(const NmsParams& p, size_t smem, void* stream) {
     static size_t configured[64] = {0};
     int dev = 0;
@@ -1304,8 +1334,12 @@ int launch(NmsParams& p, void* ws, size_t ws_bytes, void* stream, bool train = f
     // YOLOv1 B=2, C=20); anything else, and decoded-box input, runs the run-time-geometry variant
     constexpr int NTF = kThreadsFull;
     if (train) {  // the fused step (the caller checked img_mode_applies and version 2)
-        if (p.g.a == 5 && p.c == 20) return launch_variant<2, 5, 20, MODE_IMG, NTF, true>(p, smem, stream);
-        return launch_variant<2, 0, 0, MODE_IMG, NTF, true>(p, smem, stream);
+        // batches dense with ground truth (BASELINE config 5) run the variant whose record warps take four records at
+        // a time (yh_record.cuh: same bits); the common, sparse case keeps the kernel without that code
+        const bool dense_gt = (long long)p.m_local > (long long)kRec4Min * p.n;
+        if (p.g.a == 5 && p.c == 20)
+            return dense_gt ? launch_variant<2, 5, 20, MODE_IMG, NTF, 2>(p, smem, stream) : launch_variant<2, 5, 20, MODE_IMG, NTF, 1>(p, smem, stream);
+        return dense_gt ? launch_variant<2, 0, 0, MODE_IMG, NTF, 2>(p, smem, stream) : launch_variant<2, 0, 0, MODE_IMG, NTF, 1>(p, smem, stream);
     }
     if (img_mode) {
         if (p.g.version == 2 && p.g.a == 5 && p.c == 20) return launch_variant<2, 5, 20, MODE_IMG, NTF>(p, smem, stream);

@@ -8,8 +8,11 @@ tensor and ground truth live in HOST memory.
 
 Each submit stages its inputs through pinned buffers, runs the fused step (train head + post-process,
 libyolohead's yh_v2_train_post through the C ABI; YOLOv1: the two separate kernels) and brings the loss,
-its terms, the detections and -- on request -- dL/dy back.  Three streams (H2D, kernels, D2H) and `depth`
-slots let consecutive steps overlap on the two PCIe directions; nothing is computed on the CPU.
+its terms, the detections and -- on request -- dL/dy back.  Four streams (two H2D, kernels, D2H) and `depth`
+slots let consecutive steps overlap on the two PCIe directions; nothing is computed on the CPU.  The head tensor
+goes up in two halves on two streams: a copy carries ~45 us of set-up and completion latency that queued copies
+on ONE stream do not overlap (measured on the B200 boxes, scratch/h2d_probe.py: 21.7 MB back to back 48.6 GB/s
+on one stream, 53.9 GB/s as two halves on two streams -- the link's rate for large copies is 54.5 GB/s).
 """
 from __future__ import annotations
 
@@ -41,7 +44,7 @@ class HostHeadPipeline:
         shape = (n, s_h, s_w, a, 5 + c) if version == 2 else (n, s_h, s_w, 5 * a + c)
         self.shape = shape
         d, f32, i32 = self.dev, torch.float32, torch.int32
-        self.s_h2d, self.s_run, self.s_d2h = (torch.cuda.Stream(d) for _ in range(3))
+        self.s_h2d, self.s_h2d2, self.s_run, self.s_d2h = (torch.cuda.Stream(d) for _ in range(4))
         self.slots = []
         # Small inputs (records + offsets) and small outputs (terms, loss, detections) are packed into
         # one buffer each, so a step is two host-to-device and two device-to-host copies: every
@@ -83,7 +86,7 @@ class HostHeadPipeline:
                 h_y=torch.empty(shape, dtype=f32).pin_memory(), h_gt=hi["gt"], h_off=hi["off"],
                 h_dy=torch.empty(shape, dtype=f32).pin_memory() if return_dy else None,
                 h=ho,
-                ev_in=torch.cuda.Event(), ev_run=torch.cuda.Event(), ev_post=torch.cuda.Event(), ev_out=torch.cuda.Event(),
+                ev_in=torch.cuda.Event(), ev_in2=torch.cuda.Event(), ev_run=torch.cuda.Event(), ev_post=torch.cuda.Event(), ev_out=torch.cuda.Event(),
                 busy=False, post=post,
             )
             s["res"] = dict(train=dict(dy=s["dy"] if self.compute_dy else None, loss=s["loss"], terms=s["terms"]),
@@ -115,8 +118,13 @@ class HostHeadPipeline:
             s["h_y"].copy_(y_host)
             s["h_gt"][:m].copy_(gt_host)
             s["h_off"].copy_(gt_off_host)
+        yd, yh = s["y"].view(-1), s["h_y"].view(-1)
+        half = (yd.numel() // 2) & ~63
+        with torch.cuda.stream(self.s_h2d2):
+            yd[half:].copy_(yh[half:], non_blocking=True)
+            s["ev_in2"].record(self.s_h2d2)
         with torch.cuda.stream(self.s_h2d):
-            s["y"].copy_(s["h_y"], non_blocking=True)
+            yd[:half].copy_(yh[:half], non_blocking=True)
             nb = (m * 48 + 15) & ~15  # the records in use; the offsets sit behind the full record area
             if nb + (self.n + 1) * 4 + 64 >= self._in_bytes // 2:
                 s["d_in"].copy_(s["h_in"], non_blocking=True)
@@ -126,6 +134,7 @@ class HostHeadPipeline:
             s["ev_in"].record(self.s_h2d)
         with torch.cuda.stream(self.s_run):
             self.s_run.wait_event(s["ev_in"])
+            self.s_run.wait_event(s["ev_in2"])
             if self.version == 2:
                 # the fused step: train head + post-process, the head tensor read once (yh_v2_train_post)
                 s["res"] = ops.train_post(s["y"], s["gt"][:m], s["off"], img_hw=self.img_hw, lambdas=self.lambdas,

@@ -50,6 +50,11 @@ def run(name, case, conf_thre, iou_thre=0.45):
         s["post"] = ops.postprocess(s["y"], conf_thre=conf_thre, iou_thre=iou_thre, max_out=128, want_cls_spec=False,
                                     out=s.get("post"), **kw)
 
+    def fused(s):
+        s["fu"] = ops.train_post(s["y"], s["gt"], s["off"], img_hw=kw["img_hw"], anchors=kw["anchors"], lambdas=lam,
+                                 conf_thre=conf_thre, iou_thre=iou_thre, max_out=128, want_cls_spec=False, out=s.get("fu"))
+
+    t_fused = time_graph(fused, sets) if case.version == 2 and os.environ.get("YH_TIME_FUSED", "1") == "1" else None
     t_train = time_graph(train, sets)
     t_post = time_graph(post, sets)
     # predict(): the six decoded outputs (49 floats per predictor)
@@ -70,6 +75,8 @@ def run(name, case, conf_thre, iou_thre=0.45):
                           train_frac=round(b_train / t_train / 1e3 / PEAK, 3),
                           post_us=round(t_post, 2), post_MB=round(b_post / 1e6, 2),
                           post_frac=round(b_post / t_post / 1e3 / PEAK, 3), kept_per_image=round(kept / case.n, 1),
+                          fused_us=None if t_fused is None else round(t_fused, 2),
+                          fused_frac_3P=None if t_fused is None else round((b_train + b_post) / t_fused / 1e3 / PEAK, 3),
                           decode_us_incl_alloc=round(t_dec, 2),
                           decode_MB=round((p * case.n + 49 * 4 * case.n * case.s_h * case.s_w * case.a) / 1e6, 2))), flush=True)
 
