@@ -742,8 +742,7 @@ extern "C" YH_API int yh_x_rcycles_copy(unsigned int* host, int n) {
 
 // Totals -> terms and loss (reference models/yolov2.py:1132-1138; sharded batches: summed over all ranks through
 // peer memory first, yh_finalize.cuh), and the workspace back to zero for the next launch.  Launched as a
-// programmatic dependent right behind yh_train_kernel.  (The fused step has no such launch: one extra CTA of its
-// post-process kernel does this.)
+// programmatic dependent right behind yh_train_kernel (and behind the fused step's kernel, yh_nms.cu).
 __global__ void __launch_bounds__(32) yh_train_finalize_kernel(const YhFinalParams f) {
     yh_grid_launch_dependents();
     yh_grid_dependency_wait();  // the train kernel has completed and its sums are visible

@@ -81,8 +81,10 @@ def run(name, case, conf_thre, iou_thre=0.45):
                           decode_MB=round((p * case.n + 49 * 4 * case.n * case.s_h * case.s_w * case.a) / 1e6, 2))), flush=True)
 
 
-run("cfg1 v1 7x7 B=2 N=8", synthetic.cfg1(), 0.5)
-run("cfg2 v2 13x13 N=64", synthetic.cfg2(), 0.5)
-run("cfg3 v2 13x13 N=256 (inference, conf 0.5)", synthetic.cfg3(), 0.5)
-run("headline v2 13x13 N=256", synthetic.headline(), 0.5)
-run("cfg5 v2 19x19 N=512 50-100 boxes", synthetic.cfg5(), 0.5)
+ONLY = os.environ.get("YH_TIME_ONLY", "")  # e.g. "cfg5,headline"
+ALL = [("cfg1 v1 7x7 B=2 N=8", synthetic.cfg1), ("cfg2 v2 13x13 N=64", synthetic.cfg2),
+       ("cfg3 v2 13x13 N=256 (inference, conf 0.5)", synthetic.cfg3), ("headline v2 13x13 N=256", synthetic.headline),
+       ("cfg5 v2 19x19 N=512 50-100 boxes", synthetic.cfg5)]
+for name, mk in ALL:
+    if not ONLY or any(name.startswith(k) for k in ONLY.split(",")):
+        run(name, mk(), 0.5)

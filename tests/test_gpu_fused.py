@@ -93,17 +93,27 @@ CASES = {
     "images_without_boxes": (lambda: synthetic.make_case("empty", 2, 33, 13, 13, 5, 20, 416, 416, seed=46, k_lo=0, k_hi=2,
                                                          to_shift=-1.563), 0.5, 0.45),
     # 6-14 boxes per image: the fused kernel takes four records per warp (more than 8 per image) where the train head
-    # patches most tiles with the one-warp form and sends the record-dense ones through the four-per-warp form
+    # uses the one-warp form throughout (patches in the shadow of the stream, record-dense tiles after it)
     "mid_density_both_record_forms": (lambda: synthetic.make_case("mid", 2, 96, 13, 13, 5, 20, 416, 416, seed=48, k_lo=6, k_hi=14,
                                                                   to_shift=-1.563), 0.5, 0.45),
     "mid_density_collisions": (lambda: synthetic.with_collisions(synthetic.make_case("midc", 2, 48, 13, 13, 5, 20, 416, 416, seed=49,
                                                                                      k_lo=6, k_hi=14, to_shift=-1.563), 300, seed=8), 0.5, 0.45),
-    # 5 + C > 32: the train head cannot patch, all its records take the four-per-warp form; the fused kernel's images
-    # with at most 8 records take the one-warp form -- C = 40 and 80 run the class loops beyond the registers
+    # 5 + C > 32: the train head cannot patch, all its records are processed after the stream; the fused kernel's images
+    # with at most 8 records take the one-warp form, the others four per warp -- C = 40 and 80 run the class loops
+    # beyond the registers
     "c40_a4_sparse_records": (lambda: synthetic.make_case("c40", 2, 24, 13, 13, 4, 40, 416, 416, seed=50, to_shift=-1.5,
                                                            anchors=synthetic.YOLOV2_ANCHORS[:4]), 0.5, 0.45),
     "coco_c80_a3_dense_records": (lambda: synthetic.make_case("cocod", 2, 24, 13, 13, 3, 80, 416, 416, seed=51, to_shift=-1.5,
                                                                k_lo=10, k_hi=30, anchors=synthetic.YOLOV2_ANCHORS[:3]), 0.5, 0.45),
+    # more than 12 records per tile on average: the train head takes every record of such a tile after its dense pass
+    # (one warp per record, grouped by tile) where the fused kernel takes four per warp, grouped by image
+    "dense_19x19_record_dense_tiles": (lambda: synthetic.make_case("d19", 2, 64, 19, 19, 5, 20, 608, 608, seed=52, k_lo=85,
+                                                                         k_hi=110, to_shift=-1.59), 0.5, 0.45),
+    "dense_collisions_record_dense_tiles": (lambda: synthetic.with_collisions(
+        synthetic.make_case("d13", 2, 40, 13, 13, 5, 20, 416, 416, seed=53, k_lo=80, k_hi=110, to_shift=-1.563), 2500, seed=9), 0.5, 0.45),
+    "dense_c80_a3_record_dense_tiles": (lambda: synthetic.make_case("dcoco", 2, 32, 13, 13, 3, 80, 416, 416, seed=54,
+                                                                          to_shift=-1.5, k_lo=130, k_hi=160,
+                                                                          anchors=synthetic.YOLOV2_ANCHORS[:3]), 0.5, 0.45),
     "two_classes_unfused_route": (lambda: synthetic.make_case("c2", 2, 12, 13, 13, 5, 2, 416, 416, seed=47, to_shift=-1.5), 0.5, 0.45),
 }
 

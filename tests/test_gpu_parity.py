@@ -97,6 +97,16 @@ CASES = {
                                              anchors=synthetic.YOLOV2_ANCHORS[:3]),
     "v1_b3_c7": lambda: synthetic.make_case("v1b3", 1, 5, 5, 6, 3, 7, 160, 192, seed=24),
     "v2_c1": lambda: synthetic.make_case("c1", 2, 4, 13, 13, 5, 1, 416, 416, seed=25),
+    # batches with more than 12 records per tile on average (BASELINE config 5's density): the train head processes
+    # every record of such a tile after its dense pass, all warps at once, records dealt by cell (compile-time and
+    # run-time geometry, v2 and v1, collisions on top of dense values, C beyond the class registers)
+    "dense_v2_19x19_n64": lambda: synthetic.make_case("d19", 2, 64, 19, 19, 5, 20, 608, 608, seed=26, k_lo=85, k_hi=110),
+    "dense_v2_13x13_coll": lambda: synthetic.with_collisions(
+        synthetic.make_case("d13", 2, 40, 13, 13, 5, 20, 416, 416, seed=27, k_lo=80, k_hi=110), 2500, seed=5),
+    "dense_v2_c80_a3": lambda: synthetic.make_case("dcoco", 2, 32, 13, 13, 3, 80, 416, 416, seed=28, k_lo=130, k_hi=160,
+                                                   anchors=synthetic.YOLOV2_ANCHORS[:3]),
+    "dense_v1_7x7": lambda: synthetic.make_case("dv1", 1, 64, 7, 7, 2, 20, 448, 448, seed=29, k_lo=80, k_hi=100),
+    "dense_v1_b3_c7": lambda: synthetic.make_case("dv1b3", 1, 96, 5, 6, 3, 7, 160, 192, seed=30, k_lo=60, k_hi=80),
 }
 
 
