@@ -79,11 +79,13 @@ __device__ __forceinline__ unsigned long long nt_now() {
     return t;
 }
 #define NT(slot) do { if (threadIdx.x == 0) g_ntrace[blockIdx.x * 16 + (slot)] = nt_now(); } while (0)
+#define NTR(slot) do { if (threadIdx.x == kTeam) g_ntrace[blockIdx.x * 16 + (slot)] = nt_now(); } while (0)
 extern "C" YH_API int yh_x_ntrace_copy(unsigned long long* host, int n) {
     return (int)cudaMemcpyFromSymbol(host, g_ntrace, (size_t)n * 8);
 }
 #else
 #define NT(slot) do { } while (0)
+#define NTR(slot) do { } while (0)
 #endif
 
 template <bool B>
@@ -351,6 +353,7 @@ __global__ void __launch_bounds__(NTH, NTH >= 512 ? 2 : 3) yh_nms_kernel(const N
     __shared__ unsigned int rem0[kTileWords];
     __shared__ __align__(8) uint64_t bar;      // staged rows have landed (transaction bytes)
     __shared__ __align__(8) uint64_t bar_list; // every thread has listed its candidates
+    __shared__ __align__(8) uint64_t bar_dense; // TRAIN: every thread has written its share of the dense dL/dy
     __shared__ __align__(8) uint64_t bar_img[kGroups];  // IMG: one per bulk copy of the image
     __shared__ int s_count, s_kept;
 
@@ -378,6 +381,7 @@ __global__ void __launch_bounds__(NTH, NTH >= 512 ? 2 : 3) yh_nms_kernel(const N
         s_kept = 0;
         yh_mbar_init(&bar, kThreads);
         yh_mbar_init(&bar_list, kThreads);
+        if (TRAIN) yh_mbar_init(&bar_dense, kThreads);
         if (IMG) {
 #pragma unroll
             for (int q = 0; q < kGroups; ++q) yh_mbar_init(&bar_img[q], 1);
@@ -484,7 +488,7 @@ __global__ void __launch_bounds__(NTH, NTH >= 512 ? 2 : 3) yh_nms_kernel(const N
         if (gtid < 32) yh_mbar_wait(&bar_img[grp], 0);
         asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kGroupThreads) : "memory");
         yh_mbar_wait(&bar_img[grp], 0);
-        if (TRAIN) {
+        auto dense_pass = [&]() {
             // ---- dense pass over this group's piece (the train head's, yh_train.cu: same helpers, same bits): window
             // floats 4*i4 .. 4*i4+3 are image floats f0 .. f0+3 and sit at positions m .. m+3 of a predictor row; the
             // objectness logit (position 4) is among them iff 1 <= m <= 4.  dL/dy is zero but the objectness channel.
@@ -533,7 +537,7 @@ __global__ void __launch_bounds__(NTH, NTH >= 512 ? 2 : 3) yh_nms_kernel(const N
                 m += mstep;
                 m = m >= bs ? m - bs : m;
             }
-        }
+        };
         // conf >= conf_thre is decided on the logit wherever that is safe (to_reject / to_accept leave a
         // band around logit(conf_thre) in which the sigmoid is evaluated); survivors are listed with
         // their LOGIT -- the sigmoid of the ~50 survivors is taken later by as many threads, instead
@@ -564,6 +568,14 @@ __global__ void __launch_bounds__(NTH, NTH >= 512 ? 2 : 3) yh_nms_kernel(const N
                     else overflow_put(p.ws + (size_t)img * p.ws_per_image, P, slot, t1, i1);
                 }
             }
+        }
+        if (TRAIN) {
+            // Fused step: the candidates of this piece are listed BEFORE its dense pass runs, so that the NMS team (whose
+            // own pieces landed first) can rank and decode while the last pieces' dense passes are still writing dL/dy;
+            // what needs the complete gradient -- the records, which overwrite its rows -- waits on bar_dense instead.
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(yh_smem_u32(&bar_list)) : "memory");
+            dense_pass();
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(yh_smem_u32(&bar_dense)) : "memory");
         }
     } else
     // ---------------- A: threshold + stage the survivors' rows ----------------
@@ -615,7 +627,7 @@ __global__ void __launch_bounds__(NTH, NTH >= 512 ? 2 : 3) yh_nms_kernel(const N
     // two arrivals per thread: "my candidates are listed" and, carrying the bytes its bulk copies
     // will deliver, "my rows are on their way".  Ranking only needs the list, so it runs while the
     // rows are still in flight.
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(yh_smem_u32(&bar_list)) : "memory");
+    if (!TRAIN) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(yh_smem_u32(&bar_list)) : "memory");
     if (!IMG) {
         if (tx) yh_mbar_expect_tx(&bar, tx);
         else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(yh_smem_u32(&bar)) : "memory");
@@ -984,27 +996,37 @@ __global__ void __launch_bounds__(NTH, NTH >= 512 ? 2 : 3) yh_nms_kernel(const N
         // the common case first, and out of the way of everything below
         // (logit, predictor) -> sort key: confidence bits in the high word (positive floats order like
         // integers), complement of the predictor index in the low word (ties: lower index first)
-        for (int k = tid; k < K; k += kThreads) {
-            const int2 e = pairs[k];
-            pairs[k] = make_int2(~e.y, __float_as_int(yh_sigmoid(__int_as_float(e.x))));
-        }
-        __syncthreads();
         if (TRAIN) {
             if (warp < kTeam / 32) {
+                for (int k = tid; k < K; k += kTeam) {
+                    const int2 e = pairs[k];
+                    pairs[k] = make_int2(~e.y, __float_as_int(yh_sigmoid(__int_as_float(e.x))));
+                }
+                asm volatile("bar.sync 6, %0;" ::"n"(kTeam) : "memory");
                 if (!with_labels) rest_img(FastTag<false>{}, IntTag<kTeam>{});
                 else rest_img(FastTag<true>{}, IntTag<kTeam>{});
             } else {
+                yh_mbar_wait(&bar_dense, 0);  // the whole image's dense dL/dy is written: the records go on top of it
+                NTR(9);
                 do_records();
+                NTR(10);
             }
             publish_sums();
+            NT(11);
         } else {
+            for (int k = tid; k < K; k += kThreads) {
+                const int2 e = pairs[k];
+                pairs[k] = make_int2(~e.y, __float_as_int(yh_sigmoid(__int_as_float(e.x))));
+            }
+            __syncthreads();
             if (!with_labels) rest_img(FastTag<false>{}, IntTag<NTH>{});
             else rest_img(FastTag<true>{}, IntTag<NTH>{});
         }
         if (p.late_wait && img == 0 && tid == 0) yh_grid_dependency_wait();  // (see the end of the kernel)
         return;
     }
-    if (TRAIN && warp >= kTeam / 32) do_records();  // (an image with more candidates than shared memory holds: records first)
+    if (TRAIN) yh_mbar_wait(&bar_dense, 0);  // (an image with more candidates than shared memory holds: the whole CTA goes on together)
+    if (TRAIN && warp >= kTeam / 32) do_records();  // (... records first)
 
     Cand cw = ca;
     if (overflow) {  // continue in the workspace arrays

@@ -98,6 +98,36 @@ int main(int argc, char** argv) {
                                  nullptr, s.olab, s.oscore, s.pws, pws_bytes, st);
     };
     const double tb = 2.0 * floats * 4 + 48.0 * M;
+    std::vector<void*> fws(R);
+    const size_t fws_bytes = yh_train_post_workspace_bytes(N, S, S, A, C);
+    for (int i = 0; i < R; ++i) { CK(cudaMalloc(&fws[i], fws_bytes)); CK(cudaMemset(fws[i], 0, fws_bytes)); }
+    int fused_flags = 0;
+    auto fused = [&](Set& s) {
+        return yh_v2_train_post(s.y, N, S, S, A, C, anchors, 416.f, 416.f, s.gt, s.off, M, M, lam, s.dy, s.terms, s.loss, nullptr, nullptr,
+                                0.5f, 0.45f, fused_flags, MAXO, s.kidx, s.kcnt, s.obox, s.oconf, nullptr, s.olab, s.oscore, nullptr,
+                                fws[&s - &sets[0]], fws_bytes, st);
+    };
+    run("fused (stream-ordered)", tb + floats * 4, fused);
+    fused_flags = YH_STEP_OVERLAPPED;
+    run("fused (overlapped chain)", tb + floats * 4, fused);
+    fused_flags = 0;
+#ifdef YH_X_TRACE
+    {
+        for (int rep = 0; rep < 3; ++rep) { fused(sets[rep]); CK(cudaStreamSynchronize(st)); }
+        std::vector<unsigned long long> tr(4096 * 16);
+        yh_x_ntrace_copy(tr.data(), 4096 * 16);
+        const int G = N;
+        unsigned long long t0 = ~0ull; for (int b = 0; b < G; ++b) t0 = std::min(t0, tr[b * 16]);
+        const char* nm[16] = {"fused start", "copies issued", "lists arrived", "-", "B rank+decode done", "-", "-", "D pairs done", "D greedy done", "records start", "records done", "sums published", "-", "E emit done", "-", "-"};
+        for (int sl = 0; sl < 14; ++sl) {
+            if (nm[sl][0] == '-') continue;
+            std::vector<double> v; for (int b = 0; b < G; ++b) if (tr[b * 16 + sl] >= t0) v.push_back((double)(tr[b * 16 + sl] - t0));
+            if (v.empty()) continue;
+            std::sort(v.begin(), v.end());
+            printf("  fused %-20s n=%3zu min %6.0f  p10 %6.0f  med %6.0f  p90 %6.0f  max %6.0f ns\n", nm[sl], v.size(), v[0], v[v.size() / 10], v[v.size() / 2], v[v.size() * 9 / 10], v.back());
+        }
+    }
+#endif
     run("train", tb, train);
     run("post", 1.0 * floats * 4, post);
     run("train+post", tb + floats * 4, [&](Set& s) { int rc = train(s); return rc ? rc : post(s); });
