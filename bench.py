@@ -822,7 +822,14 @@ def main():
         roofline["frac_of_fused_minimum"] = gbs(fused_min, dom_ms) / peak
         roofline["step"]["fused_minimum_bytes"] = fused_min
         roofline["step"]["frac_of_fused_minimum"] = gbs(fused_min, ms / K) / peak
-    roofline["traffic"], roofline["traffic_source"] = measured_traffic()
+    if fused and args.workload == "headline" and B == WORKLOADS["headline"]["batch"]:
+        roofline["traffic"], roofline["traffic_source"] = measured_traffic()
+    else:  # (the capture under profiles/ is of the fused kernel on the headline batch)
+        roofline["traffic"], roofline["traffic_source"] = None, "no ncu --set full capture of this workload's dominant kernel under profiles/"
+    if fused:
+        roofline["note"] = ("frac and step.frac count SURVEY 8(d)'s bytes for train head + post-process (3P per image); the fused "
+                            "kernel reads y once (2P), so on that figure a step can exceed 1.0 of the HBM peak -- "
+                            "frac_of_fused_minimum is the fraction on the bytes it really moves")
 
     # ---- e2e: host buffers in, host buffers out
     e2e = None
