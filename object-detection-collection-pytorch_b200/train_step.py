@@ -180,11 +180,15 @@ def check(world, rank, dev):
     loss1 = model.get_loss_compact(x_all.to(dev), targets.records_to_tensor(case.rec, dev), torch.from_numpy(case.gt_off).to(dev))
     loss1.backward()
     opt.step()
+    # (one step moves a parameter by ~1e-6 while its own fp32 spacing is ~1e-8: a gradient that differs in its last
+    #  bits -- cuDNN sums a batch of 4 and a batch of 8 in different orders -- may round the new value one ulp
+    #  apart, which is no difference of the update; two ulps of the tensor's largest value are not counted)
     worst = 0.0
     for k, v in model.state_dict().items():
         d = (sharded[k] - v).abs().max().item()
         upd = (v - state0[k]).abs().max().item()
-        worst = max(worst, d / max(upd, 1e-12))
+        slack = 2.0 * torch.finfo(v.dtype).eps * v.abs().max().item() if v.is_floating_point() else 0.0
+        worst = max(worst, max(d - slack, 0.0) / max(upd, 1e-12))
     ok = worst < 1e-3 and abs(total.item() - loss1.item()) <= 1e-5 * abs(loss1.item())
     return dict(check="cfg4 sharded step == whole-batch step", world=world, loss_sharded=total.item(),
                 loss_whole=loss1.item(), worst_param_diff_over_update=worst, ok=bool(ok))
