@@ -51,30 +51,51 @@ __device__ __forceinline__ void yh_finalize_warp(const YhFinalParams& f, int lan
         const int slot = (par * YH_MAX_RANKS + f.rank) * kYhXchSlotWords;
         if (lane < 14)
             for (int q = 0; q < f.world; ++q) yh_st_sys(f.peer[q] + slot + lane, word);
-        // every rank's slot in this rank's buffer (bounded: a rank that never arrives turns the loss into NaN
-        // after 4 s instead of hanging the device)
+        // every rank's slot in this rank's buffer: the 14 * world words are polled by all lanes AT ONCE (word w on lane
+        // w mod 32) -- one local round trip once the last rank's words are in, not one per rank -- and handed over
+        // through shared memory; bounded: a rank that never arrives turns the loss into NaN after 4 s instead of
+        // hanging the device
+        __shared__ unsigned s_pay[YH_MAX_RANKS * 14];
+        constexpr int kMaxW = (14 * YH_MAX_RANKS + 31) / 32;
+        const int nw = 14 * f.world;
+        const unsigned long long* base = mine + (size_t)par * YH_MAX_RANKS * kYhXchSlotWords;
+        unsigned long long wv[kMaxW];
+#pragma unroll
+        for (int i = 0; i < kMaxW; ++i) {
+            const int w = lane + 32 * i;
+            wv[i] = w < nw ? yh_ld_sys(base + (w / 14) * kYhXchSlotWords + (w % 14)) : ((unsigned long long)seq32 << 32);
+        }
         bool ok = true;
-        unsigned long long tot = 0ull;
         const unsigned long long t0 = yh_globaltimer();
-        for (int r = 0; r < f.world; ++r) {
-            unsigned payload = 0u;
-            if (lane < 14) {
-                const unsigned long long* src = mine + (par * YH_MAX_RANKS + r) * kYhXchSlotWords + lane;
-                unsigned long long w = yh_ld_sys(src);
-                while ((unsigned)(w >> 32) != seq32) {
-                    if (yh_globaltimer() - t0 > 4000000000ull) { ok = false; break; }
-                    w = yh_ld_sys(src);
+        for (;;) {
+            bool all = true;
+#pragma unroll
+            for (int i = 0; i < kMaxW; ++i) {
+                const int w = lane + 32 * i;
+                if (w < nw && (unsigned)(wv[i] >> 32) != seq32) {
+                    wv[i] = yh_ld_sys(base + (w / 14) * kYhXchSlotWords + (w % 14));
+                    all = all && (unsigned)(wv[i] >> 32) == seq32;
                 }
-                payload = (unsigned)w;
             }
-            // rank r's value (lane >> 1) = hi:lo, assembled on the even lane of each pair; summed in rank order
-            const unsigned hi = __shfl_down_sync(0xffffffffu, payload, 1);
-            const unsigned long long v = ((unsigned long long)hi << 32) | payload;
-            tot = (lane >> 1) == 6 ? (tot | v) : tot + v;
+            if (all) break;
+            if (yh_globaltimer() - t0 > 4000000000ull) { ok = false; break; }
+        }
+#pragma unroll
+        for (int i = 0; i < kMaxW; ++i) {
+            const int w = lane + 32 * i;
+            if (w < nw) s_pay[w] = (unsigned)wv[i];
+        }
+        __syncwarp();
+        // value v (lanes 0..6) = sum over the ranks, in rank order, of hi:lo (the flags: or)
+        unsigned long long tot = 0ull;
+        if (lane < 7) {
+            for (int r = 0; r < f.world; ++r) {
+                const unsigned long long v = ((unsigned long long)s_pay[r * 14 + 2 * lane + 1] << 32) | s_pay[r * 14 + 2 * lane];
+                tot = lane == 6 ? (tot | v) : tot + v;
+            }
         }
         lost = !__all_sync(0xffffffffu, ok);
-        // value q sits on lane 2q: bring it to lane q
-        a = __shfl_sync(0xffffffffu, tot, (2 * lane) & 31);
+        a = tot;
         if (lane == 0) yh_st_sys(mine + kYhXchSeqWord, seq);
     }
     unsigned long long v[7];
