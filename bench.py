@@ -834,7 +834,7 @@ def main():
     # ---- e2e: host buffers in, host buffers out
     e2e = None
     if not args.no_e2e:
-        ke = args.e2e_steps or max(20, min(K, 400))
+        ke = args.e2e_steps or max(100, min(K, 400))  # (its own step count, stated in the line: 20 steps = 8 ms of wall clock)
         pipe = HostHeadPipeline(B, case.s_h, case.s_w, case.a, case.c, img_hw=(case.height, case.width),
                                 anchors=case.anchors, lambdas=lam, conf_thre=CONF_THRE, iou_thre=IOU_THRE,
                                 max_out=MAX_OUT, max_boxes=m_local, depth=3, device=dev,
@@ -858,27 +858,37 @@ def main():
             return last
 
         t0 = pipe._ticket
-        run_e2e(max(3, pipe.depth))
+        # warm-up: one untimed repetition -- the first ~100 steps after the device-resident part run up to 40 % slower
+        # (measured: 0.59, 0.44, 0.41 ms per step over three consecutive repetitions; host-side caches and the PCIe
+        # link leaving its idle state), which a short run would mistake for the pipeline's rate
+        run_e2e(max(ke, pipe.depth))
         torch.cuda.synchronize()
-        barrier()
-        t0 = pipe._ticket
-        tic = time.perf_counter()
-        res = run_e2e(ke)
-        torch.cuda.synchronize()
-        toc = time.perf_counter()
-        e2e_s = toc - tic
-        if dist is not None:
-            t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
+        # three repetitions of `ke` steps (wall clock between device syncs, max over ranks each); reported: the median
+        e2e_runs = []
+        for _ in range(3):
+            barrier()
+            t0 = pipe._ticket
+            tic = time.perf_counter()
+            res = run_e2e(ke)
+            torch.cuda.synchronize()
+            toc = time.perf_counter()
+            e2e_s = toc - tic
+            if dist is not None:
+                t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                e2e_s = float(t.item())
+            e2e_runs.append(e2e_s)
+        e2e_s = sorted(e2e_runs)[1]
         # (the pipeline runs without the exchange: its loss is this rank's share, 1 / world of the reduced one --
         #  every rank holds the same shard here)
         want_loss = loss_value / world if xch is not None else loss_value
         assert abs(float(res["loss"]) - want_loss) <= 1e-5 * abs(want_loss), (float(res["loss"]), want_loss)
         e2e = {"value": images * ke / e2e_s, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes(m_local),
                "d2h_bytes_per_step": pipe.d2h_bytes(), "steps": ke, "ms_per_step": 1e3 * e2e_s / ke,
+               "repeats_ms_per_step": [1e3 * t_ / ke for t_ in e2e_runs],
                "path": "HostHeadPipeline: pinned host y+GT -> H2D -> yh_v2_train_post (loss + dL/dy + kept boxes) -> "
-                       "D2H of loss, terms and kept boxes%s; 3 slots; the head tensor goes up in two halves on two H2D streams, kernels and D2H on their own streams"
+                       "D2H of loss, terms and kept boxes%s; 3 slots; the head tensor goes up in two halves on two H2D streams, kernels and D2H on their own streams; "
+                       "one untimed repetition, then the median of three"
                        % (" and dL/dy" if args.e2e_return_dy else " (dL/dy is computed every step and stays on the device)")}
 
     collective = None
