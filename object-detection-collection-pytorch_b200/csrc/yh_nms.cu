@@ -341,7 +341,7 @@ __device__ __forceinline__ bool suppresses_dense(const float4& bi, float ai, con
 //     image's NMS (rank, decode, pair tests, greedy order, class pick, emit: the lean path below on a 256-thread team);
 //   * the CTA's six loss sums go onto the 64-bit fixed-point accumulators; yh_train_finalize_kernel follows.
 template <int TV, int TA, int TC, int MODE, int NTH, int TRAIN>
-__global__ void __launch_bounds__(NTH, NTH >= 512 ? 2 : 3) yh_nms_kernel(const NmsParams p) {
+__global__ void __launch_bounds__(NTH, NTH >= 1024 ? 1 : (NTH >= 512 ? 2 : 3)) yh_nms_kernel(const NmsParams p) {
     constexpr int kThreads = NTH, kWarps = NTH / 32;
     constexpr bool IMG = MODE == MODE_IMG;
     static_assert(!TRAIN || (MODE == MODE_IMG && NTH > kTeam), "the fused step runs on the whole-image kernel");
@@ -1355,13 +1355,28 @@ int launch(NmsParams& p, void* ws, size_t ws_bytes, void* stream, bool train = f
     // compile-time geometries for the shapes the reference uses (VOC: YOLOv2 5 anchors x 20 classes,
     // YOLOv1 B=2, C=20); anything else, and decoded-box input, runs the run-time-geometry variant
     constexpr int NTF = kThreadsFull;
+    // Images whose stage leaves room for ONE CTA per SM only (19x19x5x25: 180.5 KB) run on 1024 threads instead of
+    // 512: twice the warps for the dense pass and, in the fused step, 24 record warps instead of 8 next to the NMS
+    // team (BASELINE config 5: fused step 90.8 -> 85.7 us stream-ordered, 72.6 -> 69.0 us chained; post-process
+    // 35.9 -> 34.9 us).  Same code, same results: nothing in the kernel depends on the CTA size but its loop strides.
+    constexpr int NTB = 1024;
+    const bool one_cta = img_mode && 2 * (smem + 12 * 1024) > 227 * 1024;
     if (train) {  // the fused step (the caller checked img_mode_applies and version 2)
         // batches dense with ground truth (BASELINE config 5) run the variant whose record warps take four records at
         // a time (yh_record.cuh: same bits); the common, sparse case keeps the kernel without that code
         const bool dense_gt = (long long)p.m_local > (long long)kRec4Min * p.n;
+        if (one_cta) {
+            if (p.g.a == 5 && p.c == 20)
+                return dense_gt ? launch_variant<2, 5, 20, MODE_IMG, NTB, 2>(p, smem, stream) : launch_variant<2, 5, 20, MODE_IMG, NTB, 1>(p, smem, stream);
+            return dense_gt ? launch_variant<2, 0, 0, MODE_IMG, NTB, 2>(p, smem, stream) : launch_variant<2, 0, 0, MODE_IMG, NTB, 1>(p, smem, stream);
+        }
         if (p.g.a == 5 && p.c == 20)
             return dense_gt ? launch_variant<2, 5, 20, MODE_IMG, NTF, 2>(p, smem, stream) : launch_variant<2, 5, 20, MODE_IMG, NTF, 1>(p, smem, stream);
         return dense_gt ? launch_variant<2, 0, 0, MODE_IMG, NTF, 2>(p, smem, stream) : launch_variant<2, 0, 0, MODE_IMG, NTF, 1>(p, smem, stream);
+    }
+    if (img_mode && one_cta) {
+        if (p.g.version == 2 && p.g.a == 5 && p.c == 20) return launch_variant<2, 5, 20, MODE_IMG, NTB>(p, smem, stream);
+        return launch_variant<0, 0, 0, MODE_IMG, NTB>(p, smem, stream);
     }
     if (img_mode) {
         if (p.g.version == 2 && p.g.a == 5 && p.c == 20) return launch_variant<2, 5, 20, MODE_IMG, NTF>(p, smem, stream);
