@@ -89,12 +89,15 @@ __device__ __forceinline__ unsigned long long xt_now() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+__device__ unsigned long long g_tiletrace[4096 * 32];
+#define XTT(k, w) do { if (threadIdx.x == 0 && (k) < 10) g_tiletrace[blockIdx.x * 32 + 1 + 3 * (k) + (w)] = xt_now(); } while (0)
 #define XT_DECL unsigned long long xt_[8] = {0, 0, 0, 0, 0, 0, 0, 0}
 #define XT(slot) do { if ((threadIdx.x & 31) == 0 || threadIdx.x == kThreads - 1) xt_[slot] = xt_now(); } while (0)
 #define XT_FLUSH do { if (threadIdx.x == 0) for (int i_ = 0; i_ < 8; ++i_) g_xtrace[blockIdx.x * 24 + i_] = xt_[i_]; \
                       if (threadIdx.x == kDense) for (int i_ = 0; i_ < 8; ++i_) g_xtrace[blockIdx.x * 24 + 8 + i_] = xt_[i_]; \
                       if (threadIdx.x == kThreads - 1) for (int i_ = 0; i_ < 8; ++i_) g_xtrace[blockIdx.x * 24 + 16 + i_] = xt_[i_]; } while (0)
 #else
+#define XTT(k, w) do { } while (0)
 #define XT_DECL
 #define XT(slot) do { } while (0)
 #define XT_FLUSH
@@ -276,6 +279,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
 
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, phase ^= 1u) {
         // everything is 32-bit: train_impl checks that the tensor has < 2^31 floats
+#ifdef YH_X_TRACE
+        const int tk_ = (t - (int)blockIdx.x) / (int)gridDim.x;
+        if (threadIdx.x == 0 && tk_ == 0) { unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); g_tiletrace[blockIdx.x * 32] = sm_ + 1; }
+        XTT(tk_, 0);
+#endif
         const int c0 = t * R;
         const int nc = min(R, p.total_cells - c0);
         const int nfl = nc * cf;
@@ -622,6 +630,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
         XT(1);
         __syncthreads();  // the tile's dense dL/dy is written (and visible to the whole CTA); patches are ready
         XT(2);
+        XTT(tk_, 1);
         const int nrec = s_nrec, npatch = s_npatch;
         // (no records left over: the sums folded before the barrier are final and get published
         //  right after the patch stores, without another CTA barrier)
@@ -710,6 +719,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
             }
         }
         if (multi_tile) __syncthreads();  // the stage and the lists are rewritten by the next tile
+        XTT(tk_, 2);
     }
     XT(3);
 
@@ -734,6 +744,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) yh_train_kernel(const Tr
 #ifdef YH_X_TRACE
 extern "C" YH_API int yh_x_trace_copy(unsigned long long* host, int n) {
     return (int)cudaMemcpyFromSymbol(host, g_xtrace, (size_t)n * 8);
+}
+extern "C" YH_API int yh_x_tiletrace_copy(unsigned long long* host, int n) {
+    return (int)cudaMemcpyFromSymbol(host, g_tiletrace, (size_t)n * 8);
 }
 extern "C" YH_API int yh_x_rcycles_copy(unsigned int* host, int n) {
     return (int)cudaMemcpyFromSymbol(host, g_rcycles, (size_t)n * 4);

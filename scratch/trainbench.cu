@@ -18,6 +18,7 @@
 extern "C" int yh_x_trace_copy(unsigned long long*, int);
 extern "C" int yh_x_ntrace_copy(unsigned long long*, int);
 extern "C" int yh_x_rcycles_copy(unsigned int*, int);
+extern "C" int yh_x_tiletrace_copy(unsigned long long*, int);
 #endif
 
 int main(int argc, char** argv) {
@@ -146,6 +147,20 @@ int main(int argc, char** argv) {
     {
         CK(cudaMemset(sets[0].dy, 0, 16));
         for (int rep = 0; rep < 3; ++rep) { train(sets[rep]); CK(cudaStreamSynchronize(st)); }
+        {   // per-tile timeline of the CTAs that share SM 0..1 (multi-tile launches): start | dense pass done | records done
+            std::vector<unsigned long long> tt(4096 * 32);
+            yh_x_tiletrace_copy(tt.data(), 4096 * 32);
+            unsigned long long tmin = ~0ull;
+            for (int b = 0; b < 4096; ++b) if (tt[b * 32] && tt[b * 32 + 1]) tmin = std::min(tmin, tt[b * 32 + 1]);
+            for (int sm = 0; sm < 2; ++sm)
+                for (int b = 0; b < 4096; ++b) {
+                    if (tt[b * 32] != (unsigned long long)sm + 1) continue;
+                    printf("  sm %d cta %4d:", sm, b);
+                    for (int k = 0; k < 10 && tt[b * 32 + 1 + 3 * k]; ++k)
+                        printf("  [%5.1f %5.1f %5.1f]", (tt[b * 32 + 1 + 3 * k] - tmin) / 1e3, (tt[b * 32 + 2 + 3 * k] - tmin) / 1e3, (tt[b * 32 + 3 + 3 * k] - tmin) / 1e3);
+                    printf("\n");
+                }
+        }
         std::vector<unsigned long long> tr(4096 * 24);
         yh_x_trace_copy(tr.data(), 4096 * 24);
         int G = 0; while (G < 4095 && tr[G * 24] != 0) ++G;  // CTAs that left a trace
