@@ -199,10 +199,11 @@ YH_API int yh_v1_postprocess(const float* y, int n, int s_h, int s_w, int b, int
 
 /* ---- the fused step: train head + post-process of the SAME head tensor in ONE kernel, y read once ---------
  * yh_v2_train followed by yh_v2_postprocess reads y twice, in two kernels.  Here one CTA per image stages the
- * image in shared memory (as the post-process does) and does BOTH: the train head's dense pass as the pieces
- * land (no-object term, dL/dy written from registers), then half of the CTA processes the image's ground-truth
- * records while the other half resolves its NMS (rank, decode, pair tests, greedy order, class pick, emit); the
- * one-warp finalize kernel follows.  Decisions, dL/dy and detections are bit-identical to the two separate
+ * image in shared memory (as the post-process does) and does BOTH: as the pieces land their candidates are
+ * listed and the train head's dense pass runs over them (no-object term, dL/dy written from registers); eight
+ * warps resolve the image's NMS (rank, decode, pair tests, greedy order, class pick, emit) as soon as the list
+ * is complete while the others process the image's ground-truth records on top of the complete dense gradient;
+ * the one-warp finalize kernel follows.  Decisions, dL/dy and detections are bit-identical to the two separate
  * calls; loss and terms agree to float rounding (the partial sums are grouped by image instead of by tile).
  * Inputs the fused kernel does not cover (unaligned y or dy, images larger than the 200 KB shared-memory
  * stage, fewer than 3 classes) run the kernels of the two separate calls instead -- same results.

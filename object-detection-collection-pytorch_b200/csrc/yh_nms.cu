@@ -5,7 +5,8 @@
 // predict -> nms -> argmax chain of detect() (reference models/yolov2.py:694-731,
 // models/yolov1.py:491-534).
 //
-// One CTA (512 threads) per image, one launch for the whole batch, no sort.  Measured on B200: the
+// One CTA per image (512 threads; 1024 where an image leaves room for one CTA per SM only), one launch for the
+// whole batch, no sort.  Measured on B200: the
 // kernel is DRAM-bound while the images arrive (all CTAs are resident) and bound by instruction
 // issue afterwards (two CTAs per SM, each phase a few hundred nanoseconds), so it is organised
 // around ONE global round trip and few warp instructions:
@@ -333,12 +334,15 @@ __device__ __forceinline__ bool suppresses_dense(const float4& bi, float ai, con
 // logits are read with strided loads and only the candidates' rows are staged.
 // TRAIN != 0 (the fused step, yh_v2_train_post; whole-image mode, v2; TRAIN == 2: with the four-records-per-warp form): the CTA that holds an image in shared memory for
 // the post-process ALSO does the train head's work on it -- y is read once per step, by one kernel:
-//   * as each piece of the image lands, its warp group runs the dense pass over it: the no-object term and its
-//     gradient per objectness logit, dL/dy written with 16-byte stores straight from registers (zero elsewhere);
-//   * once the image is complete, the upper half of the CTA processes the image's ground-truth records (one warp
-//     per record, dealt by cell so that records sharing a cell accumulate in CSR order; yh_record.cuh -- the same
-//     arithmetic, the same bits as the train head) on top of the dense values, while the lower half resolves the
-//     image's NMS (rank, decode, pair tests, greedy order, class pick, emit: the lean path below on a 256-thread team);
+//   * as each piece of the image lands, its warp group first lists the piece's NMS candidates (arriving on bar_list),
+//     then runs the dense pass over it: the no-object term and its gradient per objectness logit, dL/dy written with
+//     16-byte stores straight from registers (zero elsewhere), and arrives on bar_dense;
+//   * the first 256 threads -- their pieces land first -- resolve the image's NMS as soon as the list is complete
+//     (keys, rank, decode, pair tests, greedy order, class pick, emit: the lean path below on a 256-thread team),
+//     i.e. while the last pieces' gradients are still being written; the other warps wait for the complete dense
+//     gradient (bar_dense) and process the image's ground-truth records on top of it (one warp per record, or four
+//     records per warp, dealt by cell so that records sharing a cell accumulate in CSR order; yh_record.cuh -- the
+//     same arithmetic, the same bits as the train head);
 //   * the CTA's six loss sums go onto the 64-bit fixed-point accumulators; yh_train_finalize_kernel follows.
 template <int TV, int TA, int TC, int MODE, int NTH, int TRAIN>
 __global__ void __launch_bounds__(NTH, NTH >= 1024 ? 1 : (NTH >= 512 ? 2 : 3)) yh_nms_kernel(const NmsParams p) {
