@@ -57,6 +57,9 @@ def parse_args():
     ap.add_argument("--unfused", action="store_true",
                     help="a step = the two separate calls (yh_v2_train + yh_v2_postprocess: 3 launches, y read twice) "
                          "instead of the fused step (yh_v2_train_post: one kernel per image batch + finalize, y read once)")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: the workload's batch is the GLOBAL batch, every rank takes batch / N images "
+                         "(default: weak scaling, the batch per GPU is fixed)")
     ap.add_argument("--no-collective", action="store_true",
                     help="N > 1: leave the in-kernel peer-memory reduction of the loss terms out of the steps")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 400)")
@@ -562,6 +565,8 @@ def main():
 
     K, W, R = args.steps, max(args.warmup, 3), args.sets
     B = args.batch or WORKLOADS[args.workload]["batch"]
+    if args.strong:
+        B = max(1, B // world)
     lam = synthetic.DEFAULT_LAMBDAS
     case = WORKLOADS[args.workload]["case"](B)
     conf_thre, iou_thre = CONF_THRE, IOU_THRE
@@ -915,9 +920,9 @@ def main():
             "ms_per_step": ms / K, "repeats": n_regions,
             "region_ms": {"median": ms, "min": region_ms[0], "max": region_ms[-1],
                           "what": "device time of the K-step region, max over ranks, per repetition"},
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.workload, B),
+            "config": dict(workload_config(args.workload, B), **({"global_batch": B * world} if args.strong else {})),
             "run": run_description(R, set_bytes + (sets[0]["res"].get("_ws").numel() if fused else 0), fused, collective),
             "clocks": sampler.summary(window), "e2e": e2e, "gpu_launches": (2 if fused else 3) * K,
             "roofline": roofline, "cpu_baseline": cpu, "loss": loss_value, "terms": terms_value,
