@@ -1083,6 +1083,22 @@ __global__ void __launch_bounds__(NTH, NTH >= 1024 ? 1 : (NTH >= 512 ? 2 : 3)) y
         // group's first lane decodes the box into the ranked slot.
         const int sub8 = tid & 7;
         bool rows_in = false;
+        // Images that overflowed the shared-memory lists keep their candidates in the workspace -- but the 12 KB of the
+        // shared lists are idle then, and they hold a 64-bit sort key (order-preserving image of the confidence |
+        // complemented predictor index, as in the lean path) for up to 1536 candidates: the K^2 comparisons of the
+        // ranking read those with 16-byte shared loads instead of two global loads each (K = 420: 22 -> 3 us).
+        constexpr int kKeyMax = kSmemCand * (16 + 4 * 8) / 8;  // cand_bytes(kSmemCand) / 8
+        unsigned long long* const skeys = reinterpret_cast<unsigned long long*>(smem_raw + p.stage_bytes);
+        const bool keyed = !FAST && overflow && K <= kKeyMax;
+        auto sort_key = [](float c, int idx) -> unsigned long long {
+            const unsigned u = __float_as_uint(c + 0.0f);  // (-0 -> +0: equal confidences must give equal high words)
+            const unsigned o = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+            return ((unsigned long long)o << 32) | (unsigned)~idx;
+        };
+        if (keyed) {
+            for (int k = tid; k < K; k += kThreads) skeys[k] = sort_key(ca.u_conf[k], ca.u_idx[k]);
+            __syncthreads();
+        }
         for (int k0 = 0; k0 < K; k0 += kThreads / 8) {
             if (k0 + 4 * warp >= K) break;  // no candidate left for this warp: it stays out of the issue slots
             const int k = k0 + (tid >> 3);
@@ -1090,7 +1106,17 @@ __global__ void __launch_bounds__(NTH, NTH >= 1024 ? 1 : (NTH >= 512 ? 2 : 3)) y
             const float ck = on ? ca.u_conf[k] : 0.f;
             const int ik = on ? ca.u_idx[k] : 0;
             int rank = 0;
-            if (on) {
+            if (on && keyed) {
+                const unsigned long long kk = skeys[k];
+                const ulonglong2* k2 = reinterpret_cast<const ulonglong2*>(skeys);
+                const int K2 = K >> 1;
+                for (int q = sub8; q < K2; q += 8) {  // (keys are unique: the predictor index is part of them)
+                    const ulonglong2 kj = k2[q];
+                    rank += kj.x > kk ? 1 : 0;
+                    rank += kj.y > kk ? 1 : 0;
+                }
+                if (sub8 == 0 && (K & 1)) rank += skeys[K - 1] > kk ? 1 : 0;
+            } else if (on) {
                 for (int j = sub8; j < K; j += 8) {
                     const float cj = ca.u_conf[j];
                     rank += (cj > ck || (cj == ck && ca.u_idx[j] < ik)) ? 1 : 0;
@@ -1160,21 +1186,41 @@ __global__ void __launch_bounds__(NTH, NTH >= 1024 ? 1 : (NTH >= 512 ? 2 : 3)) y
         for (int base = 0; base < K; base += kTile) {
             const int tn = min(kTile, K - base);
             const int W = (tn + 31) >> 5;
-            // (1) against the boxes kept in earlier tiles
-            for (int jp = tid; jp < kTile; jp += kThreads) {  // (whole warps: kTile and kThreads are multiples of 32)
-                bool dead = false;
-                if (jp < tn && base > 0) {
-                    const float4 bj = ca.s_box[base + jp];
-                    const float aj = ca.s_area[base + jp];
-                    const int lj = use_lab ? ca.s_lab[base + jp] : 0;
-                    const int kept = s_kept;
-                    for (int q = 0; q < kept; ++q) {
-                        const int i = ca.keep[q];
-                        if (suppresses_dense(ca.s_box[i], ca.s_area[i], bj, aj, thr, thr_pos) && (!use_lab || ca.s_lab[i] == lj)) { dead = true; break; }
-                    }
+            // (1) against the boxes kept in earlier tiles: one warp per candidate, the lanes split the kept boxes
+            //     (a serial walk per thread was the longest phase of an image with several tiles)
+            if (tid < kTileWords) rem0[tid] = 0u;
+            // the tile's ranked boxes, areas and labels -> the idle shared lists (read K/2 times each below)
+            float4* const t_box = reinterpret_cast<float4*>(smem_raw + p.stage_bytes);
+            float* const t_area = reinterpret_cast<float*>(t_box + kTile);
+            int32_t* const t_lab = reinterpret_cast<int32_t*>(t_area + kTile);
+            const bool tiled = !FAST && overflow;  // (the shared lists are idle: everything lives in the workspace)
+            if (tiled) {
+                __syncthreads();  // (the sort keys / the previous tile's copy are no longer read)
+                for (int j = tid; j < tn; j += kThreads) {
+                    t_box[j] = ca.s_box[base + j];
+                    t_area[j] = ca.s_area[base + j];
+                    if (use_lab) t_lab[j] = ca.s_lab[base + j];
                 }
-                const unsigned bal = __ballot_sync(0xffffffffu, dead);
-                if (lane == 0) rem0[jp >> 5] = bal;
+            }
+            __syncthreads();
+            if (base > 0) {
+                const int kept = s_kept;
+                for (int jp = warp; jp < tn; jp += kWarps) {
+                    const float4 bj = tiled ? t_box[jp] : ca.s_box[base + jp];
+                    const float aj = tiled ? t_area[jp] : ca.s_area[base + jp];
+                    const int lj = use_lab ? (tiled ? t_lab[jp] : ca.s_lab[base + jp]) : 0;
+                    bool hit = false;
+                    for (int q0 = 0; q0 < kept && !hit; q0 += 32) {
+                        const int q = q0 + lane;
+                        bool bit = false;
+                        if (q < kept) {
+                            const int i = ca.keep[q];
+                            bit = suppresses_dense(ca.s_box[i], ca.s_area[i], bj, aj, thr, thr_pos) && (!use_lab || ca.s_lab[i] == lj);
+                        }
+                        hit = __any_sync(0xffffffffu, bit);
+                    }
+                    if (hit && lane == 0) atomicOr(&rem0[jp >> 5], 1u << (jp & 31));
+                }
             }
             __syncthreads();
             // (2) intra-tile mask, by column: word (j, w) = candidates i in [32w, 32w+32), ranked before j,
@@ -1182,16 +1228,17 @@ __global__ void __launch_bounds__(NTH, NTH >= 1024 ? 1 : (NTH >= 512 ? 2 : 3)) y
             //     the words up to j's own (two at a time: the tests are independent)
             if (base == 0) NT(5);
             for (int j = warp; j < tn; j += kWarps) {
-                const float4 bj = ca.s_box[base + j];
-                const float aj = ca.s_area[base + j];
-                const int lj = use_lab ? ca.s_lab[base + j] : 0;
+                const float4 bj = tiled ? t_box[j] : ca.s_box[base + j];
+                const float aj = tiled ? t_area[j] : ca.s_area[base + j];
+                const int lj = use_lab ? (tiled ? t_lab[j] : ca.s_lab[base + j]) : 0;
     #pragma unroll 2
                 for (int w = 0; w <= (j >> 5); ++w) {
                     const int i = w * 32 + lane;
                     bool bit = false;
                     if (i < j) {
-                        bit = suppresses_dense(ca.s_box[base + i], ca.s_area[base + i], bj, aj, thr, thr_pos);
-                        if (use_lab) bit = bit && lj == ca.s_lab[base + i];
+                        bit = tiled ? suppresses_dense(t_box[i], t_area[i], bj, aj, thr, thr_pos)
+                                    : suppresses_dense(ca.s_box[base + i], ca.s_area[base + i], bj, aj, thr, thr_pos);
+                        if (use_lab) bit = bit && lj == (tiled ? t_lab[i] : ca.s_lab[base + i]);
                     }
                     const unsigned m = __ballot_sync(0xffffffffu, bit);
                     if (lane == 0) mask[j * kTileWords + w] = m;
