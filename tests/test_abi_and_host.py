@@ -29,6 +29,13 @@ def test_header_declares_the_expected_entry_points():
     assert sorted(_lib.SIGNATURES) == syms  # the ctypes binding mirrors the header one to one
 
 
+def test_integration_doc_names_every_entry_point():
+    """INTEGRATION.md maps every exported entry point to the reference interface it replaces."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [name for name in header_symbols() if name not in doc]
+    assert not missing, missing
+
+
 def test_library_loads_and_exports_every_declared_symbol():
     lib = _lib.load()
     raw = C.CDLL(_lib.LIB_PATH)
