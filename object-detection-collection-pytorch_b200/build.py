@@ -47,19 +47,33 @@ def needs_build():
 
 
 def build(force=False, verbose=False, extra=(), out=None):
-    """`out`: build an experimental variant (extra -D flags) next to the product library."""
+    """`out`: build an experimental variant (extra -D flags) next to the product library.
+    The translation units are compiled in parallel (one nvcc -c each), then linked into the shared library."""
     if out is None and not force and not needs_build():
         return LIB_PATH
-    cmd = [find_nvcc(), "-shared", *NVCC_FLAGS, *extra, "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-           "-o", out or LIB_PATH, *sources()]
-    if verbose:
-        print(" ".join(cmd), flush=True)
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose and (res.stdout or res.stderr):
-        print(res.stdout + res.stderr)
-    return out or LIB_PATH
+    import concurrent.futures
+    import tempfile
+    nvcc = find_nvcc()
+    target = out or LIB_PATH
+    common = [*NVCC_FLAGS, *extra, "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+    log = []
+
+    def run(cmd):
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        log.append(res.stdout + res.stderr)
+
+    with tempfile.TemporaryDirectory(prefix="yh_build_") as tmp:
+        objs = [os.path.join(tmp, os.path.basename(src)[:-3] + ".o") for src in sources()]
+        with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+            list(pool.map(lambda so: run([nvcc, "-c", *common, "-o", so[1], so[0]]), zip(sources(), objs)))
+        run([nvcc, "-shared", *NVCC_FLAGS, "-o", target, *objs])
+    if verbose and any(log):
+        print("".join(log))
+    return target
 
 
 if __name__ == "__main__":
