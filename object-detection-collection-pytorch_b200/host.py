@@ -22,10 +22,24 @@ import torch
 from . import ops
 
 
+def _write_combined_pinned(nbytes):
+    """`nbytes` of write-combined pinned host memory as a uint8 tensor (cudaHostAlloc, WRITE_COMBINED | PORTABLE).
+    The device reads such memory over PCIe without snooping the CPU caches -- what helps when several GPUs pull
+    from one host at once -- and the CPU must only ever WRITE to it (reads are uncached).  Freed at process exit."""
+    import ctypes as C
+    rt = C.CDLL("libcudart.so.12")
+    ptr = C.c_void_p()
+    rc = rt.cudaHostAlloc(C.byref(ptr), C.c_size_t(nbytes), C.c_uint(0x04 | 0x01))
+    if rc != 0 or not ptr.value:
+        raise RuntimeError("cudaHostAlloc(write-combined, %d bytes) failed: %d" % (nbytes, rc))
+    buf = (C.c_uint8 * nbytes).from_address(ptr.value)
+    return torch.frombuffer(buf, dtype=torch.uint8)
+
+
 class HostHeadPipeline:
     def __init__(self, n, s_h, s_w, a, c, *, version=2, img_hw, anchors=None, lambdas, conf_thre=0.5,
                  iou_thre=0.45, max_out=128, max_boxes=None, depth=3, device=None, return_dy=True,
-                 compute_dy=True, class_aware=False):
+                 compute_dy=True, class_aware=False, write_combined=None):
         """`compute_dy`: the train head also produces dL/dy (the backward of get_loss).  `return_dy`: that
         gradient is copied back to host memory as well; with return_dy=False it stays in the slot's device
         buffer (`device_dy(ticket)`), which is where a caller whose backbone runs on the GPU consumes it --
@@ -38,6 +52,9 @@ class HostHeadPipeline:
         self.conf_thre, self.iou_thre, self.max_out = conf_thre, iou_thre, max_out
         self.class_aware = class_aware
         self.compute_dy = bool(compute_dy or return_dy)
+        # the head tensor's staging buffers in write-combined pinned memory (opt-in: YH_PINNED_WC=1 or the argument)
+        import os
+        self.write_combined = bool(int(os.environ.get("YH_PINNED_WC", "0"))) if write_combined is None else bool(write_combined)
         self.return_dy = return_dy
         self.depth = depth
         self.max_boxes = int(max_boxes if max_boxes is not None else 128 * n)
@@ -83,7 +100,9 @@ class HostHeadPipeline:
                 y=torch.empty(shape, dtype=f32, device=d), dy=torch.empty(shape, dtype=f32, device=d),
                 d_in=d_in, d_out=d_out, h_in=h_in, h_out=h_out,
                 gt=di["gt"], off=di["off"], loss=do["loss"], terms=do["terms"],
-                h_y=torch.empty(shape, dtype=f32).pin_memory(), h_gt=hi["gt"], h_off=hi["off"],
+                h_y=(_write_combined_pinned(4 * int(np.prod(shape))).view(f32).view(shape) if self.write_combined
+                     else torch.empty(shape, dtype=f32).pin_memory()),
+                h_gt=hi["gt"], h_off=hi["off"],
                 h_dy=torch.empty(shape, dtype=f32).pin_memory() if return_dy else None,
                 h=ho,
                 ev_in=torch.cuda.Event(), ev_in2=torch.cuda.Event(), ev_run=torch.cuda.Event(), ev_post=torch.cuda.Event(), ev_out=torch.cuda.Event(),
