@@ -293,3 +293,28 @@ def test_yolov2_net_is_the_reference_network():
     x = torch.rand(1, 416, 416, 3, generator=torch.Generator().manual_seed(3)) * 255.0
     with torch.no_grad():
         assert torch.equal(ours(x), theirs(x))
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` runs on the host cores alone (no GPU): one JSON line with the base contract's keys,
+    `impl: reference`, a cpu_baseline describing the run and an e2e object without copies; under a launcher only
+    rank 0 prints."""
+    import json
+    import subprocess
+    from oracle import refharness
+    if not refharness.available():
+        pytest.skip("no reference sources (neither /root/reference nor the staged oracle/_ref)")
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-sample", "2"]
+    res = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, res.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "yolo_head_images_per_sec" and d["unit"] == "images/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("yolov2_head_13x13x5_c20_b256")
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    res = subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, timeout=600, env=env)
+    assert res.returncode == 0 and not res.stdout.strip()  # (the other ranks exit 0 without work)
