@@ -264,6 +264,15 @@ def main():
         np.savez_compressed(os.path.join(HERE, "v1_detect.npz"), **r)
         print("v1_detect", len(r["bbox"]), "boxes")
         return
+    if "--only-dense" in sys.argv:
+        # --- v2 loss/grad on images DENSE with ground truth (30-40 boxes per image + same-cell collisions): what the
+        # fused step's four-records-per-warp form and the train head's record paths see on BASELINE config 5
+        torch.set_num_threads(1)
+        c = synthetic.with_collisions(synthetic.make_case("g_v2_dense", 2, 2, 13, 13, 5, 20, 416, 416, seed=15, k_lo=30, k_hi=40), 12, seed=3)
+        r = run_loss(c, lam)
+        np.savez_compressed(os.path.join(HERE, "v2_loss_dense.npz"), **case_arrays(c), **r)
+        print("v2_loss_dense", c.m, r["loss"])
+        return
     r = run_v1_detect(401)
     np.savez_compressed(os.path.join(HERE, "v1_detect.npz"), **r)
     np.savez_compressed(os.path.join(HERE, "evaluate.npz"), **run_evaluate(301))
@@ -277,6 +286,12 @@ def main():
     r = run_loss(c, lam)
     np.savez_compressed(os.path.join(HERE, "v2_loss_small.npz"), **case_arrays(c), **r)
     print("v2_loss_small", c.m, r["loss"])
+
+    # --- v2, images dense with ground truth (see --only-dense)
+    c = synthetic.with_collisions(synthetic.make_case("g_v2_dense", 2, 2, 13, 13, 5, 20, 416, 416, seed=15, k_lo=30, k_hi=40), 12, seed=3)
+    r = run_loss(c, lam)
+    np.savez_compressed(os.path.join(HERE, "v2_loss_dense.npz"), **case_arrays(c), **r)
+    print("v2_loss_dense", c.m, r["loss"])
 
     # --- v2 non-square grid (validation path feeds native-size images, SURVEY B-12)
     c = synthetic.make_case("g_v2_nonsq", 2, 2, 10, 13, 5, 20, 320, 416, seed=12, k_hi=4)

@@ -235,3 +235,20 @@ def test_fused_overlapped_chain_with_different_data_per_step(cuda_device):
             for i in range(R):
                 assert_same_train(want[i]["train"], outs[i]["train"])
                 assert_same_post(want[i]["post"], outs[i]["post"])
+
+
+def test_fused_step_dense_images_match_the_reference_gradient_golden(cuda_device):
+    """Two images with 40+ boxes each (tests/golden/v2_loss_dense.npz: loss and autograd gradient of the REFERENCE):
+    the fused step processes them four records per warp -- against the reference itself, not the oracle."""
+    case, z = load_golden("v2_loss_dense.npz")
+    assert case.m > 8 * case.n  # (the four-per-warp variant is the one that launches)
+    r = fused(case, cuda_device, 0.5, 0.45, want_cls_spec=False)["train"]
+    assert abs(float(r["loss"]) - float(z["loss"])) <= TOL * abs(float(z["loss"]))
+    dy = r["dy"].cpu().numpy()
+    assert rel_err(dy, z["dy"]) <= TOL
+    assert np.array_equal(dy != 0, z["dy"] != 0), "gradient sparsity pattern differs"
+    assert np.allclose(dy, z["dy"], rtol=1e-3, atol=1e-6 * np.abs(z["dy"]).max())
+    resp = r["resp"].cpu().numpy()
+    for j in np.nonzero(resp != z["resp"])[0]:  # (only exact IoU ties may differ)
+        top2 = np.sort(z["iou_all"][j])[-2:]
+        assert top2[1] - top2[0] <= 4 * np.spacing(np.float32(top2[1])), int(j)

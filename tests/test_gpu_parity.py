@@ -19,7 +19,7 @@ from oracle import yolo_head_oracle as O
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
-LOSS_FILES = ["v2_loss_small.npz", "v2_loss_nonsquare.npz", "v1_loss_small.npz", "v1_loss_b3c7.npz"]
+LOSS_FILES = ["v2_loss_small.npz", "v2_loss_nonsquare.npz", "v1_loss_small.npz", "v1_loss_b3c7.npz", "v2_loss_dense.npz"]
 
 
 def run_train(case, lambdas, dev, m_global=None, want_grad=True):

@@ -8,7 +8,7 @@ import torch
 from conftest import golden_lambdas, load_golden, rel_err
 from oracle import yolo_head_oracle as O
 
-LOSS_FILES = ["v2_loss_small.npz", "v2_loss_nonsquare.npz", "v1_loss_small.npz", "v1_loss_b3c7.npz"]
+LOSS_FILES = ["v2_loss_small.npz", "v2_loss_nonsquare.npz", "v1_loss_small.npz", "v1_loss_b3c7.npz", "v2_loss_dense.npz"]
 TOL = 1e-5  # north-star: loss and gradients within 1e-5 relative in fp32
 
 
